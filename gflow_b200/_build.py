@@ -1,0 +1,90 @@
+"""In-tree build of libgflow_b200.so (hand-written CUDA for sm_100a, plain nvcc, no torch headers).
+
+The library is the C-ABI drop-in boundary declared in include/gflow_b200.h.  It is built
+into gflow_b200/_lib/ so it travels with the repository snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+CSRC = os.path.join(_PKG, "csrc")
+INCLUDE = os.path.join(_ROOT, "include")
+LIB_DIR = os.path.join(_PKG, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "libgflow_b200.so")
+_STAMP = os.path.join(LIB_DIR, "build.stamp")
+
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC]
+# geometry.cu must not fuse multiply-adds: its float32 results are bit-compared with the oracle
+PER_FILE_FLAGS = {"geometry.cu": ["-fmad=false"], "binning.cu": ["-fmad=false"]}
+SOURCES = ["capi.cu", "geometry.cu", "binning.cu", "blend.cu"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libgflow_b200.so")
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "gflow_b200.h"), __file__]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH) or not os.path.exists(_STAMP):
+        return True
+    with open(_STAMP) as fh:
+        return fh.read().strip() != _fingerprint()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ for sm_100a and link libgflow_b200.so."""
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    env = dict(os.environ)
+    if os.path.exists("/usr/bin/g++"):
+        host = ["-ccbin", "/usr/bin/g++"]
+    else:
+        host = []
+    objs = []
+    log = []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH_FLAGS, *COMMON_FLAGS, *host, *PER_FILE_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        log.append("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + log[-1])
+        objs.append(obj)
+    cmd = [nvcc, *ARCH_FLAGS, *host, "-shared", "-o", LIB_PATH, *objs]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    log.append("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + log[-1])
+    with open(os.path.join(LIB_DIR, "build.log"), "w") as fh:
+        fh.write("\n".join(log))
+    with open(_STAMP, "w") as fh:
+        fh.write(_fingerprint())
+    if verbose:
+        print("\n".join(log))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build(force="--force" in sys.argv, verbose=True))

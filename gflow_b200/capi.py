@@ -1,0 +1,70 @@
+"""ctypes binding of libgflow_b200.so (the C ABI of include/gflow_b200.h).
+
+There is no CPU or PyTorch fallback: if the CUDA library cannot be built / loaded the
+import raises, and every op raises when handed a tensor that is not on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
+
+from . import _build
+
+_lib = None
+
+# symbol -> (restype, argtypes); mirrors include/gflow_b200.h declaration by declaration
+P, I, F, L = c_void_p, c_int, c_float, c_int64
+SIGNATURES = {
+    "gfb_version": (c_int, []),
+    "gfb_build_arch": (ctypes.c_char_p, []),
+    "gfb_error_string": (ctypes.c_char_p, [I]),
+    "gfb_kernel_launch_count": (c_int64, []),
+    "gfb_project_point_fwd": (I, [P, P, P, I, I, I, F, F, P, P, P]),
+    "gfb_project_point_bwd": (I, [P, P, P, I, I, I, F, F, P, P, P, P, P]),
+    "gfb_compute_cov3d_fwd": (I, [P, P, P, I, P, P]),
+    "gfb_compute_cov3d_bwd": (I, [P, P, P, I, P, P, P, P]),
+    "gfb_ewa_project_fwd": (I, [P, P, P, P, P, I, I, I, P, P, P, P, P]),
+    "gfb_ewa_project_bwd": (I, [P, P, P, P, P, I, I, I, P, P, P, P, P, P]),
+    "gfb_compute_sh_fwd": (I, [P, P, P, I, I, I, P, P]),
+    "gfb_compute_sh_bwd": (I, [P, P, P, I, I, I, P, P, P, P]),
+    "gfb_sort_workspace_bytes": (c_size_t, [L]),
+    "gfb_sort_count": (I, [P, P, P, I, I, I, P, P, P]),
+    "gfb_sort_emit": (I, [P, P, P, P, I, I, I, P, P, L, P, P, P, P]),
+    "gfb_blend_geometry_stream_bytes": (c_size_t, [L]),
+    "gfb_blend_feature_stream_bytes": (c_size_t, [L]),
+    "gfb_blend_grad_pack_bytes": (c_size_t, [I]),
+    "gfb_blend_pack_geometry": (I, [P, P, P, P, L, P, P]),
+    "gfb_blend_pack_feature": (I, [P, I, I, I, P, L, P, P]),
+    "gfb_alpha_blending_fwd": (I, [P, P, L, P, I, I, I, F, I, I, P, P, P, P]),
+    "gfb_alpha_blending_bwd": (I, [P, P, L, P, P, I, I, I, F, I, I, P, P, P, P, P]),
+    "gfb_blend_unpack_grads": (I, [P, I, I, I, I, P, P, P, P, I, P]),
+}
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the in-tree .so is missing or stale).  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if os.environ.get("GFLOW_B200_NO_BUILD") != "1" and _build.needs_build():
+        _build.build()
+    if not os.path.exists(_build.LIB_PATH):
+        raise ImportError(f"gflow_b200: CUDA library missing at {_build.LIB_PATH}; run __graft_entry__.build()")
+    lib = ctypes.CDLL(_build.LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().gfb_error_string(rc).decode()
+        raise RuntimeError(f"gflow_b200 {what} failed: {msg} (code {rc})")

@@ -1,0 +1,250 @@
+// binning.cu -- msplat.sort_gaussian for sm_100a: tile binning + per-tile segmented sort.
+//
+// Reference interface: msplat.sort_gaussian(uv, depth, W, H, radius, tiles_touched) ->
+// (gaussian_ids_sorted (K,), tile_range (T,2)), called from
+// /root/reference/gflow/utils/render.py:52-54,138-140.
+//
+// The 3DGS lineage emits K 64-bit (tile << 32 | depth bits) keys and runs a global radix
+// sort (~6 passes over 12-byte pairs).  The result of that sort is fully determined: for
+// every tile, the Gaussians touching it ordered by (depth bits, Gaussian id).  We produce
+// exactly that order without the global sort:
+//   1. bin_count   : one thread per Gaussian, atomicAdd on its tiles' counters
+//   2. tile_scan   : exclusive scan of the T counters (single CTA), K = total
+//   3. bin_scatter : one thread per Gaussian, claims a slot in each tile's segment (the
+//                    counters of step 1 count back down) and writes the 64-bit key
+//                    (depth bits << 32 | id)
+//   4. tile_sort   : one CTA per tile sorts its segment in shared memory (bitonic network;
+//                    warp-shuffle compare-exchange for strides < 32), writes ids + range
+// K is ~3 N and segments are ~100 entries, so everything after step 1 stays in L2/SMEM.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSortThreads = 128;
+constexpr int kSortSmemKeys = 4096;  // 32 KB of 64-bit keys per CTA
+
+__device__ __forceinline__ bool gaussian_rect(const float2* __restrict__ uv, const int32_t* __restrict__ radius,
+                                              const int32_t* __restrict__ tiles_touched, int i, int gx, int gy,
+                                              int& x0, int& y0, int& x1, int& y1) {
+    const int r = radius[i];
+    if (r <= 0 || tiles_touched[i] <= 0) return false;
+    const float2 p = uv[i];
+    gfb_tile_rect(p.x, p.y, (float)r, gx, gy, x0, y0, x1, y1);
+    return (x1 > x0) && (y1 > y0);
+}
+
+__global__ void __launch_bounds__(kThreads)
+bin_count_kernel(const float2* __restrict__ uv, const int32_t* __restrict__ radius,
+                 const int32_t* __restrict__ tiles_touched, int N, int gx, int gy, int32_t* __restrict__ counts) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= N) return;
+    int x0, y0, x1, y1;
+    if (!gaussian_rect(uv, radius, tiles_touched, i, gx, gy, x0, y0, x1, y1)) return;
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) atomicAdd(counts + y * gx + x, 1);
+}
+
+// Single CTA: exclusive scan of counts[0..T) into offsets[0..T].
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const int32_t* __restrict__ counts, int T, int32_t* __restrict__ offsets) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + threadIdx.x;
+        const int c = (t < T) ? counts[t] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += n;
+            }
+            s_warp[lane] = w;  // inclusive scan of warp totals
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - c;
+        if (t < T) offsets[t] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[T] = s_carry;
+}
+
+__global__ void __launch_bounds__(kThreads)
+bin_scatter_kernel(const float2* __restrict__ uv, const float* __restrict__ depth,
+                   const int32_t* __restrict__ radius, const int32_t* __restrict__ tiles_touched, int N, int gx,
+                   int gy, const int32_t* __restrict__ offsets, int32_t* __restrict__ counts,
+                   unsigned long long* __restrict__ keys, long long K) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= N) return;
+    int x0, y0, x1, y1;
+    if (!gaussian_rect(uv, radius, tiles_touched, i, gx, gy, x0, y0, x1, y1)) return;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(depth[i]) << 32) | (unsigned int)i;
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+            const int t = y * gx + x;
+            // the phase-1 counters double as countdown cursors: slot = offset + (count-- - 1)
+            const long long pos = (long long)offsets[t] + (atomicSub(counts + t, 1) - 1);
+            if (pos >= 0 && pos < K) keys[pos] = key;  // K is the caller's copy of offsets[T]; never overrun
+        }
+}
+
+// Direction-free bitonic network: every compare-exchange puts the smaller key at the lower
+// index ("flip" first stage of each merge, then plain half-cleaners).  Because all exchanges are
+// ascending, virtual +inf keys at indices >= n never move, so pairs whose upper index is >= n
+// are skipped and no padding is stored.  `buf` may be shared or global memory; one CTA.
+__device__ void bitonic_sort_block(unsigned long long* buf, int n, int n_pad) {
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        const int half = k >> 1;
+        for (int q = threadIdx.x; q < (n_pad >> 1); q += blockDim.x) {
+            const int blk = q / half, pos = q - blk * half;
+            const int lo = blk * k + pos, hi = blk * k + (k - 1 - pos);
+            if (hi < n) {
+                const unsigned long long a = buf[lo], b = buf[hi];
+                if (a > b) {
+                    buf[lo] = b;
+                    buf[hi] = a;
+                }
+            }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int q = threadIdx.x; q < (n_pad >> 1); q += blockDim.x) {
+                const int lo = 2 * q - (q & (j - 1));
+                const int hi = lo + j;
+                if (hi < n) {
+                    const unsigned long long a = buf[lo], b = buf[hi];
+                    if (a > b) {
+                        buf[lo] = b;
+                        buf[hi] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long u64_min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long u64_max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+// Segments of <= 64 keys: one warp, element e = lane (k0) and lane + 32 (k1); the same
+// direction-free network with every compare-exchange done by warp shuffle.
+__device__ __forceinline__ void warp_sort64(unsigned long long& k0, unsigned long long& k1, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 64; k <<= 1) {
+        if (k < 64) {
+            // flip stage: partner element e ^ (k-1), same register, lane ^ (k-1)
+            const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, k0, k - 1);
+            const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, k1, k - 1);
+            const bool lower = (lane & (k >> 1)) == 0;
+            k0 = lower ? u64_min(k0, p0) : u64_max(k0, p0);
+            k1 = lower ? u64_min(k1, p1) : u64_max(k1, p1);
+        } else {
+            // k == 64: partner of e is e ^ 63 -> the other register of lane ^ 31
+            const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, k1, 31);
+            const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, k0, 31);
+            k0 = u64_min(k0, p0);
+            k1 = u64_max(k1, p1);
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, k0, j);
+            const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, k1, j);
+            const bool lower = (lane & j) == 0;
+            k0 = lower ? u64_min(k0, p0) : u64_max(k0, p0);
+            k1 = lower ? u64_min(k1, p1) : u64_max(k1, p1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+tile_sort_kernel(const int32_t* __restrict__ offsets, unsigned long long* __restrict__ keys,
+                 int32_t* __restrict__ ids_sorted, int2* __restrict__ tile_range, int T) {
+    __shared__ unsigned long long s_keys[kSortSmemKeys];
+    const int t = blockIdx.x;
+    const int start = offsets[t], end = offsets[t + 1];
+    const int n = end - start;
+    if (threadIdx.x == 0) tile_range[t] = (n > 0) ? make_int2(start, end) : make_int2(0, 0);
+    if (n <= 0) return;
+    if (n <= 64) {
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            unsigned long long k0 = (lane < n) ? keys[start + lane] : ~0ull;
+            unsigned long long k1 = (lane + 32 < n) ? keys[start + lane + 32] : ~0ull;
+            warp_sort64(k0, k1, lane);
+            if (lane < n) ids_sorted[start + lane] = (int32_t)(unsigned int)k0;
+            if (lane + 32 < n) ids_sorted[start + lane + 32] = (int32_t)(unsigned int)k1;
+        }
+        return;
+    }
+    int n_pad = 128;
+    while (n_pad < n) n_pad <<= 1;
+    // > 4096 Gaussians on one tile: same network, in place on the (L2-resident) global segment.
+    unsigned long long* buf = (n <= kSortSmemKeys) ? s_keys : (keys + start);
+    if (n <= kSortSmemKeys) {
+        for (int i = threadIdx.x; i < n; i += kSortThreads) s_keys[i] = keys[start + i];
+        __syncthreads();
+    }
+    bitonic_sort_block(buf, n, n_pad);
+    for (int i = threadIdx.x; i < n; i += kSortThreads) ids_sorted[start + i] = (int32_t)(unsigned int)buf[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t gfb_sort_workspace_bytes(int64_t K) { return K < 0 ? 0 : (size_t)K * sizeof(unsigned long long); }
+
+int gfb_sort_count(const float* uv, const int32_t* radius, const int32_t* tiles_touched, int N, int W, int H,
+                   int32_t* tile_counts, int32_t* tile_offsets, void* stream) {
+    if (N < 0 || W <= 0 || H <= 0 || !tile_counts || !tile_offsets) return GFB_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
+    GFB_TRY(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)T, st));
+    if (N > 0) {
+        if (!uv || !radius || !tiles_touched) return GFB_E_BADARG;
+        bin_count_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(reinterpret_cast<const float2*>(uv), radius,
+                                                                       tiles_touched, N, gx, gy, tile_counts);
+        GFB_CHECK_LAUNCH();
+    }
+    tile_scan_kernel<<<1, 1024, 0, st>>>(tile_counts, T, tile_offsets);
+    GFB_CHECK_LAUNCH();
+    return 0;
+}
+
+int gfb_sort_emit(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles_touched, int N,
+                  int W, int H, int32_t* tile_counts, const int32_t* tile_offsets, int64_t K, void* keys_ws,
+                  int32_t* gaussian_ids_sorted, int32_t* tile_range, void* stream) {
+    if (N < 0 || W <= 0 || H <= 0 || K < 0 || !tile_counts || !tile_offsets || !tile_range) return GFB_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
+    unsigned long long* keys = (unsigned long long*)keys_ws;
+    if (K > 0) {
+        if (!uv || !depth || !radius || !tiles_touched || !gaussian_ids_sorted || !keys) return GFB_E_BADARG;
+        bin_scatter_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(
+            reinterpret_cast<const float2*>(uv), depth, radius, tiles_touched, N, gx, gy, tile_offsets, tile_counts,
+            keys, (long long)K);
+        GFB_CHECK_LAUNCH();
+    }
+    tile_sort_kernel<<<T, kSortThreads, 0, st>>>(tile_offsets, keys, gaussian_ids_sorted,
+                                                 reinterpret_cast<int2*>(tile_range), T);
+    GFB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

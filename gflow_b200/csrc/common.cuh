@@ -1,0 +1,55 @@
+// common.cuh -- shared helpers for the sm_100a splat kernels (gflow_b200).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gflow_b200.h"
+
+#define GFB_ALPHA_MIN (1.0f / 255.0f)
+#define GFB_ALPHA_MAX 0.99f
+#define GFB_T_EPS 1e-4f
+#define GFB_COV_BLUR 0.3f
+#define GFB_FRUSTUM_CLAMP 1.3f
+
+// host-side counter of kernels launched by this library (gfb_kernel_launch_count)
+void gfb_internal_count_launch();
+
+// follows every kernel launch: error check + launch accounting
+#define GFB_CHECK_LAUNCH()                      \
+    do {                                        \
+        cudaError_t e__ = cudaGetLastError();   \
+        if (e__ != cudaSuccess) return (int)e__; \
+        gfb_internal_count_launch();            \
+    } while (0)
+
+#define GFB_TRY(expr)                            \
+    do {                                         \
+        cudaError_t e__ = (expr);                \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
+static inline int gfb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// camera-space point with the oracle's operation order: ((e0*x + e1*y) + e2*z) + e3
+// (geometry.cu is compiled with -fmad=false so no multiply-add is fused).
+__device__ __forceinline__ void gfb_cam_point(const float* __restrict__ e, float x, float y, float z, float& xc,
+                                              float& yc, float& zc) {
+    xc = ((e[0] * x + e[1] * y) + e[2] * z) + e[3];
+    yc = ((e[4] * x + e[5] * y) + e[6] * z) + e[7];
+    zc = ((e[8] * x + e[9] * y) + e[10] * z) + e[11];
+}
+
+// 3DGS getRect rule on the 16x16 tile grid.
+__device__ __forceinline__ void gfb_tile_rect(float u, float v, float r, int gx, int gy, int& x0, int& y0, int& x1,
+                                              int& y1) {
+    x0 = min(gx, max(0, (int)((u - r) / (float)GFB_TILE)));
+    y0 = min(gy, max(0, (int)((v - r) / (float)GFB_TILE)));
+    x1 = min(gx, max(0, (int)(((u + r) + (float)(GFB_TILE - 1)) / (float)GFB_TILE)));
+    y1 = min(gy, max(0, (int)(((v + r) + (float)(GFB_TILE - 1)) / (float)GFB_TILE)));
+}
+
+__device__ __forceinline__ float gfb_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

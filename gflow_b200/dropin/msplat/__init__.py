@@ -1,0 +1,26 @@
+"""Drop-in replacement for the `msplat` package, backed by gflow_b200 (hand-written sm_100a CUDA).
+
+Put ``<repo>/gflow_b200/dropin`` on PYTHONPATH (or call ``gflow_b200.install_dropin()``) and the
+unmodified GFlow sources (``import msplat`` at /root/reference/gflow/trainer.py:7 and
+/root/reference/gflow/utils/render.py:2) resolve to this module.
+"""
+import os as _os
+import sys as _sys
+
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))))
+if _ROOT not in _sys.path:
+    _sys.path.insert(0, _ROOT)
+
+from gflow_b200.ops import (  # noqa: E402,F401
+    alpha_blending,
+    compute_cov3d,
+    compute_sh,
+    ewa_project,
+    project_point,
+    rasterization,
+    sort_gaussian,
+)
+
+__all__ = ["project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "alpha_blending", "compute_sh",
+           "rasterization"]
+__version__ = "gflow_b200-1.0"

@@ -1,0 +1,432 @@
+"""Host-side mirror of the `msplat` operator surface, backed by libgflow_b200.so.
+
+Same names, positional arguments, return tuples, dtypes and error behaviour as the
+operators GFlow calls (/root/reference/gflow/utils/render.py:21-154,
+/root/reference/gflow/trainer.py:955):
+
+    project_point(xyz, intr, extr, W, H, nearest=0.2, extent=1.3) -> (uv, depth)
+    compute_cov3d(scale, rotate, visible=None)                    -> cov3d
+    ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible=None)   -> (conic, radius, tiles_touched)
+    sort_gaussian(uv, depth, W, H, radius, tiles_touched)         -> (gaussian_ids_sorted, tile_range)
+    alpha_blending(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range, bg, W, H, ndc=None)
+                                                                  -> feature_map (C,H,W)
+    compute_sh(shs, dirs, visible=None)                           -> (N,C)
+    rasterization(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg) -> (C,H,W)
+
+Each differentiable op is a torch.autograd.Function whose forward / backward call the C ABI
+with raw device pointers on the current CUDA stream.  PyTorch is plumbing only (device
+memory, streams, autograd graph).  There is no CPU path: CPU tensors raise RuntimeError.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import capi
+
+_lib = capi.load()
+TILE = 16
+
+
+# --------------------------------------------------------------------------- helpers
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _prep(t: torch.Tensor, name: str, dtype=torch.float32, shape=None) -> torch.Tensor:
+    """Validate device / dtype / shape and return a contiguous, 16-byte aligned tensor."""
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"gflow_b200: {name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"gflow_b200: {name} must be a CUDA tensor (no CPU fallback exists), got device {t.device}")
+    if t.dtype != dtype:
+        raise RuntimeError(f"gflow_b200: {name} must have dtype {dtype}, got {t.dtype}")
+    if shape is not None:
+        if t.dim() != len(shape) or any(s is not None and int(d) != s for d, s in zip(t.shape, shape)):
+            raise RuntimeError(f"gflow_b200: {name} must have shape {shape}, got {tuple(t.shape)}")
+    t = t.detach()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+def _vis(visible, N, device):
+    if visible is None:
+        return None
+    if not visible.is_cuda:
+        raise RuntimeError("gflow_b200: visible must be a CUDA tensor")
+    if visible.numel() != N:
+        raise RuntimeError(f"gflow_b200: visible must have {N} elements, got {visible.numel()}")
+    v = visible.detach().reshape(-1)
+    if v.dtype == torch.bool:
+        v = v.contiguous().view(torch.uint8)
+    else:
+        v = (v != 0).view(torch.uint8)
+    return v
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _same_device(*ts):
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"gflow_b200: tensors on different devices ({dev} vs {t.device})")
+    return dev
+
+
+def _grid(W: int, H: int):
+    return (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
+
+
+# --------------------------------------------------------------------------- project_point
+class _ProjectPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, intr, extr, W, H, nearest, extent):
+        xyz_c = _prep(xyz, "xyz", shape=(None, 3))
+        intr_c = _prep(intr, "intr", shape=(4,))
+        extr_c = _prep(extr, "extr", shape=(3, 4))
+        dev = _same_device(xyz_c, intr_c, extr_c)
+        N = xyz_c.shape[0]
+        with torch.cuda.device(dev):
+            uv = torch.empty(N, 2, device=dev, dtype=torch.float32)
+            depth = torch.empty(N, 1, device=dev, dtype=torch.float32)
+            capi.check(_lib.gfb_project_point_fwd(xyz_c.data_ptr(), intr_c.data_ptr(), extr_c.data_ptr(), N, W, H,
+                                                  nearest, extent, uv.data_ptr(), depth.data_ptr(), _stream()),
+                       "project_point forward")
+        ctx.save_for_backward(xyz_c, intr_c, extr_c)
+        ctx.meta = (W, H, nearest, extent)
+        return uv, depth
+
+    @staticmethod
+    def backward(ctx, g_uv, g_depth):
+        xyz, intr, extr = ctx.saved_tensors
+        W, H, nearest, extent = ctx.meta
+        N = xyz.shape[0]
+        dev = xyz.device
+        with torch.cuda.device(dev):
+            g_uv = torch.zeros(N, 2, device=dev) if g_uv is None else _prep(g_uv, "grad uv")
+            g_depth = None if g_depth is None else _prep(g_depth, "grad depth")
+            d_xyz = torch.empty(N, 3, device=dev, dtype=torch.float32)
+            d_cam = torch.empty(16, device=dev, dtype=torch.float32)
+            capi.check(_lib.gfb_project_point_bwd(xyz.data_ptr(), intr.data_ptr(), extr.data_ptr(), N, W, H, nearest,
+                                                  extent, g_uv.data_ptr(), _ptr(g_depth), d_xyz.data_ptr(),
+                                                  d_cam.data_ptr(), _stream()), "project_point backward")
+        return d_xyz, d_cam[12:16], d_cam[:12].view(3, 4), None, None, None, None
+
+
+def project_point(xyz, intr, extr, W, H, nearest=0.2, extent=1.3):
+    """msplat.project_point -- /root/reference/gflow/utils/render.py:21-24, trainer.py:955."""
+    return _ProjectPoint.apply(xyz, intr, extr, int(W), int(H), float(nearest), float(extent))
+
+
+# --------------------------------------------------------------------------- compute_cov3d
+class _ComputeCov3D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scale, rotate, visible):
+        scale_c = _prep(scale, "scale", shape=(None, 3))
+        rotate_c = _prep(rotate, "rotate", shape=(None, 4))
+        dev = _same_device(scale_c, rotate_c)
+        N = scale_c.shape[0]
+        if rotate_c.shape[0] != N:
+            raise RuntimeError("gflow_b200: scale and rotate must have the same number of rows")
+        vis = _vis(visible, N, dev)
+        with torch.cuda.device(dev):
+            cov3d = torch.empty(N, 6, device=dev, dtype=torch.float32)
+            capi.check(_lib.gfb_compute_cov3d_fwd(scale_c.data_ptr(), rotate_c.data_ptr(), _ptr(vis), N,
+                                                  cov3d.data_ptr(), _stream()), "compute_cov3d forward")
+        ctx.save_for_backward(scale_c, rotate_c)
+        ctx.vis = vis
+        return cov3d
+
+    @staticmethod
+    def backward(ctx, g_cov):
+        scale, rotate = ctx.saved_tensors
+        N = scale.shape[0]
+        dev = scale.device
+        with torch.cuda.device(dev):
+            g_cov = _prep(g_cov, "grad cov3d")
+            d_scale = torch.empty(N, 3, device=dev, dtype=torch.float32)
+            d_rotate = torch.empty(N, 4, device=dev, dtype=torch.float32)
+            capi.check(_lib.gfb_compute_cov3d_bwd(scale.data_ptr(), rotate.data_ptr(), _ptr(ctx.vis), N,
+                                                  g_cov.data_ptr(), d_scale.data_ptr(), d_rotate.data_ptr(),
+                                                  _stream()), "compute_cov3d backward")
+        return d_scale, d_rotate, None
+
+
+def compute_cov3d(scale, rotate, visible=None):
+    """msplat.compute_cov3d -- /root/reference/gflow/utils/render.py:37-41."""
+    return _ComputeCov3D.apply(scale, rotate, visible)
+
+
+# --------------------------------------------------------------------------- ewa_project
+class _EwaProject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, cov3d, intr, extr, uv, W, H, visible):
+        xyz_c = _prep(xyz, "xyz", shape=(None, 3))
+        N = xyz_c.shape[0]
+        cov_c = _prep(cov3d, "cov3d", shape=(N, 6))
+        intr_c = _prep(intr, "intr", shape=(4,))
+        extr_c = _prep(extr, "extr", shape=(3, 4))
+        uv_c = _prep(uv, "uv", shape=(N, 2))
+        dev = _same_device(xyz_c, cov_c, intr_c, extr_c, uv_c)
+        vis = _vis(visible, N, dev)
+        with torch.cuda.device(dev):
+            conic = torch.empty(N, 3, device=dev, dtype=torch.float32)
+            radius = torch.empty(N, 1, device=dev, dtype=torch.int32)
+            tiles = torch.empty(N, 1, device=dev, dtype=torch.int32)
+            capi.check(_lib.gfb_ewa_project_fwd(xyz_c.data_ptr(), cov_c.data_ptr(), intr_c.data_ptr(),
+                                                extr_c.data_ptr(), uv_c.data_ptr(), N, W, H, _ptr(vis),
+                                                conic.data_ptr(), radius.data_ptr(), tiles.data_ptr(), _stream()),
+                       "ewa_project forward")
+        ctx.save_for_backward(xyz_c, cov_c, intr_c, extr_c, uv_c)
+        ctx.vis = vis
+        ctx.meta = (W, H)
+        ctx.mark_non_differentiable(radius, tiles)
+        return conic, radius, tiles
+
+    @staticmethod
+    def backward(ctx, g_conic, _g_radius, _g_tiles):
+        xyz, cov3d, intr, extr, uv = ctx.saved_tensors
+        W, H = ctx.meta
+        N = xyz.shape[0]
+        dev = xyz.device
+        with torch.cuda.device(dev):
+            g_conic = _prep(g_conic, "grad conic")
+            d_xyz = torch.empty(N, 3, device=dev, dtype=torch.float32)
+            d_cov = torch.empty(N, 6, device=dev, dtype=torch.float32)
+            d_cam = torch.empty(16, device=dev, dtype=torch.float32)
+            capi.check(_lib.gfb_ewa_project_bwd(xyz.data_ptr(), cov3d.data_ptr(), intr.data_ptr(), extr.data_ptr(),
+                                                uv.data_ptr(), N, W, H, _ptr(ctx.vis), g_conic.data_ptr(),
+                                                d_xyz.data_ptr(), d_cov.data_ptr(), d_cam.data_ptr(), _stream()),
+                       "ewa_project backward")
+        return d_xyz, d_cov, d_cam[12:16], d_cam[:12].view(3, 4), None, None, None, None
+
+
+def ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible=None):
+    """msplat.ewa_project -- /root/reference/gflow/utils/render.py:44-49."""
+    return _EwaProject.apply(xyz, cov3d, intr, extr, uv, int(W), int(H), visible)
+
+
+# --------------------------------------------------------------------------- sort_gaussian
+@torch.no_grad()
+def sort_gaussian(uv, depth, W, H, radius, tiles_touched):
+    """msplat.sort_gaussian -- /root/reference/gflow/utils/render.py:52-54.
+
+    Returns gaussian_ids_sorted (K,) int32 and tile_range (T,2) int32.  One 4-byte
+    device->host read (K) is unavoidable because the API returns a tensor of exactly K entries.
+    """
+    W, H = int(W), int(H)
+    uv_c = _prep(uv, "uv", shape=(None, 2))
+    N = uv_c.shape[0]
+    depth_c = _prep(depth, "depth").reshape(-1)
+    radius_c = _prep(radius, "radius", dtype=torch.int32).reshape(-1)
+    tiles_c = _prep(tiles_touched, "tiles_touched", dtype=torch.int32).reshape(-1)
+    if depth_c.numel() != N or radius_c.numel() != N or tiles_c.numel() != N:
+        raise RuntimeError("gflow_b200: uv, depth, radius and tiles_touched must describe the same N Gaussians")
+    dev = _same_device(uv_c, depth_c, radius_c, tiles_c)
+    gx, gy = _grid(W, H)
+    T = gx * gy
+    with torch.cuda.device(dev):
+        counts = torch.empty(T, device=dev, dtype=torch.int32)
+        offsets = torch.empty(T + 1, device=dev, dtype=torch.int32)
+        capi.check(_lib.gfb_sort_count(uv_c.data_ptr(), radius_c.data_ptr(), tiles_c.data_ptr(), N, W, H,
+                                       counts.data_ptr(), offsets.data_ptr(), _stream()), "sort_gaussian count")
+        K = int(offsets[T].item())
+        keys = torch.empty(max(K, 1), device=dev, dtype=torch.int64)
+        ids = torch.empty(K, device=dev, dtype=torch.int32)
+        tile_range = torch.empty(T, 2, device=dev, dtype=torch.int32)
+        capi.check(_lib.gfb_sort_emit(uv_c.data_ptr(), depth_c.data_ptr(), radius_c.data_ptr(), tiles_c.data_ptr(), N,
+                                      W, H, counts.data_ptr(), offsets.data_ptr(), K, keys.data_ptr(), ids.data_ptr(),
+                                      tile_range.data_ptr(), _stream()), "sort_gaussian emit")
+    return ids, tile_range
+
+
+# --------------------------------------------------------------------------- alpha_blending
+class _GeomStreamCache:
+    """Last packed geometry stream, keyed on tensor identity + version counters.
+
+    render_multiple blends rgb, depth and depth-colour with the same (uv, conic, opacity,
+    gaussian_ids_sorted) objects (/root/reference/gflow/utils/render.py:58-90); the packed
+    stream is built once and shared.  Strong references pin the key tensors so an address can
+    never be recycled under a stale entry.
+    """
+
+    def __init__(self):
+        self.key = None
+        self.refs = None
+        self.stream = None
+
+    def get(self, uv, conic, opacity, ids):
+        key = (id(uv), uv._version, id(conic), conic._version, id(opacity), opacity._version, id(ids), ids._version)
+        if self.key == key:
+            return self.stream
+        return None
+
+    def put(self, uv, conic, opacity, ids, stream):
+        self.key = (id(uv), uv._version, id(conic), conic._version, id(opacity), opacity._version, id(ids),
+                    ids._version)
+        self.refs = (uv, conic, opacity, ids)
+        self.stream = stream
+
+    def clear(self):
+        self.key = self.refs = self.stream = None
+
+
+_geom_cache = _GeomStreamCache()
+
+
+def _pack_geometry(uv_c, conic_c, opacity_c, ids_c, K):
+    dev = uv_c.device
+    stream = torch.empty(max(K, 1) * 8, device=dev, dtype=torch.float32)
+    capi.check(_lib.gfb_blend_pack_geometry(uv_c.data_ptr(), conic_c.data_ptr(), opacity_c.data_ptr(),
+                                            ids_c.data_ptr(), K, stream.data_ptr(), _stream()), "blend pack geometry")
+    return stream
+
+
+class _AlphaBlending(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, uv, conic, opacity, feature, ids, tile_range, bg, W, H, ndc, geom_stream):
+        uv_c = _prep(uv, "uv", shape=(None, 2))
+        N = uv_c.shape[0]
+        conic_c = _prep(conic, "conic", shape=(N, 3))
+        opacity_c = _prep(opacity, "opacity").reshape(-1)
+        if opacity_c.numel() != N:
+            raise RuntimeError(f"gflow_b200: opacity must have {N} elements, got {opacity_c.numel()}")
+        feature_c = _prep(feature, "feature", shape=(N, None))
+        C = feature_c.shape[1]
+        if C < 1:
+            raise RuntimeError("gflow_b200: feature needs at least one channel")
+        ids_c = _prep(ids, "gaussian_ids_sorted", dtype=torch.int32).reshape(-1)
+        gx, gy = _grid(W, H)
+        T = gx * gy
+        tr_c = _prep(tile_range, "tile_range", dtype=torch.int32, shape=(T, 2))
+        dev = _same_device(uv_c, conic_c, opacity_c, feature_c, ids_c, tr_c)
+        K = ids_c.numel()
+        st = _stream
+        with torch.cuda.device(dev):
+            if geom_stream is None:
+                geom_stream = _pack_geometry(uv_c, conic_c, opacity_c, ids_c, K)
+            out = torch.empty(C, H, W, device=dev, dtype=torch.float32)
+            final_T = torch.empty(H, W, device=dev, dtype=torch.float32)
+            n_contrib = torch.empty(H, W, device=dev, dtype=torch.int32)
+            feat_streams = []
+            for c0 in range(0, C, 4):
+                cg = min(4, C - c0)
+                fs = torch.empty(max(K, 1) * 4, device=dev, dtype=torch.float32)
+                capi.check(_lib.gfb_blend_pack_feature(feature_c.data_ptr(), C, c0, cg, ids_c.data_ptr(), K,
+                                                       fs.data_ptr(), st()), "blend pack feature")
+                capi.check(_lib.gfb_alpha_blending_fwd(geom_stream.data_ptr(), fs.data_ptr(), K, tr_c.data_ptr(), C,
+                                                       c0, cg, bg, W, H, out.data_ptr(), final_T.data_ptr(),
+                                                       n_contrib.data_ptr(), st()), "alpha_blending forward")
+                feat_streams.append(fs)
+        ctx.save_for_backward(geom_stream, ids_c, tr_c, final_T, n_contrib, *feat_streams)
+        ctx.meta = (N, C, K, float(bg), W, H)
+        ctx.ndc_grad = ndc is not None and isinstance(ndc, torch.Tensor) and ndc.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        geom_stream, ids_c, tr_c, final_T, n_contrib, *feat_streams = ctx.saved_tensors
+        N, C, K, bg, W, H = ctx.meta
+        dev = geom_stream.device
+        st = _stream
+        with torch.cuda.device(dev):
+            g_out = _prep(g_out, "grad feature_map", shape=(C, H, W))
+            d_uv = torch.empty(N, 2, device=dev, dtype=torch.float32)
+            d_conic = torch.empty(N, 3, device=dev, dtype=torch.float32)
+            d_opacity = torch.empty(N, 1, device=dev, dtype=torch.float32)
+            d_feature = torch.empty(N, C, device=dev, dtype=torch.float32)
+            for gi, c0 in enumerate(range(0, C, 4)):
+                cg = min(4, C - c0)
+                grad_pack = torch.zeros(max(N, 1) * 12, device=dev, dtype=torch.float32)
+                capi.check(_lib.gfb_alpha_blending_bwd(geom_stream.data_ptr(), feat_streams[gi].data_ptr(), K,
+                                                       ids_c.data_ptr(), tr_c.data_ptr(), C, c0, cg, bg, W, H,
+                                                       final_T.data_ptr(), n_contrib.data_ptr(), g_out.data_ptr(),
+                                                       grad_pack.data_ptr(), st()), "alpha_blending backward")
+                capi.check(_lib.gfb_blend_unpack_grads(grad_pack.data_ptr(), N, C, c0, cg, d_uv.data_ptr(),
+                                                       d_conic.data_ptr(), d_opacity.data_ptr(), d_feature.data_ptr(),
+                                                       1 if gi > 0 else 0, st()), "alpha_blending unpack grads")
+        d_ndc = d_uv.clone() if ctx.ndc_grad else None
+        return d_uv, d_conic, d_opacity, d_feature, None, None, None, None, None, d_ndc, None
+
+
+def alpha_blending(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range, bg, W, H, ndc=None):
+    """msplat.alpha_blending -- /root/reference/gflow/utils/render.py:58-64 (and 68-105, 148-154).
+
+    ``bg`` is a Python float; the result is (C,H,W).  ``ndc`` (optional, upstream's hook for
+    densification statistics) receives a copy of the screen-space gradient of ``uv``.
+    """
+    W, H = int(W), int(H)
+    geom_stream = None
+    if all(isinstance(t, torch.Tensor) and t.is_cuda for t in (uv, conic, opacity, gaussian_ids_sorted)):
+        geom_stream = _geom_cache.get(uv, conic, opacity, gaussian_ids_sorted)
+        if geom_stream is None and uv.dtype == conic.dtype == opacity.dtype == torch.float32 \
+                and gaussian_ids_sorted.dtype == torch.int32 and uv.dim() == 2 and conic.dim() == 2 \
+                and conic.shape == (uv.shape[0], 3) and opacity.numel() == uv.shape[0]:
+            with torch.no_grad(), torch.cuda.device(uv.device):
+                geom_stream = _pack_geometry(_prep(uv, "uv", shape=(None, 2)), _prep(conic, "conic"),
+                                             _prep(opacity, "opacity").reshape(-1),
+                                             _prep(gaussian_ids_sorted, "gaussian_ids_sorted", dtype=torch.int32)
+                                             .reshape(-1), gaussian_ids_sorted.numel())
+            _geom_cache.put(uv, conic, opacity, gaussian_ids_sorted, geom_stream)
+    return _AlphaBlending.apply(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range, float(bg), W, H, ndc,
+                                geom_stream)
+
+
+# --------------------------------------------------------------------------- compute_sh
+class _ComputeSH(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, shs, dirs, visible):
+        shs_c = _prep(shs, "shs", shape=(None, None, None))
+        N, C, K = shs_c.shape
+        if K not in (1, 4, 9, 16):
+            raise RuntimeError(f"gflow_b200: shs last dimension must be 1, 4, 9 or 16 (degree 0..3), got {K}")
+        dirs_c = _prep(dirs, "dirs", shape=(N, 3))
+        dev = _same_device(shs_c, dirs_c)
+        vis = _vis(visible, N, dev)
+        with torch.cuda.device(dev):
+            out = torch.empty(N, C, device=dev, dtype=torch.float32)
+            capi.check(_lib.gfb_compute_sh_fwd(shs_c.data_ptr(), dirs_c.data_ptr(), _ptr(vis), N, C, K,
+                                               out.data_ptr(), _stream()), "compute_sh forward")
+        ctx.save_for_backward(shs_c, dirs_c)
+        ctx.vis = vis
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        shs, dirs = ctx.saved_tensors
+        N, C, K = shs.shape
+        dev = shs.device
+        with torch.cuda.device(dev):
+            g_out = _prep(g_out, "grad sh colour", shape=(N, C))
+            d_shs = torch.empty(N, C, K, device=dev, dtype=torch.float32)
+            d_dirs = torch.empty(N, 3, device=dev, dtype=torch.float32)
+            capi.check(_lib.gfb_compute_sh_bwd(shs.data_ptr(), dirs.data_ptr(), _ptr(ctx.vis), N, C, K,
+                                               g_out.data_ptr(), d_shs.data_ptr(), d_dirs.data_ptr(), _stream()),
+                       "compute_sh backward")
+        return d_shs, d_dirs, None
+
+
+def compute_sh(shs, dirs, visible=None):
+    """msplat.compute_sh (north_star surface; not called by GFlow): shs (N,C,K), dirs (N,3)."""
+    return _ComputeSH.apply(shs, dirs, visible)
+
+
+# --------------------------------------------------------------------------- rasterization
+def rasterization(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):
+    """Convenience chain of the five ops (upstream msplat.rasterization); same order as
+    /root/reference/gflow/utils/render.py:21-64."""
+    uv, depth = project_point(xyz, intr, extr, W, H)
+    visible = depth != 0
+    cov3d = compute_cov3d(scale, rotate, visible)
+    conic, radius, tiles_touched = ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible)
+    ids, tile_range = sort_gaussian(uv, depth, W, H, radius, tiles_touched)
+    return alpha_blending(uv, conic, opacity, feature, ids, tile_range, bg, W, H)

@@ -1,0 +1,134 @@
+/*
+ * gflow_b200.h -- C ABI of the B200-native splat rasteriser (libgflow_b200.so).
+ *
+ * Drop-in boundary for the `msplat` operator surface GFlow calls
+ * (/root/reference/gflow/utils/render.py:21-154, /root/reference/gflow/trainer.py:955).
+ * `msplat` itself is a third-party CUDA extension that is NOT part of
+ * /root/reference; each entry point below names the msplat
+ * Python-level operator it implements and the GFlow call site that pins its
+ * contract.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current CUDA device unless noted;
+ *  - float = IEEE binary32, row-major contiguous; int32 for integer tensors;
+ *    `visible` is uint8 (0/1), may be NULL (= all visible);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - return value: 0 on success, otherwise the cudaError_t of the failing call
+ *    (gfb_error_string() decodes it), or a negative GFB_E_* code for bad arguments;
+ *  - no entry point allocates device memory or synchronises the stream; work
+ *    buffers are passed in by the caller and sized with the *_bytes() helpers;
+ *  - N = number of Gaussians, K = number of (tile, Gaussian) intersections,
+ *    T = ceil(W/16) * ceil(H/16) tiles, row-major (tile = ty * ceil(W/16) + tx).
+ */
+#ifndef GFLOW_B200_H
+#define GFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFB_TILE 16
+#define GFB_E_BADARG (-1)     /* NULL pointer / negative size / unsupported channel count */
+#define GFB_E_UNSUPPORTED (-2)
+
+/* library / build information */
+int gfb_version(void);                 /* 100 * major + minor */
+const char *gfb_build_arch(void);      /* "sm_100a" */
+const char *gfb_error_string(int code);
+/* number of CUDA kernels this library has launched in this process (host-side counter) */
+int64_t gfb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ msplat.project_point
+ * call sites: render.py:21-24,116-119; trainer.py:955.
+ * uv (N,2), depth (N,1); culled points give uv = depth = 0. */
+int gfb_project_point_fwd(const float *xyz, const float *intr, const float *extr, int N, int W, int H,
+                          float nearest, float extent, float *uv, float *depth, void *stream);
+/* g_depth may be NULL.  d_cam = 16 floats {d_extr (3x4 row-major), d_intr (fx fy cx cy)},
+ * overwritten (zeroed, then reduced over N). */
+int gfb_project_point_bwd(const float *xyz, const float *intr, const float *extr, int N, int W, int H,
+                          float nearest, float extent, const float *g_uv, const float *g_depth, float *d_xyz,
+                          float *d_cam, void *stream);
+
+/* ------------------------------------------------------------------ msplat.compute_cov3d
+ * call sites: render.py:37-41,123-127.  cov3d (N,6) = upper triangle of R diag(s^2) R^T. */
+int gfb_compute_cov3d_fwd(const float *scale, const float *rotate, const uint8_t *visible, int N, float *cov3d,
+                          void *stream);
+int gfb_compute_cov3d_bwd(const float *scale, const float *rotate, const uint8_t *visible, int N,
+                          const float *g_cov3d, float *d_scale, float *d_rotate, void *stream);
+
+/* ------------------------------------------------------------------ msplat.ewa_project
+ * call sites: render.py:44-49,130-135.  conic (N,3), radius (N,1) int32, tiles_touched (N,1) int32. */
+int gfb_ewa_project_fwd(const float *xyz, const float *cov3d, const float *intr, const float *extr, const float *uv,
+                        int N, int W, int H, const uint8_t *visible, float *conic, int32_t *radius,
+                        int32_t *tiles_touched, void *stream);
+int gfb_ewa_project_bwd(const float *xyz, const float *cov3d, const float *intr, const float *extr, const float *uv,
+                        int N, int W, int H, const uint8_t *visible, const float *g_conic, float *d_xyz,
+                        float *d_cov3d, float *d_cam /* as in gfb_project_point_bwd */, void *stream);
+
+/* ------------------------------------------------------------------ msplat.compute_sh
+ * (no GFlow call site; north_star surface).  shs (N,C,K), K in {1,4,9,16}; dirs (N,3). */
+int gfb_compute_sh_fwd(const float *shs, const float *dirs, const uint8_t *visible, int N, int C, int K, float *out,
+                       void *stream);
+int gfb_compute_sh_bwd(const float *shs, const float *dirs, const uint8_t *visible, int N, int C, int K,
+                       const float *g_out, float *d_shs, float *d_dirs, void *stream);
+
+/* ------------------------------------------------------------------ msplat.sort_gaussian
+ * call sites: render.py:52-54,138-140.  Two phases because the caller must size
+ * gaussian_ids_sorted (K,) before phase 2:
+ *   1. gfb_sort_count: per-tile intersection counts (tile_counts, T int32) and their
+ *      exclusive scan (tile_offsets, T+1 int32; tile_offsets[T] = K).  The caller reads K back.
+ *   2. gfb_sort_emit: scatter (depth bits, id) keys per tile into keys_ws
+ *      (gfb_sort_workspace_bytes(K) bytes), sort every tile's segment, write
+ *      gaussian_ids_sorted (K,) and tile_range (T,2).  tile_counts is consumed (counted down to 0).
+ * The result equals a stable ascending sort of (tile << 32 | float bits of depth)
+ * over a Gaussian-major emission. */
+size_t gfb_sort_workspace_bytes(int64_t K);
+int gfb_sort_count(const float *uv, const int32_t *radius, const int32_t *tiles_touched, int N, int W, int H,
+                   int32_t *tile_counts, int32_t *tile_offsets, void *stream);
+int gfb_sort_emit(const float *uv, const float *depth, const int32_t *radius, const int32_t *tiles_touched, int N,
+                  int W, int H, int32_t *tile_counts, const int32_t *tile_offsets, int64_t K, void *keys_ws,
+                  int32_t *gaussian_ids_sorted, int32_t *tile_range, void *stream);
+
+/* ------------------------------------------------------------------ msplat.alpha_blending
+ * call sites: render.py:58-64,68-74,84-90,99-105,148-154; backward via trainer.py:533.
+ *
+ * The blend kernels read two packed, tile-contiguous streams that are staged into
+ * shared memory with 1-D bulk TMA copies:
+ *   geometry stream: 2 K records of 16 B: K x {u, v, half-extent x, y} then K x {conic a, b, c, opacity}
+ *   feature  stream: K records of 16 B (up to 4 channels, zero padded)
+ * gfb_blend_pack_geometry / gfb_blend_pack_feature build them from the msplat-level
+ * tensors; a geometry stream can be shared by every blend that uses the same
+ * (uv, conic, opacity, gaussian_ids_sorted).  C > 4 is handled by the caller as
+ * ceil(C/4) channel groups (c0 = first channel of the group, 1 <= Cg <= 4). */
+size_t gfb_blend_geometry_stream_bytes(int64_t K);
+size_t gfb_blend_feature_stream_bytes(int64_t K);
+int gfb_blend_pack_geometry(const float *uv, const float *conic, const float *opacity,
+                            const int32_t *gaussian_ids_sorted, int64_t K, void *geom_stream, void *stream);
+int gfb_blend_pack_feature(const float *feature, int C, int c0, int Cg, const int32_t *gaussian_ids_sorted, int64_t K,
+                           void *feat_stream, void *stream);
+/* out is (C,H,W); this call writes channels [c0, c0+Cg).  final_T (H,W) float and
+ * n_contrib (H,W) int32 are saved for the backward pass. */
+int gfb_alpha_blending_fwd(const void *geom_stream, const void *feat_stream, int64_t K, const int32_t *tile_range,
+                           int C, int c0, int Cg, float bg, int W, int H, float *out, float *final_T,
+                           int32_t *n_contrib, void *stream);
+/* Accumulates into grad_pack (N records of 12 floats {d_u, d_v, d_a, d_b, d_c, d_opacity,
+ * d_f[c0..c0+3], pad, pad}); the caller zeroes grad_pack before each call. */
+size_t gfb_blend_grad_pack_bytes(int N);
+int gfb_alpha_blending_bwd(const void *geom_stream, const void *feat_stream, int64_t K,
+                           const int32_t *gaussian_ids_sorted, const int32_t *tile_range, int C, int c0, int Cg,
+                           float bg, int W, int H,
+                           const float *final_T, const int32_t *n_contrib, const float *g_out, float *grad_pack,
+                           void *stream);
+/* Scatter grad_pack into msplat-shaped gradients.  Feature slots go to
+ * d_feature[:, c0:c0+Cg] (row stride C).  accumulate == 0 overwrites d_uv / d_conic /
+ * d_opacity, != 0 adds to them (second and later channel groups). */
+int gfb_blend_unpack_grads(const float *grad_pack, int N, int C, int c0, int Cg, float *d_uv, float *d_conic,
+                           float *d_opacity, float *d_feature, int accumulate, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFLOW_B200_H */

@@ -1,0 +1,399 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via gflow_b200.ops) against the CPU oracle.
+
+Tolerances follow BASELINE.json north_star: rendered values within 1e-4 relative, gradients
+within 1e-3 relative (max-norm relative, see conftest.assert_close), tile / sort indices and the
+per-Gaussian float32 geometry bit-exact.  Nothing here reads /root/reference.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+from gflow_b200.synthetic import make_grad_image, make_scene
+from oracle import c_oracle as C
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+# isolated threshold flips are tolerated on this fraction of elements (see conftest.assert_close)
+IMG_OUTLIERS = dict(outlier_frac=2e-5, outlier_rel=2e-2)
+GRAD_OUTLIERS = dict(outlier_frac=1e-4, outlier_rel=5e-2)
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gflow_b200
+
+    return gflow_b200
+
+
+def cu(*ts):
+    out = [t.to(DEV) if torch.is_tensor(t) else t for t in ts]
+    return out if len(out) > 1 else out[0]
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name))
+    return {k: torch.from_numpy(z[k]) if z[k].ndim else z[k].item() for k in z.files}
+
+
+def _geometry_oracle(sc):
+    uv, depth = C.project_point(sc.xyz, sc.intr, sc.extr, sc.W, sc.H)
+    vis = depth != 0
+    cov = C.compute_cov3d(sc.scale, sc.rotate, vis)
+    conic, radius, tiles = C.ewa_project(sc.xyz, cov, sc.intr, sc.extr, uv, sc.W, sc.H, vis)
+    ids, rng = C.sort_gaussian(uv, depth, sc.W, sc.H, radius, tiles)
+    return uv, depth, vis, cov, conic, radius, tiles, ids, rng
+
+
+SCENES = [(1000, 256, 256, 0, "synthetic"), (5000, 200, 136, 1, "gflow"), (60000, 854, 480, 0, "synthetic")]
+
+
+@pytest.mark.parametrize("N,W,H,seed,profile", SCENES)
+def test_geometry_forward_bit_exact(G, N, W, H, seed, profile):
+    sc = make_scene(N, W, H, seed=seed, profile=profile)
+    uv_o, d_o, vis_o, cov_o, con_o, rad_o, t_o, ids_o, rng_o = _geometry_oracle(sc)
+    xyz, scale, rot, intr, extr = cu(sc.xyz, sc.scale, sc.rotate, sc.intr, sc.extr)
+    uv, depth = G.project_point(xyz, intr, extr, W, H)
+    assert uv.shape == (N, 2) and depth.shape == (N, 1)
+    assert torch.equal(uv.cpu(), uv_o), "uv must be bit-exact"
+    assert torch.equal(depth.cpu(), d_o), "depth must be bit-exact (it is the sort key)"
+    vis = depth != 0
+    cov = G.compute_cov3d(scale, rot, vis)
+    assert torch.equal(cov.cpu(), cov_o), "cov3d must be bit-exact"
+    conic, radius, tiles = G.ewa_project(xyz, cov, intr, extr, uv, W, H, vis)
+    assert radius.dtype == torch.int32 and tiles.dtype == torch.int32 and radius.shape == (N, 1)
+    assert torch.equal(radius.cpu(), rad_o), "radius must be bit-exact"
+    assert torch.equal(tiles.cpu(), t_o), "tiles_touched must be bit-exact"
+    assert torch.equal(conic.cpu(), con_o), "conic must be bit-exact"
+    ids, rng = G.sort_gaussian(uv, depth, W, H, radius, tiles)
+    assert ids.dtype == torch.int32 and rng.dtype == torch.int32
+    assert ids.shape == ids_o.shape and rng.shape == rng_o.shape
+    assert torch.equal(rng.cpu(), rng_o), "tile_range must be bit-exact"
+    assert torch.equal(ids.cpu(), ids_o), "gaussian_ids_sorted must be bit-exact"
+
+
+@pytest.mark.parametrize("N,W,H,seed,profile", SCENES[:2])
+def test_geometry_backward(G, N, W, H, seed, profile):
+    sc = make_scene(N, W, H, seed=seed, profile=profile)
+    uv_o, d_o, vis_o, cov_o, con_o, rad_o, t_o, ids_o, rng_o = _geometry_oracle(sc)
+    gen = torch.Generator().manual_seed(seed + 7)
+    g_uv, g_d = torch.randn(N, 2, generator=gen), torch.randn(N, 1, generator=gen)
+    g_cov, g_con = torch.randn(N, 6, generator=gen), torch.randn(N, 3, generator=gen)
+    # project_point
+    xyz, intr, extr = (t.to(DEV).requires_grad_(True) for t in (sc.xyz, sc.intr, sc.extr))
+    uv, depth = G.project_point(xyz, intr, extr, W, H)
+    ((uv * cu(g_uv)).sum() + (depth * cu(g_d)).sum()).backward()
+    d_xyz, d_intr, d_extr = C.project_point_bwd(sc.xyz, sc.intr, sc.extr, W, H, g_uv, g_d)
+    assert_close(xyz.grad, d_xyz, 1e-4, "project d_xyz")
+    assert_close(intr.grad, d_intr, 1e-3, "project d_intr")
+    assert_close(extr.grad, d_extr, 1e-3, "project d_extr")
+    # compute_cov3d
+    scale, rot = (t.to(DEV).requires_grad_(True) for t in (sc.scale, sc.rotate))
+    cov = G.compute_cov3d(scale, rot, cu(vis_o))
+    (cov * cu(g_cov)).sum().backward()
+    d_s, d_q = C.compute_cov3d_bwd(sc.scale, sc.rotate, vis_o, g_cov)
+    assert_close(scale.grad, d_s, 1e-4, "cov3d d_scale")
+    assert_close(rot.grad, d_q, 1e-4, "cov3d d_rotate")
+    # ewa_project
+    xyz, cov, intr, extr = (t.to(DEV).requires_grad_(True) for t in (sc.xyz, cov_o, sc.intr, sc.extr))
+    conic, radius, tiles = G.ewa_project(xyz, cov, intr, extr, cu(uv_o), W, H, cu(vis_o))
+    assert not radius.requires_grad and not tiles.requires_grad
+    (conic * cu(g_con)).sum().backward()
+    d_xyz, d_cov, d_intr, d_extr = C.ewa_project_bwd(sc.xyz, cov_o, sc.intr, sc.extr, uv_o, W, H, vis_o, g_con)
+    assert_close(xyz.grad, d_xyz, 1e-4, "ewa d_xyz")
+    assert_close(cov.grad, d_cov, 1e-4, "ewa d_cov3d")
+    assert_close(intr.grad[:2], d_intr[:2], 1e-3, "ewa d_intr")
+    assert_close(extr.grad, d_extr, 1e-3, "ewa d_extr")
+
+
+def test_ewa_clamp_branch_and_no_visible_mask(G):
+    gen = torch.Generator().manual_seed(3)
+    N, W, H = 2000, 128, 96
+    sc = make_scene(N, W, H, seed=4)
+    xyz = torch.cat([(torch.rand(N, 2, generator=gen) - 0.5) * 8.0, 1.0 + torch.rand(N, 1, generator=gen)], dim=1)
+    cov = C.compute_cov3d(sc.scale * 20, sc.rotate, None)
+    uv = torch.rand(N, 2, generator=gen) * torch.tensor([W, H])
+    g = torch.randn(N, 3, generator=gen)
+    con_o, rad_o, t_o = C.ewa_project(xyz, cov, sc.intr, sc.extr, uv, W, H, None)
+    d_xyz, d_cov, d_intr, d_extr = C.ewa_project_bwd(xyz, cov, sc.intr, sc.extr, uv, W, H, None, g)
+    x, c, i, e = (t.to(DEV).requires_grad_(True) for t in (xyz, cov, sc.intr, sc.extr))
+    conic, radius, tiles = G.ewa_project(x, c, i, e, cu(uv), W, H)
+    assert torch.equal(radius.cpu(), rad_o) and torch.equal(tiles.cpu(), t_o) and torch.equal(conic.cpu(), con_o)
+    (conic * cu(g)).sum().backward()
+    assert_close(x.grad, d_xyz, 1e-4, "d_xyz")
+    assert_close(c.grad, d_cov, 1e-4, "d_cov3d")
+    assert_close(e.grad, d_extr, 1e-3, "d_extr")
+
+
+def test_sort_edge_cases(G):
+    W, H = 40, 40
+    T = 9
+    i32 = dict(dtype=torch.int32, device=DEV)
+    # N = 0
+    ids, rng = G.sort_gaussian(torch.zeros(0, 2, device=DEV), torch.zeros(0, 1, device=DEV), W, H,
+                               torch.zeros(0, 1, **i32), torch.zeros(0, 1, **i32))
+    assert ids.shape == (0,) and rng.shape == (T, 2) and int(rng.abs().sum()) == 0
+    # everything culled (radius 0)
+    ids, rng = G.sort_gaussian(torch.rand(50, 2, device=DEV) * 40, torch.rand(50, 1, device=DEV), W, H,
+                               torch.zeros(50, 1, **i32), torch.zeros(50, 1, **i32))
+    assert ids.numel() == 0 and int(rng.abs().sum()) == 0
+    # ties keep id order; one Gaussian covers every tile
+    uv = torch.tensor([[20.0, 20.0], [5.0, 5.0], [5.0, 5.0], [5.0, 5.0]])
+    depth = torch.tensor([[2.0], [1.0], [1.0], [0.5]])
+    radius = torch.tensor([[100], [3], [3], [3]], dtype=torch.int32)
+    tiles = torch.tensor([[9], [1], [1], [1]], dtype=torch.int32)
+    ids, rng = G.sort_gaussian(*cu(uv, depth), W, H, *cu(radius, tiles))
+    ids_o, rng_o = C.sort_gaussian(uv, depth, W, H, radius, tiles)
+    assert torch.equal(ids.cpu(), ids_o) and torch.equal(rng.cpu(), rng_o)
+    assert ids.cpu().tolist()[:4] == [3, 1, 2, 0]
+
+
+@pytest.mark.parametrize("n_heavy", [40, 64, 65, 128, 129, 1000, 4096, 4097, 9000])
+def test_sort_heavy_tile_all_size_classes(G, n_heavy):
+    """One tile holds n_heavy Gaussians (warp path <=64, shared-memory path <=4096, global path
+    beyond), many with equal depth (ties resolved by id)."""
+    gen = torch.Generator().manual_seed(n_heavy)
+    W, H = 64, 48
+    uv = torch.cat([8.0 + torch.rand(n_heavy, 2, generator=gen) * 2.0, torch.rand(300, 2, generator=gen) * 60.0])
+    N = uv.shape[0]
+    depth = torch.randint(1, 50, (N, 1), generator=gen).float() * 0.25  # many ties
+    radius = torch.cat([torch.ones(n_heavy, 1), torch.randint(1, 9, (300, 1), generator=gen)]).to(torch.int32)
+    tiles = torch.ones(N, 1, dtype=torch.int32)  # only > 0 matters for sort_gaussian
+    ids_o, rng_o = C.sort_gaussian(uv, depth, W, H, radius, tiles)
+    ids, rng = G.sort_gaussian(*cu(uv, depth), W, H, *cu(radius, tiles))
+    assert int(rng_o[0, 1] - rng_o[0, 0]) >= n_heavy
+    assert torch.equal(rng.cpu(), rng_o)
+    assert torch.equal(ids.cpu(), ids_o)
+
+
+BLEND_CASES = [
+    # N, W, H, seed, profile, C, bg
+    (1000, 256, 256, 0, "synthetic", 3, 0.0),
+    (3000, 200, 136, 1, "gflow", 1, 0.33),
+    (3000, 203, 131, 2, "synthetic", 4, 1.0),   # W, H not multiples of 16
+    (2000, 100, 70, 3, "synthetic", 5, 0.5),    # two channel groups
+    (2000, 100, 70, 4, "synthetic", 9, 0.0),    # three channel groups
+    (60000, 854, 480, 0, "synthetic", 3, 0.0),  # BASELINE config 2
+    (60000, 854, 480, 0, "gflow", 1, 0.0),
+]
+
+
+@pytest.mark.parametrize("N,W,H,seed,profile,Cf,bg", BLEND_CASES)
+def test_alpha_blending_forward_backward(G, N, W, H, seed, profile, Cf, bg):
+    sc = make_scene(N, W, H, seed=seed, profile=profile)
+    uv_o, d_o, vis_o, cov_o, con_o, rad_o, t_o, ids_o, rng_o = _geometry_oracle(sc)
+    gen = torch.Generator().manual_seed(seed + 50)
+    feat = torch.rand(N, Cf, generator=gen)
+    img_o, fT_o, nc_o = C.alpha_blending(uv_o, con_o, sc.opacity, feat, ids_o, rng_o, bg, W, H, return_aux=True)
+    Gimg = make_grad_image(Cf, W, H, seed=seed + 1)
+    d_uv, d_conic, d_op, d_f = C.alpha_blending_bwd(uv_o, con_o, sc.opacity, feat, ids_o, rng_o, bg, W, H, fT_o, nc_o,
+                                                    Gimg)
+    uv, conic, op, f = (t.to(DEV).requires_grad_(True) for t in (uv_o, con_o, sc.opacity, feat))
+    img = G.alpha_blending(uv, conic, op, f, cu(ids_o), cu(rng_o), bg, W, H)
+    assert img.shape == (Cf, H, W)
+    assert_close(img, img_o, 1e-4, "rendered image", **IMG_OUTLIERS)
+    (img * cu(Gimg)).sum().backward()
+    assert op.grad.shape == (N, 1) and f.grad.shape == (N, Cf)
+    assert_close(uv.grad, d_uv, 1e-3, "d_uv", **GRAD_OUTLIERS)
+    assert_close(conic.grad, d_conic, 1e-3, "d_conic", **GRAD_OUTLIERS)
+    assert_close(op.grad, d_op, 1e-3, "d_opacity", **GRAD_OUTLIERS)
+    assert_close(f.grad, d_f, 1e-3, "d_feature", **GRAD_OUTLIERS)
+
+
+def test_alpha_blending_empty_inputs_render_background(G):
+    W, H, T = 50, 35, 4 * 3
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=DEV)  # noqa: E731
+    img = G.alpha_blending(z(0, 2), z(0, 3), z(0, 1), z(0, 3), z(0, dt=torch.int32), z(T, 2, dt=torch.int32), 0.25, W, H)
+    assert img.shape == (3, H, W) and torch.all(img == 0.25)
+    # N > 0 but K = 0, with gradients requested
+    uv = torch.rand(10, 2, device=DEV, requires_grad=True)
+    f = torch.rand(10, 3, device=DEV, requires_grad=True)
+    img = G.alpha_blending(uv, torch.ones(10, 3, device=DEV), torch.ones(10, 1, device=DEV), f,
+                           z(0, dt=torch.int32), z(T, 2, dt=torch.int32), 1.0, W, H)
+    assert torch.all(img == 1.0)
+    img.sum().backward()
+    assert torch.all(uv.grad == 0) and torch.all(f.grad == 0)
+
+
+def test_center_render_identity_conic_opacity_one(G):
+    """render_multiple's 'center' pass (/root/reference/gflow/utils/render.py:93-105): conic (1,0,1),
+    opacity 1 -> alpha is clamped to 0.99 at the centre pixel."""
+    sc = make_scene(4000, 320, 200, seed=6, profile="gflow")
+    uv_o, d_o, vis_o, cov_o, con_o, rad_o, t_o, ids_o, rng_o = _geometry_oracle(sc)
+    conic = torch.ones_like(con_o) * torch.tensor([1.0, 0.0, 1.0])
+    op = torch.ones_like(sc.opacity)
+    img_o = C.alpha_blending(uv_o, conic, op, sc.rgb, ids_o, rng_o, 0.0, sc.W, sc.H)
+    img = G.alpha_blending(*cu(uv_o, conic, op, sc.rgb, ids_o, rng_o), 0.0, sc.W, sc.H)
+    assert_close(img, img_o, 1e-4, "center image", **IMG_OUTLIERS)
+
+
+@pytest.mark.parametrize("N,W,H,profile", [(1000, 256, 256, "synthetic"), (60000, 854, 480, "synthetic"),
+                                           (60000, 854, 480, "gflow")])
+def test_render_step_chain_matches_oracle(G, N, W, H, profile):
+    """SURVEY 8d unit (ii): project + cov3d + ewa + sort + blend(C=3) and the whole backward chain,
+    through autograd, against the C oracle (BASELINE configs 1 and 2)."""
+    sc = make_scene(N, W, H, seed=0, profile=profile, bg=0.1)
+    Gimg = make_grad_image(3, W, H)
+    img_o, g_o, info = C.render_step_fwd_bwd(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr, sc.bg,
+                                             W, H, Gimg)
+    ps = [t.to(DEV).requires_grad_(True) for t in (sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)]
+    xyz, scale, rot, op, rgb, intr, extr = ps
+    img = G.rasterization(xyz, scale, rot, op, rgb, intr, extr, W, H, sc.bg)
+    assert_close(img, img_o, 1e-4, "rendered image", **IMG_OUTLIERS)
+    (img * cu(Gimg)).sum().backward()
+    for name, p in zip(["xyz", "scale", "rotate", "opacity", "feature", "intr", "extr"], ps):
+        assert_close(p.grad, g_o[name], 1e-3, "grad " + name, **GRAD_OUTLIERS)
+
+
+def test_render_multiple_call_pattern(G):
+    """The exact call sequence of /root/reference/gflow/utils/render.py:6-108 (four blends that share one
+    sort, 'center' with replaced conic / opacity) through the drop-in module name."""
+    G.install_dropin()
+    import msplat
+
+    sc = make_scene(20000, 427, 240, seed=2, profile="gflow")
+    W, H, bg = sc.W, sc.H, 0.0
+    xyz, scale, rot, op, rgb, intr, extr = (t.to(DEV) for t in (sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb,
+                                                                sc.intr, sc.extr))
+    for t in (xyz, scale, rot, op, rgb, extr):
+        t.requires_grad_(True)
+    uv, depth = msplat.project_point(xyz, intr, extr, W, H)
+    visible = depth != 0
+    cov3d = msplat.compute_cov3d(scale, rot, visible)
+    conic, radius, tiles = msplat.ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible)
+    ids, rng = msplat.sort_gaussian(uv, depth, W, H, radius, tiles)
+    r_rgb = msplat.alpha_blending(uv, conic, op, rgb, ids, rng, bg, W, H)
+    r_depth = msplat.alpha_blending(uv, conic, op, depth, ids, rng, bg, W, H)
+    r_dc = msplat.alpha_blending(uv, conic, op, torch.rand_like(rgb), ids, rng, bg, W, H)
+    conic2 = torch.ones_like(conic) * torch.tensor([1.0, 0.0, 1.0], device=DEV)
+    r_center = msplat.alpha_blending(uv, conic2, torch.ones_like(op), rgb, ids, rng, bg, W, H)
+    assert r_rgb.shape == (3, H, W) and r_depth.shape == (1, H, W) and r_dc.shape == (3, H, W)
+    # oracle for the two renders that enter the loss
+    uv_o, d_o, vis_o, cov_o, con_o, rad_o, t_o, ids_o, rng_o = _geometry_oracle(sc)
+    assert torch.equal(ids.cpu(), ids_o)
+    assert_close(r_rgb, C.alpha_blending(uv_o, con_o, sc.opacity, sc.rgb, ids_o, rng_o, bg, W, H), 1e-4, "rgb",
+                 **IMG_OUTLIERS)
+    assert_close(r_depth, C.alpha_blending(uv_o, con_o, sc.opacity, d_o, ids_o, rng_o, bg, W, H), 1e-4, "depth map",
+                 **IMG_OUTLIERS)
+    conic2_o = torch.ones_like(con_o) * torch.tensor([1.0, 0.0, 1.0])
+    assert_close(r_center, C.alpha_blending(uv_o, conic2_o, torch.ones_like(sc.opacity), sc.rgb, ids_o, rng_o, bg, W, H),
+                 1e-4, "center", **IMG_OUTLIERS)
+    # loss over rgb + depth like trainer.py:452-488, gradient reaches the pose (fact 6)
+    (r_rgb.mean() + 0.1 * r_depth.mean()).backward()
+    assert extr.grad is not None and float(extr.grad.abs().sum()) > 0
+    assert xyz.grad.shape == xyz.shape and torch.isfinite(xyz.grad).all()
+
+
+def test_full_size_properties(G):
+    """Size-independent properties at BASELINE config 2 (60k, 854x480)."""
+    sc = make_scene(60000, 854, 480, seed=3, profile="synthetic")
+    W, H = sc.W, sc.H
+    xyz, scale, rot, op, rgb, intr, extr = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
+    uv, depth = G.project_point(xyz, intr, extr, W, H)
+    vis = depth != 0
+    cov = G.compute_cov3d(scale, rot, vis)
+    conic, radius, tiles = G.ewa_project(xyz, cov, intr, extr, uv, W, H, vis)
+    ids, rng = G.sort_gaussian(uv, depth, W, H, radius, tiles)
+    ids2, rng2 = G.sort_gaussian(uv, depth, W, H, radius, tiles)
+    assert torch.equal(ids, ids2) and torch.equal(rng, rng2), "sort must be deterministic"
+    K = ids.numel()
+    assert K == int(tiles.sum())
+    # ranges partition [0, K) and every segment is ordered by (depth bits, id)
+    r = rng.cpu().long()
+    nz = r[:, 1] > r[:, 0]
+    assert int((r[nz, 1] - r[nz, 0]).sum()) == K
+    assert torch.equal(r[nz, 0][1:], r[nz, 1][:-1]) and int(r[nz, 0][0]) == 0 and int(r[nz, 1][-1]) == K
+    dbits = depth.reshape(-1).view(torch.int32).long()
+    key = (dbits[ids.long()] << 32) | ids.long()
+    seg = torch.repeat_interleave(torch.arange(r.shape[0], device=DEV), (rng[:, 1] - rng[:, 0]).long())
+    same = seg[1:] == seg[:-1]
+    assert bool(((key[1:] > key[:-1]) | ~same).all()), "segments must be strictly ordered by (depth, id)"
+    # partition of unity: feature == 1, bg == 1  ->  sum_j alpha_j T_j + T_final == 1
+    ones = torch.ones(sc.xyz.shape[0], 1, device=DEV)
+    img1 = G.alpha_blending(uv, conic, op, ones, ids, rng, 1.0, W, H)
+    assert float((img1 - 1.0).abs().max()) < 1e-5
+    # linearity in the feature (bg = 0)
+    f1, f2 = torch.rand_like(rgb), torch.rand_like(rgb)
+    a = G.alpha_blending(uv, conic, op, f1, ids, rng, 0.0, W, H)
+    b = G.alpha_blending(uv, conic, op, f2, ids, rng, 0.0, W, H)
+    ab = G.alpha_blending(uv, conic, op, f1 + 2.0 * f2, ids, rng, 0.0, W, H)
+    assert float((ab - (a + 2.0 * b)).abs().max()) < 1e-5
+    # channel groups: a 7-channel blend equals its 3 + 4 channel slices
+    f7 = torch.rand(sc.xyz.shape[0], 7, device=DEV)
+    full = G.alpha_blending(uv, conic, op, f7, ids, rng, 0.5, W, H)
+    lo = G.alpha_blending(uv, conic, op, f7[:, :3].contiguous(), ids, rng, 0.5, W, H)
+    hi = G.alpha_blending(uv, conic, op, f7[:, 3:].contiguous(), ids, rng, 0.5, W, H)
+    assert float((full - torch.cat([lo, hi])).abs().max()) < 1e-6
+    # d(sum out)/d(feature_c) is the same for every channel and equals the summed blend weights
+    f = rgb.clone().requires_grad_(True)
+    G.alpha_blending(uv, conic, op, f, ids, rng, 0.0, W, H).sum().backward()
+    assert float((f.grad[:, 0] - f.grad[:, 1]).abs().max()) < 1e-4 * float(f.grad.abs().max())
+    total_w = float(f.grad[:, 0].sum())
+    sum_w = float(G.alpha_blending(uv, conic, op, ones, ids, rng, 0.0, W, H).sum())
+    assert abs(total_w - sum_w) < 1e-3 * abs(sum_w)
+
+
+def test_compute_sh(G):
+    gen = torch.Generator().manual_seed(5)
+    for K in (1, 4, 9, 16):
+        N = 5000
+        shs = torch.randn(N, 3, K, generator=gen)
+        dirs = torch.randn(N, 3, generator=gen) * 2.0
+        vis = torch.rand(N, 1, generator=gen) > 0.1
+        g = torch.randn(N, 3, generator=gen)
+        out_o = C.compute_sh(shs, dirs, vis)
+        d_shs_o, d_dirs_o = C.compute_sh_bwd(shs, dirs, vis, g)
+        s, d = shs.to(DEV).requires_grad_(True), dirs.to(DEV).requires_grad_(True)
+        out = G.compute_sh(s, d, cu(vis))
+        assert_close(out, out_o, 1e-5, f"sh K={K}")
+        (out * cu(g)).sum().backward()
+        assert_close(s.grad, d_shs_o, 1e-5, "d_shs")
+        assert_close(d.grad, d_dirs_o, 1e-4, "d_dirs")
+    out = G.compute_sh(s.detach(), d.detach())  # visible omitted
+    assert out.shape == (N, 3)
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "splat_*.npz"))))
+def test_cuda_reproduces_golden_vectors(G, name):
+    g = _load(name)
+    W, H, bg = g["W"], g["H"], g["bg"]
+    uv, depth = G.project_point(*cu(g["xyz"], g["intr"], g["extr"]), W, H)
+    assert torch.equal(uv.cpu(), g["uv"]) and torch.equal(depth.cpu(), g["depth"])
+    vis = depth != 0
+    cov = G.compute_cov3d(*cu(g["scale"], g["rotate"]), vis)
+    assert torch.equal(cov.cpu(), g["cov3d"])
+    conic, radius, tiles = G.ewa_project(*cu(g["xyz"]), cov, *cu(g["intr"], g["extr"]), uv, W, H, vis)
+    assert torch.equal(conic.cpu(), g["conic"]) and torch.equal(radius.cpu(), g["radius"])
+    assert torch.equal(tiles.cpu(), g["tiles"])
+    ids, rng = G.sort_gaussian(uv, depth, W, H, radius, tiles)
+    assert torch.equal(ids.cpu(), g["ids"]) and torch.equal(rng.cpu(), g["tile_range"])
+    u, c, o, f = (t.to(DEV).requires_grad_(True) for t in (g["uv"], g["conic"], g["opacity"], g["feature"]))
+    img = G.alpha_blending(u, c, o, f, ids, rng, bg, W, H)
+    assert_close(img, g["img"], 1e-4, "image")
+    (img * cu(g["g_img"])).sum().backward()
+    for t, k in ((u, "d_uv"), (c, "d_conic"), (o, "d_opacity"), (f, "d_feature")):
+        assert_close(t.grad, g[k], 1e-3, k)
+
+
+def test_error_behaviour(G):
+    x = torch.zeros(8, 3, device=DEV)
+    intr, extr = torch.ones(4, device=DEV), torch.eye(4, device=DEV)[:3]
+    with pytest.raises(RuntimeError, match="dtype"):
+        G.project_point(x.double(), intr, extr, 32, 32)
+    with pytest.raises(RuntimeError, match="shape"):
+        G.project_point(torch.zeros(8, 2, device=DEV), intr, extr, 32, 32)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        G.project_point(x.cpu(), intr, extr, 32, 32)
+    with pytest.raises(RuntimeError, match="shape"):
+        G.alpha_blending(torch.zeros(8, 2, device=DEV), torch.zeros(8, 3, device=DEV), torch.zeros(8, 1, device=DEV),
+                         torch.zeros(8, 3, device=DEV), torch.zeros(0, dtype=torch.int32, device=DEV),
+                         torch.zeros(3, 2, dtype=torch.int32, device=DEV), 0.0, 32, 32)
+    # non-contiguous / sliced inputs are accepted (trainer.py:430-434 passes boolean-masked subsets)
+    big = torch.rand(20, 6, device=DEV)
+    uv, depth = G.project_point(big[:, :3], intr, extr, 32, 32)
+    assert uv.shape == (20, 2)
