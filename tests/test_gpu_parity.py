@@ -14,6 +14,7 @@ import torch
 from conftest import assert_close
 from gflow_b200.synthetic import make_grad_image, make_scene
 from oracle import c_oracle as C
+from oracle import splat_ref as R
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -163,7 +164,9 @@ def test_sort_heavy_tile_all_size_classes(G, n_heavy):
     N = uv.shape[0]
     depth = torch.randint(1, 50, (N, 1), generator=gen).float() * 0.25  # many ties
     radius = torch.cat([torch.ones(n_heavy, 1), torch.randint(1, 9, (300, 1), generator=gen)]).to(torch.int32)
-    tiles = torch.ones(N, 1, dtype=torch.int32)  # only > 0 matters for sort_gaussian
+    # tiles_touched must be consistent with the rect rule (it sizes the output upstream)
+    x0, y0, x1, y1 = R._tile_rect(uv[:, 0], uv[:, 1], radius.reshape(-1).float(), W, H)
+    tiles = ((x1 - x0) * (y1 - y0)).to(torch.int32).reshape(N, 1)
     ids_o, rng_o = C.sort_gaussian(uv, depth, W, H, radius, tiles)
     ids, rng = G.sort_gaussian(*cu(uv, depth), W, H, *cu(radius, tiles))
     assert int(rng_o[0, 1] - rng_o[0, 0]) >= n_heavy
@@ -367,7 +370,7 @@ def test_cuda_reproduces_golden_vectors(G, name):
     vis = depth != 0
     cov = G.compute_cov3d(*cu(g["scale"], g["rotate"]), vis)
     assert torch.equal(cov.cpu(), g["cov3d"])
-    conic, radius, tiles = G.ewa_project(*cu(g["xyz"]), cov, *cu(g["intr"], g["extr"]), uv, W, H, vis)
+    conic, radius, tiles = G.ewa_project(cu(g["xyz"]), cov, *cu(g["intr"], g["extr"]), uv, W, H, vis)
     assert torch.equal(conic.cpu(), g["conic"]) and torch.equal(radius.cpu(), g["radius"])
     assert torch.equal(tiles.cpu(), g["tiles"])
     ids, rng = G.sort_gaussian(uv, depth, W, H, radius, tiles)
