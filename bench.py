@@ -235,12 +235,12 @@ def run_ours(args):
     params = [state[k].clone().requires_grad_(True) for k in ("xyz", "scale", "rotate", "opacity", "rgb")]
     extr_p = extr.clone().requires_grad_(True)
 
-    def step():
+    def step(raster=G.rasterization):
         for p in params:
             p.grad = None
         extr_p.grad = None
         xyz, scale, rot, op, rgb = params
-        img = G.rasterization(xyz, scale, rot, op, rgb, intr, extr_p, W, H, sc.bg)
+        img = raster(xyz, scale, rot, op, rgb, intr, extr_p, W, H, sc.bg)
         loss = (img * Gimg).sum()
         loss.backward()
         return loss
@@ -280,6 +280,20 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev = float(tt.item())
     value = world * args.steps / t_dev
+
+    # ---- the same step through the five separate operators, exactly as render.py:21-64 calls them
+    for _ in range(3):
+        step(G.rasterization_unfused)
+    barrier()
+    n_chain = max(5, min(args.steps, 50))
+    ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_chain)]
+    for a, b in ev3:
+        flush_l2()
+        a.record()
+        step(G.rasterization_unfused)
+        b.record()
+    barrier()
+    chain_ms = sum(a.elapsed_time(b) for a, b in ev3) / n_chain
 
     # ---- e2e: same step through the public API with HOST buffers (pinned), H2D of the step's
     #      inputs and D2H of loss + gradients inside the timed region
@@ -346,7 +360,10 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {N} Gaussians, {W}x{H}, render step fwd+bwd (C=3), profile {args.profile}",
                        "K": roof.pop("K"), "sharding": "one frame (camera + target) per rank, no in-loop collective",
                        "l2": "256 MiB written between timed steps" if not args.no_flush else "not flushed (working set < L2)",
-                       "api": "gflow_b200.ops (msplat surface) -> C ABI"},
+                       "api": "msplat.rasterization (gflow_b200.ops, fused pipeline) -> C ABI"},
+            "operator_chain": {"value": world * 1e3 / chain_ms, "unit": UNIT, "ms_per_step": chain_ms,
+                               "what": "same step through project_point/compute_cov3d/ewa_project/sort_gaussian/"
+                                       "alpha_blending called one by one (render.py:21-64 pattern)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e},
             "gpu_launches": int(launches),

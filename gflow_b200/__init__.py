@@ -15,6 +15,7 @@ from .ops import (  # noqa: F401
     ewa_project,
     project_point,
     rasterization,
+    rasterization_unfused,
     sort_gaussian,
 )
 

@@ -17,12 +17,11 @@
 //                    warp-shuffle compare-exchange for strides < 32), writes ids + range
 // K is ~3 N and segments are ~100 entries, so everything after step 1 stays in L2/SMEM.
 #include "common.cuh"
+#include "sort_network.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSortThreads = 128;
-constexpr int kSortSmemKeys = 4096;  // 32 KB of 64-bit keys per CTA
 
 __device__ __forceinline__ bool gaussian_rect(const float2* __restrict__ uv, const int32_t* __restrict__ radius,
                                               const int32_t* __restrict__ tiles_touched, int i, int gx, int gy,
@@ -103,81 +102,15 @@ bin_scatter_kernel(const float2* __restrict__ uv, const float* __restrict__ dept
         }
 }
 
-// Direction-free bitonic network: every compare-exchange puts the smaller key at the lower
-// index ("flip" first stage of each merge, then plain half-cleaners).  Because all exchanges are
-// ascending, virtual +inf keys at indices >= n never move, so pairs whose upper index is >= n
-// are skipped and no padding is stored.  `buf` may be shared or global memory; one CTA.
-__device__ void bitonic_sort_block(unsigned long long* buf, int n, int n_pad) {
-    for (int k = 2; k <= n_pad; k <<= 1) {
-        const int half = k >> 1;
-        for (int q = threadIdx.x; q < (n_pad >> 1); q += blockDim.x) {
-            const int blk = q / half, pos = q - blk * half;
-            const int lo = blk * k + pos, hi = blk * k + (k - 1 - pos);
-            if (hi < n) {
-                const unsigned long long a = buf[lo], b = buf[hi];
-                if (a > b) {
-                    buf[lo] = b;
-                    buf[hi] = a;
-                }
-            }
-        }
-        __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            for (int q = threadIdx.x; q < (n_pad >> 1); q += blockDim.x) {
-                const int lo = 2 * q - (q & (j - 1));
-                const int hi = lo + j;
-                if (hi < n) {
-                    const unsigned long long a = buf[lo], b = buf[hi];
-                    if (a > b) {
-                        buf[lo] = b;
-                        buf[hi] = a;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-__device__ __forceinline__ unsigned long long u64_min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
-__device__ __forceinline__ unsigned long long u64_max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
-
-// Segments of <= 64 keys: one warp, element e = lane (k0) and lane + 32 (k1); the same
-// direction-free network with every compare-exchange done by warp shuffle.
-__device__ __forceinline__ void warp_sort64(unsigned long long& k0, unsigned long long& k1, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 64; k <<= 1) {
-        if (k < 64) {
-            // flip stage: partner element e ^ (k-1), same register, lane ^ (k-1)
-            const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, k0, k - 1);
-            const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, k1, k - 1);
-            const bool lower = (lane & (k >> 1)) == 0;
-            k0 = lower ? u64_min(k0, p0) : u64_max(k0, p0);
-            k1 = lower ? u64_min(k1, p1) : u64_max(k1, p1);
-        } else {
-            // k == 64: partner of e is e ^ 63 -> the other register of lane ^ 31
-            const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, k1, 31);
-            const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, k0, 31);
-            k0 = u64_min(k0, p0);
-            k1 = u64_max(k1, p1);
-        }
-#pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, k0, j);
-            const unsigned long long p1 = __shfl_xor_sync(0xffffffffu, k1, j);
-            const bool lower = (lane & j) == 0;
-            k0 = lower ? u64_min(k0, p0) : u64_max(k0, p0);
-            k1 = lower ? u64_min(k1, p1) : u64_max(k1, p1);
-        }
-    }
-}
-
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_kernel(const int32_t* __restrict__ offsets, unsigned long long* __restrict__ keys,
-                 int32_t* __restrict__ ids_sorted, int2* __restrict__ tile_range, int T) {
+                 int32_t* __restrict__ ids_sorted, int2* __restrict__ tile_range, int T, long long capacity) {
     __shared__ unsigned long long s_keys[kSortSmemKeys];
     const int t = blockIdx.x;
-    const int start = offsets[t], end = offsets[t + 1];
+    const int start = offsets[t];
+    long long end_ll = offsets[t + 1];
+    if (end_ll > capacity) end_ll = max((long long)start, capacity);  // speculative capacity too small: host retries
+    const int end = (int)end_ll;
     const int n = end - start;
     if (threadIdx.x == 0) tile_range[t] = (n > 0) ? make_int2(start, end) : make_int2(0, 0);
     if (n <= 0) return;
@@ -242,9 +175,32 @@ int gfb_sort_emit(const float* uv, const float* depth, const int32_t* radius, co
         GFB_CHECK_LAUNCH();
     }
     tile_sort_kernel<<<T, kSortThreads, 0, st>>>(tile_offsets, keys, gaussian_ids_sorted,
-                                                 reinterpret_cast<int2*>(tile_range), T);
+                                                 reinterpret_cast<int2*>(tile_range), T, (long long)K);
     GFB_CHECK_LAUNCH();
     return 0;
+}
+
+int gfb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles_touched, int N,
+                      int W, int H, int32_t* tile_counts, int32_t* tile_offsets, int64_t capacity, void* keys_ws,
+                      int32_t* gaussian_ids_sorted, int32_t* tile_range, int64_t* K_host, void* stream) {
+    if (capacity < 0 || !K_host) return GFB_E_BADARG;
+    int32_t* pinned = nullptr;
+    cudaEvent_t ev = nullptr;
+    int rc = gfb_internal_host_sync(&pinned, &ev);
+    if (rc) return rc;
+    rc = gfb_sort_count(uv, radius, tiles_touched, N, W, H, tile_counts, tile_offsets, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = ((W + GFB_TILE - 1) / GFB_TILE) * ((H + GFB_TILE - 1) / GFB_TILE);
+    GFB_TRY(cudaMemcpyAsync(pinned, tile_offsets + T, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GFB_TRY(cudaEventRecord(ev, st));
+    // speculative: scatter + per-tile sort are enqueued with the caller's capacity before K is known
+    rc = gfb_sort_emit(uv, depth, radius, tiles_touched, N, W, H, tile_counts, tile_offsets, capacity, keys_ws,
+                       gaussian_ids_sorted, tile_range, stream);
+    if (rc) return rc;
+    GFB_TRY(cudaEventSynchronize(ev));  // waits for count + scan only
+    *K_host = (int64_t)pinned[0];
+    return (*K_host > capacity) ? GFB_E_CAPACITY : 0;
 }
 
 }  // extern "C"

@@ -26,7 +26,7 @@
 //    added with one RED per value into a packed 48-byte-per-Gaussian gradient record, so
 //    the (up to) ten atomics of a warp hit one or two L2 sectors.
 //  No tensor cores: this is a gather / scatter bounded by issue rate and L2 atomics.
-#include "common.cuh"
+#include "splat_math.cuh"
 
 namespace {
 
@@ -90,25 +90,8 @@ pack_geometry_kernel(const float2* __restrict__ uv, const float* __restrict__ co
     const float2 p = uv[id];
     const float a = conic[3 * id], b = conic[3 * id + 1], c = conic[3 * id + 2];
     const float o = opacity[id];
-    // alpha = o * exp(power) >= 1/255  <=>  d^T Q d <= 2 ln(255 o): an ellipse whose bbox has
-    // half extents sqrt(2 L c / det), sqrt(2 L a / det).  Never reaching 1/255 -> reject always;
-    // a conic that is not positive definite -> no culling.
-    float hx = -INFINITY, hy = -INFINITY;
-    const float o255 = 255.0f * o;
-    if (o255 >= 1.0f) {
-        const float det = a * c - b * b;
-        if (a > 0.0f && c > 0.0f && det > 0.0f) {
-            const float s = 2.0f * logf(o255) / det;
-            hx = sqrtf(s * c) * 1.0005f + 0.01f;  // conservative: rounding of log / sqrt / det
-            hy = sqrtf(s * a) * 1.0005f + 0.01f;
-        } else {
-            hx = INFINITY;
-            hy = INFINITY;
-        }
-    } else if (!(o255 < 1.0f)) {  // NaN opacity: keep the pair, let the blend arithmetic decide
-        hx = INFINITY;
-        hy = INFINITY;
-    }
+    float hx, hy;
+    gfbm::splat_bbox(a, b, c, o, hx, hy);
     sA[k] = make_float4(p.x, p.y, hx, hy);
     sB[k] = make_float4(a, b, c, o);
 }
@@ -383,7 +366,7 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                             if (alpha >= GFB_ALPHA_MIN) {
                                 act = true;
                                 const float4 f4 = st.F[jj];
-                                const float inv1ma = __frcp_rn(1.0f - alpha);
+                                const float inv1ma = __fdividef(1.0f, 1.0f - alpha);
                                 T = T * inv1ma;
                                 const float w = alpha * T;
                                 float dalpha = 0.0f;

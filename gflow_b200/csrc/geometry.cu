@@ -11,53 +11,19 @@
 // Reference interface: msplat.project_point / compute_cov3d / ewa_project /
 // compute_sh as called from /root/reference/gflow/utils/render.py:21-49,116-135 and
 // /root/reference/gflow/trainer.py:955.
-#include "common.cuh"
+#include "splat_math.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-
-// Block-wide sum of NV per-thread values, then one atomicAdd per value per block.
-template <int NV>
-__device__ __forceinline__ void block_reduce_atomic(float (&v)[NV], float* __restrict__ dst) {
-    __shared__ float s_part[kThreads / 32][NV];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = gfb_warp_sum(v[k]);
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) s_part[warp][k] = v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) acc += s_part[w][threadIdx.x];
-        if (acc != 0.0f) atomicAdd(dst + threadIdx.x, acc);
-    }
-}
+using namespace gfbm;
 
 // ------------------------------------------------------------------ project_point
-__device__ __forceinline__ bool project_one(const float* __restrict__ intr, const float* __restrict__ extr, int W,
-                                            int H, float nearest, float extent, float x, float y, float z, float& u,
-                                            float& v, float& xc, float& yc, float& zc) {
-    gfb_cam_point(extr, x, y, z, xc, yc, zc);
-    if (!(zc > nearest)) return false;
-    u = (intr[0] * xc) / zc + intr[2];
-    v = (intr[1] * yc) / zc + intr[3];
-    const float xn = u / (0.5f * (float)W) - 1.0f;
-    const float yn = v / (0.5f * (float)H) - 1.0f;
-    return (fabsf(xn) <= extent) && (fabsf(yn) <= extent);
-}
-
 __global__ void __launch_bounds__(kThreads)
 project_point_fwd_kernel(const float* __restrict__ xyz, const float* __restrict__ intr,
                          const float* __restrict__ extr, int N, int W, int H, float nearest, float extent,
                          float2* __restrict__ uv, float* __restrict__ depth) {
     __shared__ float s_cam[16];
-    if (threadIdx.x < 12) s_cam[threadIdx.x] = extr[threadIdx.x];
-    if (threadIdx.x >= 12 && threadIdx.x < 16) s_cam[threadIdx.x] = intr[threadIdx.x - 12];
-    __syncthreads();
+    load_camera(s_cam, intr, extr);
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= N) return;
     float u, v, xc, yc, zc;
@@ -73,11 +39,7 @@ project_point_bwd_kernel(const float* __restrict__ xyz, const float* __restrict_
                          const float2* __restrict__ g_uv, const float* __restrict__ g_depth,
                          float* __restrict__ d_xyz, float* __restrict__ d_cam /* 12 extr + 4 intr */) {
     __shared__ float s_cam[16];
-    if (threadIdx.x < 12) s_cam[threadIdx.x] = extr[threadIdx.x];
-    if (threadIdx.x >= 12 && threadIdx.x < 16) s_cam[threadIdx.x] = intr[threadIdx.x - 12];
-    __syncthreads();
-    const float* e = s_cam;
-    const float* in = s_cam + 12;
+    load_camera(s_cam, intr, extr);
     const int i = blockIdx.x * kThreads + threadIdx.x;
     float acc[16];
 #pragma unroll
@@ -85,46 +47,19 @@ project_point_bwd_kernel(const float* __restrict__ xyz, const float* __restrict_
     if (i < N) {
         const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
         float u, v, xc, yc, zc;
-        const bool ok = project_one(in, e, W, H, nearest, extent, x, y, z, u, v, xc, yc, zc);
-        float dx = 0.0f, dy = 0.0f, dz = 0.0f;
-        if (ok) {
+        float dp[3] = {0.0f, 0.0f, 0.0f};
+        if (project_one(s_cam + 12, s_cam, W, H, nearest, extent, x, y, z, u, v, xc, yc, zc)) {
             const float2 g = g_uv[i];
-            const float gd = g_depth ? g_depth[i] : 0.0f;
-            const float iz = 1.0f / zc;
-            const float gx = in[0] * iz * g.x;
-            const float gy = in[1] * iz * g.y;
-            const float gz = -(in[0] * xc * iz * iz) * g.x - (in[1] * yc * iz * iz) * g.y + gd;
-            dx = e[0] * gx + e[4] * gy + e[8] * gz;
-            dy = e[1] * gx + e[5] * gy + e[9] * gz;
-            dz = e[2] * gx + e[6] * gy + e[10] * gz;
-            acc[0] = gx * x; acc[1] = gx * y; acc[2] = gx * z; acc[3] = gx;
-            acc[4] = gy * x; acc[5] = gy * y; acc[6] = gy * z; acc[7] = gy;
-            acc[8] = gz * x; acc[9] = gz * y; acc[10] = gz * z; acc[11] = gz;
-            acc[12] = g.x * xc * iz;
-            acc[13] = g.y * yc * iz;
-            acc[14] = g.x;
-            acc[15] = g.y;
+            project_bwd_one(s_cam + 12, s_cam, x, y, z, xc, yc, zc, g.x, g.y, g_depth ? g_depth[i] : 0.0f, dp, acc);
         }
-        d_xyz[3 * i] = dx;
-        d_xyz[3 * i + 1] = dy;
-        d_xyz[3 * i + 2] = dz;
+        d_xyz[3 * i] = dp[0];
+        d_xyz[3 * i + 1] = dp[1];
+        d_xyz[3 * i + 2] = dp[2];
     }
     block_reduce_atomic<16>(acc, d_cam);
 }
 
 // ------------------------------------------------------------------ compute_cov3d
-__device__ __forceinline__ void quat_rot(float w, float x, float y, float z, float* R) {
-    R[0] = 1.0f - 2.0f * (y * y + z * z);
-    R[1] = 2.0f * (x * y - w * z);
-    R[2] = 2.0f * (x * z + w * y);
-    R[3] = 2.0f * (x * y + w * z);
-    R[4] = 1.0f - 2.0f * (x * x + z * z);
-    R[5] = 2.0f * (y * z - w * x);
-    R[6] = 2.0f * (x * z - w * y);
-    R[7] = 2.0f * (y * z + w * x);
-    R[8] = 1.0f - 2.0f * (x * x + y * y);
-}
-
 __global__ void __launch_bounds__(kThreads)
 compute_cov3d_fwd_kernel(const float* __restrict__ scale, const float4* __restrict__ rotate,
                          const uint8_t* __restrict__ visible, int N, float* __restrict__ cov3d) {
@@ -132,20 +67,8 @@ compute_cov3d_fwd_kernel(const float* __restrict__ scale, const float4* __restri
     if (i >= N) return;
     float o[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     if (!visible || visible[i]) {
-        const float4 q = rotate[i];
         const float s[3] = {scale[3 * i], scale[3 * i + 1], scale[3 * i + 2]};
-        float R[9], M[9];
-        quat_rot(q.x, q.y, q.z, q.w, R);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) M[3 * r + c] = R[3 * r + c] * s[c];
-        o[0] = (M[0] * M[0] + M[1] * M[1]) + M[2] * M[2];
-        o[1] = (M[0] * M[3] + M[1] * M[4]) + M[2] * M[5];
-        o[2] = (M[0] * M[6] + M[1] * M[7]) + M[2] * M[8];
-        o[3] = (M[3] * M[3] + M[4] * M[4]) + M[5] * M[5];
-        o[4] = (M[3] * M[6] + M[4] * M[7]) + M[5] * M[8];
-        o[5] = (M[6] * M[6] + M[7] * M[7]) + M[8] * M[8];
+        cov3d_fwd_one(s, rotate[i], o);
     }
     float2* dst = reinterpret_cast<float2*>(cov3d + 6 * (size_t)i);  // 24 B records are 8 B aligned
     dst[0] = make_float2(o[0], o[1]);
@@ -162,39 +85,10 @@ compute_cov3d_bwd_kernel(const float* __restrict__ scale, const float4* __restri
     float ds[3] = {0.0f, 0.0f, 0.0f};
     float4 dq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (!visible || visible[i]) {
-        const float4 q4 = rotate[i];
-        const float w = q4.x, x = q4.y, y = q4.z, z = q4.w;
         const float s[3] = {scale[3 * i], scale[3 * i + 1], scale[3 * i + 2]};
-        const float2* gp = reinterpret_cast<const float2*>(g_cov3d + 6 * (size_t)i);
-        const float2 g01 = gp[0], g23 = gp[1], g45 = gp[2];
-        const float g[6] = {g01.x, g01.y, g23.x, g23.y, g45.x, g45.y};
-        float R[9], M[9], Gs[9], dM[9], D[9];
-        quat_rot(w, x, y, z, R);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) M[3 * r + c] = R[3 * r + c] * s[c];
-        Gs[0] = 2.0f * g[0]; Gs[1] = g[1]; Gs[2] = g[2];
-        Gs[3] = g[1]; Gs[4] = 2.0f * g[3]; Gs[5] = g[4];
-        Gs[6] = g[2]; Gs[7] = g[4]; Gs[8] = 2.0f * g[5];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                dM[3 * r + c] = Gs[3 * r] * M[c] + Gs[3 * r + 1] * M[3 + c] + Gs[3 * r + 2] * M[6 + c];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) ds[c] = dM[c] * R[c] + dM[3 + c] * R[3 + c] + dM[6 + c] * R[6 + c];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) D[3 * r + c] = dM[3 * r + c] * s[c];
-        dq.x = 2.0f * (-z * D[1] + y * D[2] + z * D[3] - x * D[5] - y * D[6] + x * D[7]);
-        dq.y = 2.0f * (y * D[1] + z * D[2] + y * D[3] - 2.0f * x * D[4] - w * D[5] + z * D[6] + w * D[7] -
-                       2.0f * x * D[8]);
-        dq.z = 2.0f * (-2.0f * y * D[0] + x * D[1] + w * D[2] + x * D[3] + z * D[5] - w * D[6] + z * D[7] -
-                       2.0f * y * D[8]);
-        dq.w = 2.0f * (-2.0f * z * D[0] - w * D[1] + x * D[2] + w * D[3] - 2.0f * z * D[4] + y * D[5] + x * D[6] +
-                       y * D[7]);
+        float g[6];
+        load_cov3d(g_cov3d, i, g);
+        cov3d_bwd_one(s, rotate[i], g, ds, dq);
     }
     d_scale[3 * i] = ds[0];
     d_scale[3 * i + 1] = ds[1];
@@ -203,72 +97,13 @@ compute_cov3d_bwd_kernel(const float* __restrict__ scale, const float4* __restri
 }
 
 // ------------------------------------------------------------------ ewa_project
-struct EwaMid {
-    float tx, ty, tz, txc, tyc, j00, j02, j11, j12, T0[3], T1[3], a, b, c, det;
-    bool clampx, clampy;
-};
-
-__device__ __forceinline__ void ewa_mid_eval(const float* p, const float* S, const float* __restrict__ intr,
-                                             const float* __restrict__ e, int W, int H, EwaMid& m) {
-    const float fx = intr[0], fy = intr[1];
-    gfb_cam_point(e, p[0], p[1], p[2], m.tx, m.ty, m.tz);
-    const float limx = GFB_FRUSTUM_CLAMP * ((float)W / (2.0f * fx));
-    const float limy = GFB_FRUSTUM_CLAMP * ((float)H / (2.0f * fy));
-    const float rx = m.tx / m.tz, ry = m.ty / m.tz;
-    m.clampx = (rx < -limx) || (rx > limx);
-    m.clampy = (ry < -limy) || (ry > limy);
-    m.txc = fminf(limx, fmaxf(-limx, rx)) * m.tz;
-    m.tyc = fminf(limy, fmaxf(-limy, ry)) * m.tz;
-    m.j00 = fx / m.tz;
-    m.j02 = -(fx * m.txc) / (m.tz * m.tz);
-    m.j11 = fy / m.tz;
-    m.j12 = -(fy * m.tyc) / (m.tz * m.tz);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        m.T0[k] = m.j00 * e[k] + m.j02 * e[8 + k];
-        m.T1[k] = m.j11 * e[4 + k] + m.j12 * e[8 + k];
-    }
-    const float* T0 = m.T0;
-    const float* T1 = m.T1;
-    const float a0 = (S[0] * T0[0] + S[1] * T0[1]) + S[2] * T0[2];
-    const float a1 = (S[1] * T0[0] + S[3] * T0[1]) + S[4] * T0[2];
-    const float a2 = (S[2] * T0[0] + S[4] * T0[1]) + S[5] * T0[2];
-    const float b0 = (S[0] * T1[0] + S[1] * T1[1]) + S[2] * T1[2];
-    const float b1 = (S[1] * T1[0] + S[3] * T1[1]) + S[4] * T1[2];
-    const float b2 = (S[2] * T1[0] + S[4] * T1[1]) + S[5] * T1[2];
-    m.a = ((T0[0] * a0 + T0[1] * a1) + T0[2] * a2) + GFB_COV_BLUR;
-    m.b = (T1[0] * a0 + T1[1] * a1) + T1[2] * a2;
-    m.c = ((T1[0] * b0 + T1[1] * b1) + T1[2] * b2) + GFB_COV_BLUR;
-    m.det = m.a * m.c - m.b * m.b;
-}
-
-__device__ __forceinline__ void load_cov3d(const float* __restrict__ cov3d, int i, float* S) {
-    const float2* sp = reinterpret_cast<const float2*>(cov3d + 6 * (size_t)i);
-    const float2 s01 = sp[0], s23 = sp[1], s45 = sp[2];
-    S[0] = s01.x; S[1] = s01.y; S[2] = s23.x; S[3] = s23.y; S[4] = s45.x; S[5] = s45.y;
-}
-
-// Returns true when the Gaussian is live (visible, det != 0, touches >= 1 tile).
-__device__ __forceinline__ bool ewa_live(const EwaMid& m, float2 uv, int gx, int gy, float& rf, int& area) {
-    if (m.det == 0.0f) return false;
-    const float mid = 0.5f * (m.a + m.c);
-    const float lam = mid + sqrtf(fmaxf(0.1f, mid * mid - m.det));
-    rf = ceilf(3.0f * sqrtf(lam));
-    int x0, y0, x1, y1;
-    gfb_tile_rect(uv.x, uv.y, rf, gx, gy, x0, y0, x1, y1);
-    area = (x1 - x0) * (y1 - y0);
-    return area > 0;
-}
-
 __global__ void __launch_bounds__(kThreads)
 ewa_project_fwd_kernel(const float* __restrict__ xyz, const float* __restrict__ cov3d,
                        const float* __restrict__ intr, const float* __restrict__ extr,
                        const float2* __restrict__ uv, int N, int W, int H, const uint8_t* __restrict__ visible,
                        float* __restrict__ conic, int32_t* __restrict__ radius, int32_t* __restrict__ tiles_touched) {
     __shared__ float s_cam[16];
-    if (threadIdx.x < 12) s_cam[threadIdx.x] = extr[threadIdx.x];
-    if (threadIdx.x >= 12 && threadIdx.x < 16) s_cam[threadIdx.x] = intr[threadIdx.x - 12];
-    __syncthreads();
+    load_camera(s_cam, intr, extr);
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= N) return;
     float ca = 0.0f, cb = 0.0f, cc = 0.0f;
@@ -280,14 +115,15 @@ ewa_project_fwd_kernel(const float* __restrict__ xyz, const float* __restrict__ 
         EwaMid m;
         ewa_mid_eval(p, S, s_cam + 12, s_cam, W, H, m);
         float rf;
-        int area;
-        if (ewa_live(m, uv[i], (W + GFB_TILE - 1) / GFB_TILE, (H + GFB_TILE - 1) / GFB_TILE, rf, area)) {
+        int x0, y0, x1, y1;
+        const float2 q = uv[i];
+        if (ewa_live(m, q.x, q.y, (W + GFB_TILE - 1) / GFB_TILE, (H + GFB_TILE - 1) / GFB_TILE, rf, x0, y0, x1, y1)) {
             const float dinv = 1.0f / m.det;
             ca = m.c * dinv;
             cb = -m.b * dinv;
             cc = m.a * dinv;
             rad = (int)rf;
-            tiles = area;
+            tiles = (x1 - x0) * (y1 - y0);
         }
     }
     conic[3 * i] = ca;
@@ -304,11 +140,7 @@ ewa_project_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ 
                        const float* __restrict__ g_conic, float* __restrict__ d_xyz, float* __restrict__ d_cov3d,
                        float* __restrict__ d_cam /* 12 extr + 4 intr (only [12],[13] used) */) {
     __shared__ float s_cam[16];
-    if (threadIdx.x < 12) s_cam[threadIdx.x] = extr[threadIdx.x];
-    if (threadIdx.x >= 12 && threadIdx.x < 16) s_cam[threadIdx.x] = intr[threadIdx.x - 12];
-    __syncthreads();
-    const float* e = s_cam;
-    const float* in = s_cam + 12;
+    load_camera(s_cam, intr, extr);
     const int i = blockIdx.x * kThreads + threadIdx.x;
     float acc[14];
 #pragma unroll
@@ -316,72 +148,19 @@ ewa_project_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ 
     if (i < N) {
         float dp[3] = {0.0f, 0.0f, 0.0f};
         float dS[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        bool live = (!visible || visible[i]);
-        EwaMid m;
-        float p[3], S[6];
-        if (live) {
-            p[0] = xyz[3 * i]; p[1] = xyz[3 * i + 1]; p[2] = xyz[3 * i + 2];
+        if (!visible || visible[i]) {
+            const float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+            float S[6];
             load_cov3d(cov3d, i, S);
-            ewa_mid_eval(p, S, in, e, W, H, m);
+            EwaMid m;
+            ewa_mid_eval(p, S, s_cam + 12, s_cam, W, H, m);
             float rf;
-            int area;
-            live = ewa_live(m, uv[i], (W + GFB_TILE - 1) / GFB_TILE, (H + GFB_TILE - 1) / GFB_TILE, rf, area);
-        }
-        if (live) {
-            const float gA = g_conic[3 * i], gB = g_conic[3 * i + 1], gC = g_conic[3 * i + 2];
-            const float a = m.a, b = m.b, c = m.c, dinv = 1.0f / m.det, d2 = dinv * dinv;
-            const float ga = d2 * (-c * c * gA + b * c * gB) + gC * (dinv - a * c * d2);
-            const float gb = 2.0f * b * c * d2 * gA + gB * (-dinv - 2.0f * b * b * d2) + 2.0f * a * b * d2 * gC;
-            const float gc = gA * (dinv - a * c * d2) + a * b * d2 * gB - a * a * d2 * gC;
-            const float* T0 = m.T0;
-            const float* T1 = m.T1;
-            dS[0] = ga * T0[0] * T0[0] + gb * T0[0] * T1[0] + gc * T1[0] * T1[0];
-            dS[3] = ga * T0[1] * T0[1] + gb * T0[1] * T1[1] + gc * T1[1] * T1[1];
-            dS[5] = ga * T0[2] * T0[2] + gb * T0[2] * T1[2] + gc * T1[2] * T1[2];
-            dS[1] = 2.0f * ga * T0[0] * T0[1] + gb * (T0[0] * T1[1] + T0[1] * T1[0]) + 2.0f * gc * T1[0] * T1[1];
-            dS[2] = 2.0f * ga * T0[0] * T0[2] + gb * (T0[0] * T1[2] + T0[2] * T1[0]) + 2.0f * gc * T1[0] * T1[2];
-            dS[4] = 2.0f * ga * T0[1] * T0[2] + gb * (T0[1] * T1[2] + T0[2] * T1[1]) + 2.0f * gc * T1[1] * T1[2];
-            float ST0[3], ST1[3], dT0[3], dT1[3];
-            ST0[0] = S[0] * T0[0] + S[1] * T0[1] + S[2] * T0[2];
-            ST0[1] = S[1] * T0[0] + S[3] * T0[1] + S[4] * T0[2];
-            ST0[2] = S[2] * T0[0] + S[4] * T0[1] + S[5] * T0[2];
-            ST1[0] = S[0] * T1[0] + S[1] * T1[1] + S[2] * T1[2];
-            ST1[1] = S[1] * T1[0] + S[3] * T1[1] + S[4] * T1[2];
-            ST1[2] = S[2] * T1[0] + S[4] * T1[1] + S[5] * T1[2];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                dT0[k] = 2.0f * ga * ST0[k] + gb * ST1[k];
-                dT1[k] = 2.0f * gc * ST1[k] + gb * ST0[k];
-            }
-            float dj00 = 0.0f, dj02 = 0.0f, dj11 = 0.0f, dj12 = 0.0f, dR[9];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                dj00 += dT0[k] * e[k];
-                dj02 += dT0[k] * e[8 + k];
-                dj11 += dT1[k] * e[4 + k];
-                dj12 += dT1[k] * e[8 + k];
-                dR[k] = dT0[k] * m.j00;
-                dR[3 + k] = dT1[k] * m.j11;
-                dR[6 + k] = dT0[k] * m.j02 + dT1[k] * m.j12;
-            }
-            const float fx = in[0], fy = in[1], iz = 1.0f / m.tz, iz2 = iz * iz, iz3 = iz2 * iz;
-            acc[12] = dj00 * iz - dj02 * m.txc * iz2;
-            acc[13] = dj11 * iz - dj12 * m.tyc * iz2;
-            const float dtxc = -dj02 * fx * iz2, dtyc = -dj12 * fy * iz2;
-            float dtz = -dj00 * fx * iz2 + 2.0f * dj02 * fx * m.txc * iz3 - dj11 * fy * iz2 +
-                        2.0f * dj12 * fy * m.tyc * iz3;
-            float dtx = 0.0f, dty = 0.0f;
-            if (m.clampx) dtz += dtxc * (m.txc * iz); else dtx = dtxc;
-            if (m.clampy) dtz += dtyc * (m.tyc * iz); else dty = dtyc;
-            const float dt[3] = {dtx, dty, dtz};
-#pragma unroll
-            for (int k = 0; k < 3; ++k) dp[k] = e[k] * dt[0] + e[4 + k] * dt[1] + e[8 + k] * dt[2];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) acc[4 * r + k] = dR[3 * r + k] + dt[r] * p[k];
-                acc[4 * r + 3] = dt[r];
-            }
+            int x0, y0, x1, y1;
+            const float2 q = uv[i];
+            if (ewa_live(m, q.x, q.y, (W + GFB_TILE - 1) / GFB_TILE, (H + GFB_TILE - 1) / GFB_TILE, rf, x0, y0, x1,
+                         y1))
+                ewa_bwd_one(m, p, S, s_cam + 12, s_cam, g_conic[3 * i], g_conic[3 * i + 1], g_conic[3 * i + 2], dp,
+                            dS, acc);
         }
         d_xyz[3 * i] = dp[0];
         d_xyz[3 * i + 1] = dp[1];

@@ -216,12 +216,24 @@ def ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible=None):
 
 
 # --------------------------------------------------------------------------- sort_gaussian
+import ctypes as _ctypes
+
+_K_HINT = {}  # (device index, N, W, H) -> last K: sizes the speculative buffers of the next call
+GFB_E_CAPACITY = -3
+
+
+def _capacity_for(key, N):
+    k = _K_HINT.get(key)
+    return (4 * N + 4096) if k is None else (k + k // 4 + 4096)
+
+
 @torch.no_grad()
 def sort_gaussian(uv, depth, W, H, radius, tiles_touched):
     """msplat.sort_gaussian -- /root/reference/gflow/utils/render.py:52-54.
 
-    Returns gaussian_ids_sorted (K,) int32 and tile_range (T,2) int32.  One 4-byte
-    device->host read (K) is unavoidable because the API returns a tensor of exactly K entries.
+    Returns gaussian_ids_sorted (K,) int32 and tile_range (T,2) int32.  K must reach the host because
+    the API returns a tensor of exactly K entries; the read-back is hidden behind the scatter + sort
+    kernels, which are enqueued speculatively with the previous call's K (plus slack) as capacity.
     """
     W, H = int(W), int(H)
     uv_c = _prep(uv, "uv", shape=(None, 2))
@@ -234,19 +246,27 @@ def sort_gaussian(uv, depth, W, H, radius, tiles_touched):
     dev = _same_device(uv_c, depth_c, radius_c, tiles_c)
     gx, gy = _grid(W, H)
     T = gx * gy
+    key = (dev.index, N, W, H)
+    cap = _capacity_for(key, N)
+    k_host = _ctypes.c_int64(0)
     with torch.cuda.device(dev):
-        counts = torch.empty(T, device=dev, dtype=torch.int32)
-        offsets = torch.empty(T + 1, device=dev, dtype=torch.int32)
-        capi.check(_lib.gfb_sort_count(uv_c.data_ptr(), radius_c.data_ptr(), tiles_c.data_ptr(), N, W, H,
-                                       counts.data_ptr(), offsets.data_ptr(), _stream()), "sort_gaussian count")
-        K = int(offsets[T].item())
-        keys = torch.empty(max(K, 1), device=dev, dtype=torch.int64)
-        ids = torch.empty(K, device=dev, dtype=torch.int32)
+        tile_buf = torch.empty(2 * T + 1, device=dev, dtype=torch.int32)  # counts | offsets
         tile_range = torch.empty(T, 2, device=dev, dtype=torch.int32)
-        capi.check(_lib.gfb_sort_emit(uv_c.data_ptr(), depth_c.data_ptr(), radius_c.data_ptr(), tiles_c.data_ptr(), N,
-                                      W, H, counts.data_ptr(), offsets.data_ptr(), K, keys.data_ptr(), ids.data_ptr(),
-                                      tile_range.data_ptr(), _stream()), "sort_gaussian emit")
-    return ids, tile_range
+        while True:
+            keys = torch.empty(max(cap, 1), device=dev, dtype=torch.int64)
+            ids = torch.empty(max(cap, 1), device=dev, dtype=torch.int32)
+            rc = _lib.gfb_sort_gaussian(uv_c.data_ptr(), depth_c.data_ptr(), radius_c.data_ptr(), tiles_c.data_ptr(),
+                                        N, W, H, tile_buf.data_ptr(), tile_buf.data_ptr() + 4 * T, cap,
+                                        keys.data_ptr(), ids.data_ptr(), tile_range.data_ptr(),
+                                        _ctypes.byref(k_host), _stream())
+            K = int(k_host.value)
+            if rc == GFB_E_CAPACITY:
+                cap = K + K // 8 + 1024
+                continue
+            capi.check(rc, "sort_gaussian")
+            break
+    _K_HINT[key] = K
+    return ids[:K], tile_range
 
 
 # --------------------------------------------------------------------------- alpha_blending
@@ -421,12 +441,102 @@ def compute_sh(shs, dirs, visible=None):
 
 
 # --------------------------------------------------------------------------- rasterization
-def rasterization(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):
-    """Convenience chain of the five ops (upstream msplat.rasterization); same order as
-    /root/reference/gflow/utils/render.py:21-64."""
+class _Rasterize(torch.autograd.Function):
+    """Fused chain (gfb_render_forward / gfb_render_backward): 4 + 2 kernels, no mid-pipeline drain."""
+
+    @staticmethod
+    def forward(ctx, xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg, nearest, extent):
+        xyz_c = _prep(xyz, "xyz", shape=(None, 3))
+        N = xyz_c.shape[0]
+        scale_c = _prep(scale, "scale", shape=(N, 3))
+        rotate_c = _prep(rotate, "rotate", shape=(N, 4))
+        opacity_c = _prep(opacity, "opacity").reshape(-1)
+        if opacity_c.numel() != N:
+            raise RuntimeError(f"gflow_b200: opacity must have {N} elements, got {opacity_c.numel()}")
+        feature_c = _prep(feature, "feature", shape=(N, None))
+        C = feature_c.shape[1]
+        intr_c = _prep(intr, "intr", shape=(4,))
+        extr_c = _prep(extr, "extr", shape=(3, 4))
+        dev = _same_device(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr_c)
+        gx, gy = _grid(W, H)
+        T = gx * gy
+        key = (dev.index, N, W, H)
+        cap = _capacity_for(key, N)
+        k_host = _ctypes.c_int64(0)
+        with torch.cuda.device(dev):
+            # per-Gaussian buffer (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N
+            gbuf = torch.empty(9 * max(N, 1), device=dev, dtype=torch.float32)
+            gp = gbuf.data_ptr()
+            p_uv, p_rect, p_depth, p_conic, p_radius = gp, gp + 8 * N, gp + 16 * N, gp + 20 * N, gp + 32 * N
+            # tile buffer (int32): range 2T (8-byte aligned) | offsets T+1 | control T+4
+            tbuf = torch.empty(4 * T + 8, device=dev, dtype=torch.int32)
+            tp = tbuf.data_ptr()
+            p_rng, p_off, p_ctl = tp, tp + 8 * T, tp + 4 * (3 * T + 1)
+            out = torch.empty(C, H, W, device=dev, dtype=torch.float32)
+            aux = torch.empty(2, H, W, device=dev, dtype=torch.float32)  # final_T | n_contrib (int32 bits)
+            while True:
+                # K-sized buffer (bytes): geom 32c | feat 16c | keys 8c | ids 4c
+                kbuf = torch.empty(15 * max(cap, 1), device=dev, dtype=torch.float32)
+                kp = kbuf.data_ptr()
+                rc = _lib.gfb_render_forward(
+                    xyz_c.data_ptr(), scale_c.data_ptr(), rotate_c.data_ptr(), opacity_c.data_ptr(),
+                    feature_c.data_ptr(), C, intr_c.data_ptr(), extr_c.data_ptr(), N, W, H, bg, nearest, extent,
+                    p_uv, p_depth, p_conic, p_radius, p_rect, p_ctl, p_off, p_rng, cap, kp + 48 * cap, kp + 56 * cap,
+                    kp, kp + 32 * cap, out.data_ptr(), aux.data_ptr(), aux.data_ptr() + 4 * H * W,
+                    _ctypes.byref(k_host), _stream())
+                K = int(k_host.value)
+                if rc == GFB_E_CAPACITY:
+                    cap = K + K // 8 + 1024
+                    continue
+                capi.check(rc, "rasterization forward")
+                break
+        _K_HINT[key] = K
+        ctx.save_for_backward(xyz_c, scale_c, rotate_c, intr_c, extr_c, kbuf, tbuf, aux)
+        ctx.meta = (N, C, T, cap, W, H, bg, nearest, extent)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        xyz, scale, rotate, intr, extr, kbuf, tbuf, aux = ctx.saved_tensors
+        N, C, T, cap, W, H, bg, nearest, extent = ctx.meta
+        dev = xyz.device
+        with torch.cuda.device(dev):
+            g_out = _prep(g_out, "grad feature_map", shape=(C, H, W))
+            grad_ws = torch.empty(12 * N + 16, device=dev, dtype=torch.float32)
+            # d_rotate 4N | d_xyz 3N | d_scale 3N | d_opacity N | d_feature CN
+            dbuf = torch.empty((11 + C) * max(N, 1), device=dev, dtype=torch.float32)
+            dp = dbuf.data_ptr()
+            kp, tp = kbuf.data_ptr(), tbuf.data_ptr()
+            capi.check(_lib.gfb_render_backward(
+                xyz.data_ptr(), scale.data_ptr(), rotate.data_ptr(), intr.data_ptr(), extr.data_ptr(), N, W, H, C, bg,
+                nearest, extent, kp + 56 * cap, tp, cap, kp, kp + 32 * cap, aux.data_ptr(),
+                aux.data_ptr() + 4 * H * W, g_out.data_ptr(), grad_ws.data_ptr(), dp + 16 * N, dp + 28 * N, dp,
+                dp + 40 * N, dp + 44 * N, _stream()), "rasterization backward")
+        d_rotate = dbuf[:4 * N].view(N, 4)
+        d_xyz = dbuf[4 * N:7 * N].view(N, 3)
+        d_scale = dbuf[7 * N:10 * N].view(N, 3)
+        d_opacity = dbuf[10 * N:11 * N].view(N, 1)
+        d_feature = dbuf[11 * N:(11 + C) * N].view(N, C)
+        d_cam = grad_ws[12 * N:]
+        return (d_xyz, d_scale, d_rotate, d_opacity, d_feature, d_cam[12:16], d_cam[:12].view(3, 4), None, None, None,
+                None, None)
+
+
+def rasterization_unfused(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):
+    """The five operators one after the other, exactly as /root/reference/gflow/utils/render.py:21-64 calls them."""
     uv, depth = project_point(xyz, intr, extr, W, H)
     visible = depth != 0
     cov3d = compute_cov3d(scale, rotate, visible)
     conic, radius, tiles_touched = ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible)
     ids, tile_range = sort_gaussian(uv, depth, W, H, radius, tiles_touched)
     return alpha_blending(uv, conic, opacity, feature, ids, tile_range, bg, W, H)
+
+
+def rasterization(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):
+    """Upstream's convenience `msplat.rasterization`: world-space Gaussians -> (C,H,W) image.
+
+    Up to four channels run through the fused pipeline; more channels fall back to the operator chain.
+    """
+    if isinstance(feature, torch.Tensor) and feature.dim() == 2 and 1 <= feature.shape[1] <= 4:
+        return _Rasterize.apply(xyz, scale, rotate, opacity, feature, intr, extr, int(W), int(H), float(bg), 0.2, 1.3)
+    return rasterization_unfused(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg)

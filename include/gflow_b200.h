@@ -33,6 +33,7 @@ extern "C" {
 #define GFB_TILE 16
 #define GFB_E_BADARG (-1)     /* NULL pointer / negative size / unsupported channel count */
 #define GFB_E_UNSUPPORTED (-2)
+#define GFB_E_CAPACITY (-3)    /* K exceeded the caller's capacity: outputs are truncated, retry larger */
 
 /* library / build information */
 int gfb_version(void);                 /* 100 * major + minor */
@@ -92,6 +93,14 @@ int gfb_sort_emit(const float *uv, const float *depth, const int32_t *radius, co
                   int W, int H, int32_t *tile_counts, const int32_t *tile_offsets, int64_t K, void *keys_ws,
                   int32_t *gaussian_ids_sorted, int32_t *tile_range, void *stream);
 
+/* One-call variant that hides the K read-back: the caller passes a capacity (e.g. its previous K
+ * plus slack) for keys_ws / gaussian_ids_sorted; scatter + sort are enqueued speculatively, the
+ * host waits only for count + scan, *K_host receives K.  Returns GFB_E_CAPACITY when K > capacity
+ * (outputs truncated; call again with capacity >= *K_host).  Synchronises on an internal event. */
+int gfb_sort_gaussian(const float *uv, const float *depth, const int32_t *radius, const int32_t *tiles_touched, int N,
+                      int W, int H, int32_t *tile_counts, int32_t *tile_offsets, int64_t capacity, void *keys_ws,
+                      int32_t *gaussian_ids_sorted, int32_t *tile_range, int64_t *K_host, void *stream);
+
 /* ------------------------------------------------------------------ msplat.alpha_blending
  * call sites: render.py:58-64,68-74,84-90,99-105,148-154; backward via trainer.py:533.
  *
@@ -127,6 +136,35 @@ int gfb_alpha_blending_bwd(const void *geom_stream, const void *feat_stream, int
  * d_opacity, != 0 adds to them (second and later channel groups). */
 int gfb_blend_unpack_grads(const float *grad_pack, int N, int C, int c0, int Cg, float *d_uv, float *d_conic,
                            float *d_opacity, float *d_feature, int accumulate, void *stream);
+
+/* ------------------------------------------------------------------ msplat.rasterization (fused)
+ * The whole chain of render.py:21-64 for callers that only need the image: 4 forward kernels
+ * (preprocess+count+scan, scatter, per-tile sort+pack, blend) and 2 backward kernels (blend
+ * backward, fused geometry backward).  Per-Gaussian results are bit-identical to the separate
+ * operators.  1 <= C <= 4.  Buffers:
+ *   uv (N,2) depth (N,1) conic (N,3) radius (N,1): per-Gaussian outputs (also msplat-visible)
+ *   rect_ws   : N x 8 bytes        control_ws : gfb_render_control_bytes(W,H), any contents
+ *   tile_offsets (T+1), tile_range (T,2) int32
+ *   capacity  : number of intersections the K-sized buffers can hold:
+ *               keys_ws (8 B), gaussian_ids_sorted (4 B), geom_stream (32 B), feat_stream (16 B) each
+ *   out (C,H,W), final_T (H,W), n_contrib (H,W)
+ * K is delivered to *K_host (HOST pointer); GFB_E_CAPACITY as in gfb_sort_gaussian. */
+size_t gfb_render_control_bytes(int W, int H);
+int gfb_render_forward(const float *xyz, const float *scale, const float *rotate, const float *opacity,
+                       const float *feature, int C, const float *intr, const float *extr, int N, int W, int H,
+                       float bg, float nearest, float extent, float *uv, float *depth, float *conic, int32_t *radius,
+                       void *rect_ws, void *control_ws, int32_t *tile_offsets, int32_t *tile_range, int64_t capacity,
+                       void *keys_ws, int32_t *gaussian_ids_sorted, void *geom_stream, void *feat_stream, float *out,
+                       float *final_T, int32_t *n_contrib, int64_t *K_host, void *stream);
+/* grad_ws: gfb_render_grad_bytes(N) bytes = N x 12 floats of packed per-Gaussian gradients followed by
+ * d_cam (16 floats: d_extr 3x4, d_intr 4); zeroed inside.  capacity as passed to the forward call. */
+size_t gfb_render_grad_bytes(int N);
+int gfb_render_backward(const float *xyz, const float *scale, const float *rotate, const float *intr,
+                        const float *extr, int N, int W, int H, int C, float bg, float nearest, float extent,
+                        const int32_t *gaussian_ids_sorted, const int32_t *tile_range, int64_t capacity,
+                        const void *geom_stream, const void *feat_stream, const float *final_T,
+                        const int32_t *n_contrib, const float *g_out, void *grad_ws, float *d_xyz, float *d_scale,
+                        float *d_rotate, float *d_opacity, float *d_feature, void *stream);
 
 #ifdef __cplusplus
 }

@@ -253,6 +253,56 @@ def test_render_step_chain_matches_oracle(G, N, W, H, profile):
         assert_close(p.grad, g_o[name], 1e-3, "grad " + name, **GRAD_OUTLIERS)
 
 
+@pytest.mark.parametrize("N,W,H,Cf", [(5000, 200, 136, 3), (60000, 854, 480, 3), (3000, 100, 70, 1), (3000, 100, 70, 4)])
+def test_fused_rasterization_equals_operator_chain(G, N, W, H, Cf):
+    """gfb_render_forward/backward (4 + 2 kernels) against the ten-kernel operator chain: the image and every
+    per-Gaussian intermediate are bit-identical, gradients agree to atomics ordering."""
+    sc = make_scene(N, W, H, seed=8, bg=0.2)
+    gen = torch.Generator().manual_seed(3)
+    feat = torch.rand(N, Cf, generator=gen)
+    Gimg = cu(make_grad_image(Cf, W, H, seed=5))
+
+    def run(fn):
+        ps = [t.to(DEV).requires_grad_(True) for t in (sc.xyz, sc.scale, sc.rotate, sc.opacity, feat, sc.intr, sc.extr)]
+        img = fn(*ps, W, H, sc.bg)
+        (img * Gimg).sum().backward()
+        return img.detach(), [p.grad for p in ps]
+
+    img_f, g_f = run(G.rasterization)
+    img_u, g_u = run(G.rasterization_unfused)
+    assert torch.equal(img_f, img_u), "fused and unfused images must be bit-identical"
+    for name, a, b in zip(["xyz", "scale", "rotate", "opacity", "feature", "intr", "extr"], g_f, g_u):
+        assert_close(a, b, 1e-4, "fused grad " + name)
+
+
+def test_speculative_capacity_retry(G):
+    """A stale / tiny K hint must trigger the GFB_E_CAPACITY retry, not truncate the result."""
+    from gflow_b200 import ops
+
+    sc = make_scene(4000, 160, 120, seed=9)
+    args = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
+    ref = G.rasterization_unfused(*args, sc.W, sc.H, 0.0)
+    ops._K_HINT.clear()
+    uv, depth = G.project_point(args[0], args[5], args[6], sc.W, sc.H)
+    vis = depth != 0
+    cov = G.compute_cov3d(args[1], args[2], vis)
+    conic, radius, tiles = G.ewa_project(args[0], cov, args[5], args[6], uv, sc.W, sc.H, vis)
+    ids_ref, rng_ref = G.sort_gaussian(uv, depth, sc.W, sc.H, radius, tiles)
+    for k in list(ops._K_HINT):
+        ops._K_HINT[k] = 1  # capacity hint far too small
+    ids, rng = G.sort_gaussian(uv, depth, sc.W, sc.H, radius, tiles)
+    assert torch.equal(ids, ids_ref) and torch.equal(rng, rng_ref)
+    for k in list(ops._K_HINT):
+        ops._K_HINT[k] = 1
+    img = G.rasterization(*args, sc.W, sc.H, 0.0)
+    assert torch.equal(img, ref)
+    # N = 0 through the fused path
+    z = torch.zeros(0, 3, device=DEV)
+    img0 = G.rasterization(z, z, torch.zeros(0, 4, device=DEV), torch.zeros(0, 1, device=DEV), z, args[5], args[6], 64,
+                           48, 0.5)
+    assert img0.shape == (3, 48, 64) and torch.all(img0 == 0.5)
+
+
 def test_render_multiple_call_pattern(G):
     """The exact call sequence of /root/reference/gflow/utils/render.py:6-108 (four blends that share one
     sort, 'center' with replaced conic / opacity) through the drop-in module name."""
