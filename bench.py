@@ -241,9 +241,9 @@ def run_ours(args):
         extr_p.grad = None
         xyz, scale, rot, op, rgb = params
         img = raster(xyz, scale, rot, op, rgb, intr, extr_p, W, H, sc.bg)
-        loss = (img * Gimg).sum()
-        loss.backward()
-        return loss
+        # loss = sum(out * G) with a fixed random G: dL/dout = G is fed to autograd directly
+        img.backward(Gimg)
+        return img
 
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 

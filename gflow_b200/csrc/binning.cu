@@ -13,8 +13,12 @@
 //   3. bin_scatter : one thread per Gaussian, claims a slot in each tile's segment (the
 //                    counters of step 1 count back down) and writes the 64-bit key
 //                    (depth bits << 32 | id)
-//   4. tile_sort   : one CTA per tile sorts its segment in shared memory (bitonic network;
-//                    warp-shuffle compare-exchange for strides < 32), writes ids + range
+//   4. tile_sort   : one WARP per tile sorts its segment in registers (direction-free bitonic
+//                    network, shuffles below stride 32, in-thread exchanges above; <= 256 keys);
+//                    oversized segments fall to a CTA-wide shared-memory / in-place pass
+// Steps 1 and 3 walk the flattened (Gaussian, tile) list 32 pairs per warp round (WarpTileWalk), so
+// their atomics are load balanced and each lane waits for one atomic per round, not one per tile of
+// its own Gaussian in sequence.
 // K is ~3 N and segments are ~100 entries, so everything after step 1 stays in L2/SMEM.
 #include "common.cuh"
 #include "sort_network.cuh"
@@ -37,11 +41,14 @@ __global__ void __launch_bounds__(kThreads)
 bin_count_kernel(const float2* __restrict__ uv, const int32_t* __restrict__ radius,
                  const int32_t* __restrict__ tiles_touched, int N, int gx, int gy, int32_t* __restrict__ counts) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= N) return;
-    int x0, y0, x1, y1;
-    if (!gaussian_rect(uv, radius, tiles_touched, i, gx, gy, x0, y0, x1, y1)) return;
-    for (int y = y0; y < y1; ++y)
-        for (int x = x0; x < x1; ++x) atomicAdd(counts + y * gx + x, 1);
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (i >= N || !gaussian_rect(uv, radius, tiles_touched, i, gx, gy, x0, y0, x1, y1)) x1 = x0, y1 = y0;
+    const WarpTileWalk walk(x0, y0, x1 - x0, y1 - y0, gx, threadIdx.x & 31);
+    for (int base = 0; base < walk.total; base += 32) {
+        int owner;
+        const int t = walk.item(base, owner);
+        if (t >= 0) red_add_s32(counts + t, 1);
+    }
 }
 
 // Single CTA: exclusive scan of counts[0..T) into offsets[0..T].
@@ -89,52 +96,31 @@ bin_scatter_kernel(const float2* __restrict__ uv, const float* __restrict__ dept
                    int gy, const int32_t* __restrict__ offsets, int32_t* __restrict__ counts,
                    unsigned long long* __restrict__ keys, long long K) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= N) return;
-    int x0, y0, x1, y1;
-    if (!gaussian_rect(uv, radius, tiles_touched, i, gx, gy, x0, y0, x1, y1)) return;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(depth[i]) << 32) | (unsigned int)i;
-    for (int y = y0; y < y1; ++y)
-        for (int x = x0; x < x1; ++x) {
-            const int t = y * gx + x;
+    const int lane = threadIdx.x & 31;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    unsigned int dbits = 0;
+    if (i >= N || !gaussian_rect(uv, radius, tiles_touched, i, gx, gy, x0, y0, x1, y1)) x1 = x0, y1 = y0;
+    else dbits = __float_as_uint(depth[i]);
+    const WarpTileWalk walk(x0, y0, x1 - x0, y1 - y0, gx, lane);
+    for (int base = 0; base < walk.total; base += 32) {
+        int owner;
+        const int t = walk.item(base, owner);
+        const unsigned int o_bits = __shfl_sync(0xffffffffu, dbits, owner);
+        if (t >= 0) {
             // the phase-1 counters double as countdown cursors: slot = offset + (count-- - 1)
             const long long pos = (long long)offsets[t] + (atomicSub(counts + t, 1) - 1);
-            if (pos >= 0 && pos < K) keys[pos] = key;  // K is the caller's copy of offsets[T]; never overrun
+            const unsigned int id = (unsigned int)(i - lane + owner);
+            if (pos >= 0 && pos < K) keys[pos] = ((unsigned long long)o_bits << 32) | id;  // never overrun
         }
+    }
 }
 
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_kernel(const int32_t* __restrict__ offsets, unsigned long long* __restrict__ keys,
                  int32_t* __restrict__ ids_sorted, int2* __restrict__ tile_range, int T, long long capacity) {
     __shared__ unsigned long long s_keys[kSortSmemKeys];
-    const int t = blockIdx.x;
-    const int start = offsets[t];
-    long long end_ll = offsets[t + 1];
-    if (end_ll > capacity) end_ll = max((long long)start, capacity);  // speculative capacity too small: host retries
-    const int end = (int)end_ll;
-    const int n = end - start;
-    if (threadIdx.x == 0) tile_range[t] = (n > 0) ? make_int2(start, end) : make_int2(0, 0);
-    if (n <= 0) return;
-    if (n <= 64) {
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            unsigned long long k0 = (lane < n) ? keys[start + lane] : ~0ull;
-            unsigned long long k1 = (lane + 32 < n) ? keys[start + lane + 32] : ~0ull;
-            warp_sort64(k0, k1, lane);
-            if (lane < n) ids_sorted[start + lane] = (int32_t)(unsigned int)k0;
-            if (lane + 32 < n) ids_sorted[start + lane + 32] = (int32_t)(unsigned int)k1;
-        }
-        return;
-    }
-    int n_pad = 128;
-    while (n_pad < n) n_pad <<= 1;
-    // > 4096 Gaussians on one tile: same network, in place on the (L2-resident) global segment.
-    unsigned long long* buf = (n <= kSortSmemKeys) ? s_keys : (keys + start);
-    if (n <= kSortSmemKeys) {
-        for (int i = threadIdx.x; i < n; i += kSortThreads) s_keys[i] = keys[start + i];
-        __syncthreads();
-    }
-    bitonic_sort_block(buf, n, n_pad);
-    for (int i = threadIdx.x; i < n; i += kSortThreads) ids_sorted[start + i] = (int32_t)(unsigned int)buf[i];
+    sort_tiles_cta(offsets, keys, T, capacity, s_keys, tile_range,
+                   [ids_sorted](long long pos, unsigned long long key) { ids_sorted[pos] = (int32_t)(unsigned int)key; });
 }
 
 }  // namespace
@@ -167,14 +153,14 @@ int gfb_sort_emit(const float* uv, const float* depth, const int32_t* radius, co
     cudaStream_t st = (cudaStream_t)stream;
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
     unsigned long long* keys = (unsigned long long*)keys_ws;
-    if (K > 0) {
+    if (K > 0 && N > 0) {
         if (!uv || !depth || !radius || !tiles_touched || !gaussian_ids_sorted || !keys) return GFB_E_BADARG;
         bin_scatter_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(
             reinterpret_cast<const float2*>(uv), depth, radius, tiles_touched, N, gx, gy, tile_offsets, tile_counts,
             keys, (long long)K);
         GFB_CHECK_LAUNCH();
     }
-    tile_sort_kernel<<<T, kSortThreads, 0, st>>>(tile_offsets, keys, gaussian_ids_sorted,
+    tile_sort_kernel<<<gfb_div_up(T, kTilesPerSortCta), kSortThreads, 0, st>>>(tile_offsets, keys, gaussian_ids_sorted,
                                                  reinterpret_cast<int2*>(tile_range), T, (long long)K);
     GFB_CHECK_LAUNCH();
     return 0;

@@ -35,7 +35,7 @@ namespace {
 using namespace gfbm;
 
 // ctrl words that follow the T tile counters in the control buffer
-enum { CTRL_DONE = 0, CTRL_K = 1, CTRL_OVERFLOW = 2, CTRL_WORDS = 4 };
+enum { CTRL_DONE = 0, CTRL_K = 1, CTRL_WORDS = 4 };
 
 __global__ void __launch_bounds__(kThreads)
 preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale, const float4* __restrict__ rotate,
@@ -50,13 +50,13 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
     load_camera(s_cam, intr, extr);
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
     const int i = blockIdx.x * kThreads + threadIdx.x;
+    ushort4 rc = make_ushort4(0, 0, 0, 0);
     if (i < N) {
         const float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
         float u, v, xc, yc, zc;
         const bool ok = project_one(s_cam + 12, s_cam, W, H, nearest, extent, p[0], p[1], p[2], u, v, xc, yc, zc);
         float ca = 0.0f, cb = 0.0f, cc = 0.0f;
         int rad = 0;
-        ushort4 rc = make_ushort4(0, 0, 0, 0);
         if (ok) {
             const float s[3] = {scale[3 * i], scale[3 * i + 1], scale[3 * i + 2]};
             float S[6];
@@ -72,8 +72,6 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                 cc = m.a * dinv;
                 rad = (int)rf;
                 rc = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-                for (int y = y0; y < y1; ++y)
-                    for (int x = x0; x < x1; ++x) atomicAdd(counts + y * gx + x, 1);
             }
         }
         uv[i] = ok ? make_float2(u, v) : make_float2(0.0f, 0.0f);
@@ -83,6 +81,14 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
         conic[3 * i + 2] = cc;
         radius[i] = rad;
         rect[i] = rc;
+    }
+    {   // per-tile counting, 32 (Gaussian, tile) pairs per warp round
+        const WarpTileWalk walk(rc.x, rc.y, rc.z - rc.x, rc.w - rc.y, gx, threadIdx.x & 31);
+        for (int base = 0; base < walk.total; base += 32) {
+            int owner;
+            const int t = walk.item(base, owner);
+            if (t >= 0) red_add_s32(counts + t, 1);
+        }
     }
     // ---- the last CTA to get here scans the tile counters (threadfence reduction pattern)
     __threadfence();
@@ -131,16 +137,24 @@ scatter_kernel(const ushort4* __restrict__ rect, const float* __restrict__ depth
                const int32_t* __restrict__ offsets, int32_t* __restrict__ counts,
                unsigned long long* __restrict__ keys, long long capacity) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= N) return;
-    const ushort4 rc = rect[i];
-    if (rc.z <= rc.x || rc.w <= rc.y) return;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(depth[i]) << 32) | (unsigned int)i;
-    for (int y = rc.y; y < rc.w; ++y)
-        for (int x = rc.x; x < rc.z; ++x) {
-            const int t = y * gx + x;
+    const int lane = threadIdx.x & 31;
+    ushort4 rc = make_ushort4(0, 0, 0, 0);
+    unsigned int dbits = 0;
+    if (i < N) {
+        rc = rect[i];
+        dbits = __float_as_uint(depth[i]);
+    }
+    const WarpTileWalk walk(rc.x, rc.y, rc.z - rc.x, rc.w - rc.y, gx, lane);
+    for (int base = 0; base < walk.total; base += 32) {
+        int owner;
+        const int t = walk.item(base, owner);
+        const unsigned int o_bits = __shfl_sync(0xffffffffu, dbits, owner);
+        if (t >= 0) {
             const long long pos = (long long)offsets[t] + (atomicSub(counts + t, 1) - 1);
-            if (pos >= 0 && pos < capacity) keys[pos] = key;
+            const unsigned int id = (unsigned int)(i - lane + owner);
+            if (pos >= 0 && pos < capacity) keys[pos] = ((unsigned long long)o_bits << 32) | id;
         }
+    }
 }
 
 // record writers -------------------------------------------------------------
@@ -175,38 +189,10 @@ __device__ __forceinline__ void write_record(const PackArgs& a, long long k, int
 
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_pack_kernel(const int32_t* __restrict__ offsets, unsigned long long* __restrict__ keys,
-                      int2* __restrict__ tile_range, long long capacity, int32_t* __restrict__ ctrl, PackArgs pa) {
+                      int2* __restrict__ tile_range, int T, long long capacity, PackArgs pa) {
     __shared__ unsigned long long s_keys[kSortSmemKeys];
-    const int t = blockIdx.x;
-    const int start = offsets[t];
-    long long end = offsets[t + 1];
-    if (end > capacity) {  // speculative capacity too small: clamp, flag, the host retries
-        end = max((long long)start, capacity);
-        if (threadIdx.x == 0) ctrl[CTRL_OVERFLOW] = 1;
-    }
-    const int n = (int)(end - start);
-    if (threadIdx.x == 0) tile_range[t] = (n > 0) ? make_int2(start, (int)end) : make_int2(0, 0);
-    if (n <= 0) return;
-    if (n <= 64) {
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            unsigned long long k0 = (lane < n) ? keys[start + lane] : ~0ull;
-            unsigned long long k1 = (lane + 32 < n) ? keys[start + lane + 32] : ~0ull;
-            warp_sort64(k0, k1, lane);
-            if (lane < n) write_record(pa, (long long)start + lane, (int)(unsigned int)k0);
-            if (lane + 32 < n) write_record(pa, (long long)start + lane + 32, (int)(unsigned int)k1);
-        }
-        return;
-    }
-    int n_pad = 128;
-    while (n_pad < n) n_pad <<= 1;
-    unsigned long long* buf = (n <= kSortSmemKeys) ? s_keys : (keys + start);
-    if (n <= kSortSmemKeys) {
-        for (int i = threadIdx.x; i < n; i += kSortThreads) s_keys[i] = keys[start + i];
-        __syncthreads();
-    }
-    bitonic_sort_block(buf, n, n_pad);
-    for (int i = threadIdx.x; i < n; i += kSortThreads) write_record(pa, (long long)start + i, (int)(unsigned int)buf[i]);
+    sort_tiles_cta(offsets, keys, T, capacity, s_keys, tile_range,
+                   [pa](long long pos, unsigned long long key) { write_record(pa, pos, (int)(unsigned int)key); });
 }
 
 // Fused geometry backward: grad_pack (from blend_bwd) -> parameter gradients.
@@ -313,8 +299,9 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     }
     PackArgs pa{reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, sA, sA + capacity,
                 reinterpret_cast<float4*>(feat_stream), gaussian_ids_sorted};
-    tile_sort_pack_kernel<<<T, kSortThreads, 0, st>>>(tile_offsets, reinterpret_cast<unsigned long long*>(keys_ws),
-                                                      reinterpret_cast<int2*>(tile_range), (long long)capacity, ctrl, pa);
+    tile_sort_pack_kernel<<<gfb_div_up(T, kTilesPerSortCta), kSortThreads, 0, st>>>(
+        tile_offsets, reinterpret_cast<unsigned long long*>(keys_ws), reinterpret_cast<int2*>(tile_range), T,
+        (long long)capacity, pa);
     GFB_CHECK_LAUNCH();
     rc = gfb_alpha_blending_fwd(geom_stream, feat_stream, capacity, tile_range, C, 0, C, bg, W, H, out, final_T,
                                 n_contrib, stream);

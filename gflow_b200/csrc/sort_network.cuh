@@ -75,3 +75,160 @@ __device__ __forceinline__ void warp_sort64(unsigned long long& k0, unsigned lon
     }
 }
 
+
+// ------------------------------------------------------------------ register-resident warp sort
+// 32*R keys per warp, element e = r*32 + lane.  Same direction-free network; exchanges with a
+// stride below 32 are warp shuffles, strides of 32 and above are in-thread register exchanges, so
+// a tile segment of up to 256 keys is sorted by one warp with no shared memory and no barrier.
+template <int R>
+__device__ __forceinline__ void warp_sort_regs(unsigned long long (&k)[R], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * R; size <<= 1) {
+        if (size <= 32) {
+            const bool lower = (lane & (size >> 1)) == 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const unsigned long long p = __shfl_xor_sync(0xffffffffu, k[r], size - 1);
+                k[r] = lower ? u64_min(k[r], p) : u64_max(k[r], p);
+            }
+        } else {
+            const int m = size / 32;  // partner: register r ^ (m-1), lane ^ 31
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if ((r & (m >> 1)) == 0) {
+                    const int r2 = r ^ (m - 1);
+                    const unsigned long long a = k[r], b = k[r2];
+                    const unsigned long long pa = __shfl_xor_sync(0xffffffffu, b, 31);
+                    const unsigned long long pb = __shfl_xor_sync(0xffffffffu, a, 31);
+                    k[r] = u64_min(a, pa);
+                    k[r2] = u64_max(b, pb);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = size >> 2; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j / 32;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & jr) == 0) {
+                        const unsigned long long a = k[r], b = k[r | jr];
+                        k[r] = u64_min(a, b);
+                        k[r | jr] = u64_max(a, b);
+                    }
+                }
+            } else {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const unsigned long long p = __shfl_xor_sync(0xffffffffu, k[r], j);
+                    k[r] = lower ? u64_min(k[r], p) : u64_max(k[r], p);
+                }
+            }
+        }
+    }
+}
+
+constexpr int kWarpSortMax = 256;   // largest segment sorted by one warp (R = 8)
+constexpr int kTilesPerSortCta = kSortThreads / 32;
+
+// Sort one tile segment keys[start, start+n) with one warp (n <= 256) and hand every sorted key to
+// emit(position, key).  All 32 lanes must call.
+template <int R, class Emit>
+__device__ __forceinline__ void warp_sort_segment(const unsigned long long* __restrict__ keys, long long start, int n,
+                                                  int lane, Emit emit) {
+    unsigned long long k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r] = (r * 32 + lane < n) ? keys[start + r * 32 + lane] : ~0ull;
+    warp_sort_regs<R>(k, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (r * 32 + lane < n) emit(start + r * 32 + lane, k[r]);
+}
+
+// One CTA of 128 threads handles kTilesPerSortCta consecutive tiles: a warp each while the segment
+// fits the register sort, then the whole CTA on every oversized segment (shared memory up to 4096
+// keys, in place on the L2-resident global segment beyond).  range(t, start, end) is called once per
+// tile by one thread.
+template <class Emit>
+__device__ __forceinline__ void sort_tiles_cta(const int32_t* __restrict__ offsets, unsigned long long* __restrict__ keys,
+                                               int T, long long capacity, unsigned long long* s_keys,
+                                               int2* __restrict__ tile_range, Emit emit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const int t = blockIdx.x * kTilesPerSortCta + warp;
+        if (t < T) {
+            const int start = offsets[t];
+            long long end = offsets[t + 1];
+            if (end > capacity) end = max((long long)start, capacity);  // speculative capacity too small
+            const int n = (int)(end - start);
+            if (lane == 0) tile_range[t] = (n > 0) ? make_int2(start, (int)end) : make_int2(0, 0);
+            if (n > 0 && n <= 64) warp_sort_segment<2>(keys, start, n, lane, emit);
+            else if (n > 64 && n <= 128) warp_sort_segment<4>(keys, start, n, lane, emit);
+            else if (n > 128 && n <= kWarpSortMax) warp_sort_segment<8>(keys, start, n, lane, emit);
+        }
+    }
+    for (int w = 0; w < kTilesPerSortCta; ++w) {
+        const int t = blockIdx.x * kTilesPerSortCta + w;
+        if (t >= T) break;
+        const int start = offsets[t];
+        long long end = offsets[t + 1];
+        if (end > capacity) end = max((long long)start, capacity);
+        const int n = (int)(end - start);
+        if (n <= kWarpSortMax) continue;  // uniform across the CTA
+        __syncthreads();
+        int n_pad = 512;
+        while (n_pad < n) n_pad <<= 1;
+        unsigned long long* buf = (n <= kSortSmemKeys) ? s_keys : (keys + start);
+        if (n <= kSortSmemKeys) {
+            for (int i = threadIdx.x; i < n; i += kSortThreads) s_keys[i] = keys[start + i];
+            __syncthreads();
+        }
+        bitonic_sort_block(buf, n, n_pad);
+        for (int i = threadIdx.x; i < n; i += kSortThreads) emit((long long)start + i, buf[i]);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ warp-expanded tile loops
+// Each lane owns one Gaussian with a w x h tile rectangle at (x0, y0) (w*h == 0: none).  The warp
+// walks the flattened list of (Gaussian, tile) pairs 32 at a time, so every lane issues one atomic
+// per round regardless of how uneven the rectangles are.  A round yields, for lane `lane`, the
+// owner lane `o` and the tile index (or tile < 0 when the round is ragged).
+struct WarpTileWalk {
+    int incl, cnt, total, w, x0, y0, gx, lane;
+    __device__ __forceinline__ WarpTileWalk(int x0_, int y0_, int w_, int h_, int gx_, int lane_)
+        : cnt(w_ * h_), w(w_), x0(x0_), y0(y0_), gx(gx_), lane(lane_) {
+        incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+    }
+    // all lanes call; returns the tile for flat index base+lane (or -1) and the owner lane
+    __device__ __forceinline__ int item(int base, int& owner) const {
+        const int j = base + lane;
+        int lo = 0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, lo + s - 1);
+            if (v <= j) lo += s;
+        }
+        lo = min(lo, 31);
+        const int o_excl = __shfl_sync(0xffffffffu, incl - cnt, lo);
+        const int o_w = __shfl_sync(0xffffffffu, w, lo);
+        const int o_x0 = __shfl_sync(0xffffffffu, x0, lo);
+        const int o_y0 = __shfl_sync(0xffffffffu, y0, lo);
+        owner = lo;
+        if (j >= total) return -1;
+        const int local = j - o_excl;
+        const int row = local / o_w;
+        return (o_y0 + row) * gx + o_x0 + (local - row * o_w);
+    }
+};
+
+__device__ __forceinline__ void red_add_s32(int32_t* p, int v) {
+    asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
