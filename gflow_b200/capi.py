@@ -29,11 +29,10 @@ SIGNATURES = {
     "gfb_compute_sh_fwd": (I, [P, P, P, I, I, I, P, P]),
     "gfb_compute_sh_bwd": (I, [P, P, P, I, I, I, P, P, P, P]),
     "gfb_sort_workspace_bytes": (c_size_t, [L]),
-    "gfb_sort_count": (I, [P, P, P, I, I, I, P, P, P]),
-    "gfb_sort_emit": (I, [P, P, P, P, I, I, I, P, P, L, P, P, P, P]),
-    "gfb_sort_gaussian": (I, [P, P, P, P, I, I, I, P, P, L, P, P, P, P, P]),
+    "gfb_sort_tile_workspace_bytes": (c_size_t, [I, I]),
+    "gfb_sort_gaussian": (I, [P, P, P, P, I, I, I, P, L, P, P, P, P, P]),
     "gfb_render_control_bytes": (c_size_t, [I, I]),
-    "gfb_render_forward": (I, [P, P, P, P, P, I, P, P, I, I, I, F, F, F, P, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P,
+    "gfb_render_forward": (I, [P, P, P, P, P, I, P, P, I, I, I, F, F, F, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P,
                                P, P]),
     "gfb_render_grad_bytes": (c_size_t, [I]),
     "gfb_render_backward": (I, [P, P, P, P, P, I, I, I, I, F, F, F, P, P, L, P, P, P, P, P, P, P, P, P, P, P, P]),

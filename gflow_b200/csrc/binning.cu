@@ -9,7 +9,8 @@
 // every tile, the Gaussians touching it ordered by (depth bits, Gaussian id).  We produce
 // exactly that order without the global sort:
 //   1. bin_count   : one thread per Gaussian, atomicAdd on its tiles' counters
-//   2. tile_scan   : exclusive scan of the T counters (single CTA), K = total
+//   2. tile_scan   : exclusive scan of the T x R counters (single CTA), K = total; counters are
+//                    replicated R ways to spread same-address atomics over R L2 lines
 //   3. bin_scatter : one thread per Gaussian, claims a slot in each tile's segment (the
 //                    counters of step 1 count back down) and writes the 64-bit key
 //                    (depth bits << 32 | id)
@@ -39,7 +40,8 @@ __device__ __forceinline__ bool gaussian_rect(const float2* __restrict__ uv, con
 
 __global__ void __launch_bounds__(kThreads)
 bin_count_kernel(const float2* __restrict__ uv, const int32_t* __restrict__ radius,
-                 const int32_t* __restrict__ tiles_touched, int N, int gx, int gy, int32_t* __restrict__ counts) {
+                 const int32_t* __restrict__ tiles_touched, int N, int gx, int gy, int R,
+                 int32_t* __restrict__ counts) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
     if (i >= N || !gaussian_rect(uv, radius, tiles_touched, i, gx, gy, x0, y0, x1, y1)) x1 = x0, y1 = y0;
@@ -47,7 +49,7 @@ bin_count_kernel(const float2* __restrict__ uv, const int32_t* __restrict__ radi
     for (int base = 0; base < walk.total; base += 32) {
         int owner;
         const int t = walk.item(base, owner);
-        if (t >= 0) red_add_s32(counts + t, 1);
+        if (t >= 0) red_add_s32(counts + t * R + (blockIdx.x % R), 1);
     }
 }
 
@@ -93,7 +95,7 @@ tile_scan_kernel(const int32_t* __restrict__ counts, int T, int32_t* __restrict_
 __global__ void __launch_bounds__(kThreads)
 bin_scatter_kernel(const float2* __restrict__ uv, const float* __restrict__ depth,
                    const int32_t* __restrict__ radius, const int32_t* __restrict__ tiles_touched, int N, int gx,
-                   int gy, const int32_t* __restrict__ offsets, int32_t* __restrict__ counts,
+                   int gy, int R, const int32_t* __restrict__ offsets, int32_t* __restrict__ counts,
                    unsigned long long* __restrict__ keys, long long K) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -108,7 +110,8 @@ bin_scatter_kernel(const float2* __restrict__ uv, const float* __restrict__ dept
         const unsigned int o_bits = __shfl_sync(0xffffffffu, dbits, owner);
         if (t >= 0) {
             // the phase-1 counters double as countdown cursors: slot = offset + (count-- - 1)
-            const long long pos = (long long)offsets[t] + (atomicSub(counts + t, 1) - 1);
+            const int slot = t * R + (blockIdx.x % R);
+            const long long pos = (long long)offsets[slot] + (atomicSub(counts + slot, 1) - 1);
             const unsigned int id = (unsigned int)(i - lane + owner);
             if (pos >= 0 && pos < K) keys[pos] = ((unsigned long long)o_bits << 32) | id;  // never overrun
         }
@@ -116,10 +119,10 @@ bin_scatter_kernel(const float2* __restrict__ uv, const float* __restrict__ dept
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-tile_sort_kernel(const int32_t* __restrict__ offsets, unsigned long long* __restrict__ keys,
+tile_sort_kernel(const int32_t* __restrict__ offsets, int R, unsigned long long* __restrict__ keys,
                  int32_t* __restrict__ ids_sorted, int2* __restrict__ tile_range, int T, long long capacity) {
     __shared__ unsigned long long s_keys[kSortSmemKeys];
-    sort_tiles_cta(offsets, keys, T, capacity, s_keys, tile_range,
+    sort_tiles_cta(offsets, R, keys, T, capacity, s_keys, tile_range,
                    [ids_sorted](long long pos, unsigned long long key) { ids_sorted[pos] = (int32_t)(unsigned int)key; });
 }
 
@@ -129,61 +132,50 @@ extern "C" {
 
 size_t gfb_sort_workspace_bytes(int64_t K) { return K < 0 ? 0 : (size_t)K * sizeof(unsigned long long); }
 
-int gfb_sort_count(const float* uv, const int32_t* radius, const int32_t* tiles_touched, int N, int W, int H,
-                   int32_t* tile_counts, int32_t* tile_offsets, void* stream) {
-    if (N < 0 || W <= 0 || H <= 0 || !tile_counts || !tile_offsets) return GFB_E_BADARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
-    GFB_TRY(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)T, st));
-    if (N > 0) {
-        if (!uv || !radius || !tiles_touched) return GFB_E_BADARG;
-        bin_count_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(reinterpret_cast<const float2*>(uv), radius,
-                                                                       tiles_touched, N, gx, gy, tile_counts);
-        GFB_CHECK_LAUNCH();
-    }
-    tile_scan_kernel<<<1, 1024, 0, st>>>(tile_counts, T, tile_offsets);
-    GFB_CHECK_LAUNCH();
-    return 0;
-}
-
-int gfb_sort_emit(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles_touched, int N,
-                  int W, int H, int32_t* tile_counts, const int32_t* tile_offsets, int64_t K, void* keys_ws,
-                  int32_t* gaussian_ids_sorted, int32_t* tile_range, void* stream) {
-    if (N < 0 || W <= 0 || H <= 0 || K < 0 || !tile_counts || !tile_offsets || !tile_range) return GFB_E_BADARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
-    unsigned long long* keys = (unsigned long long*)keys_ws;
-    if (K > 0 && N > 0) {
-        if (!uv || !depth || !radius || !tiles_touched || !gaussian_ids_sorted || !keys) return GFB_E_BADARG;
-        bin_scatter_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(
-            reinterpret_cast<const float2*>(uv), depth, radius, tiles_touched, N, gx, gy, tile_offsets, tile_counts,
-            keys, (long long)K);
-        GFB_CHECK_LAUNCH();
-    }
-    tile_sort_kernel<<<gfb_div_up(T, kTilesPerSortCta), kSortThreads, 0, st>>>(tile_offsets, keys, gaussian_ids_sorted,
-                                                 reinterpret_cast<int2*>(tile_range), T, (long long)K);
-    GFB_CHECK_LAUNCH();
-    return 0;
+// tile workspace: counts[T*R] | offsets[T*R + 1]
+size_t gfb_sort_tile_workspace_bytes(int W, int H) {
+    if (W <= 0 || H <= 0) return 0;
+    const size_t T = (size_t)((W + GFB_TILE - 1) / GFB_TILE) * ((H + GFB_TILE - 1) / GFB_TILE);
+    const size_t R = (size_t)gfb_tile_replicas((int)T);
+    return (2 * T * R + 1) * sizeof(int32_t);
 }
 
 int gfb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius, const int32_t* tiles_touched, int N,
-                      int W, int H, int32_t* tile_counts, int32_t* tile_offsets, int64_t capacity, void* keys_ws,
-                      int32_t* gaussian_ids_sorted, int32_t* tile_range, int64_t* K_host, void* stream) {
-    if (capacity < 0 || !K_host) return GFB_E_BADARG;
+                      int W, int H, void* tile_ws, int64_t capacity, void* keys_ws, int32_t* gaussian_ids_sorted,
+                      int32_t* tile_range, int64_t* K_host, void* stream) {
+    if (N < 0 || W <= 0 || H <= 0 || capacity < 0 || !tile_ws || !tile_range || !K_host) return GFB_E_BADARG;
+    if (N > 0 && (!uv || !depth || !radius || !tiles_touched)) return GFB_E_BADARG;
+    if (capacity > 0 && (!keys_ws || !gaussian_ids_sorted)) return GFB_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
+    const int R = gfb_tile_replicas(T);
+    int32_t* counts = (int32_t*)tile_ws;
+    int32_t* offsets = counts + (size_t)T * R;
+    unsigned long long* keys = (unsigned long long*)keys_ws;
     int32_t* pinned = nullptr;
     cudaEvent_t ev = nullptr;
     int rc = gfb_internal_host_sync(&pinned, &ev);
     if (rc) return rc;
-    rc = gfb_sort_count(uv, radius, tiles_touched, N, W, H, tile_counts, tile_offsets, stream);
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int T = ((W + GFB_TILE - 1) / GFB_TILE) * ((H + GFB_TILE - 1) / GFB_TILE);
-    GFB_TRY(cudaMemcpyAsync(pinned, tile_offsets + T, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    GFB_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)T * R, st));
+    if (N > 0) {
+        bin_count_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(reinterpret_cast<const float2*>(uv), radius,
+                                                                       tiles_touched, N, gx, gy, R, counts);
+        GFB_CHECK_LAUNCH();
+    }
+    tile_scan_kernel<<<1, 1024, 0, st>>>(counts, T * R, offsets);
+    GFB_CHECK_LAUNCH();
+    GFB_TRY(cudaMemcpyAsync(pinned, offsets + (size_t)T * R, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GFB_TRY(cudaEventRecord(ev, st));
     // speculative: scatter + per-tile sort are enqueued with the caller's capacity before K is known
-    rc = gfb_sort_emit(uv, depth, radius, tiles_touched, N, W, H, tile_counts, tile_offsets, capacity, keys_ws,
-                       gaussian_ids_sorted, tile_range, stream);
-    if (rc) return rc;
+    if (N > 0 && capacity > 0) {
+        bin_scatter_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(
+            reinterpret_cast<const float2*>(uv), depth, radius, tiles_touched, N, gx, gy, R, offsets, counts, keys,
+            (long long)capacity);
+        GFB_CHECK_LAUNCH();
+    }
+    tile_sort_kernel<<<gfb_div_up(T, kTilesPerSortCta), kSortThreads, 0, st>>>(
+        offsets, R, keys, gaussian_ids_sorted, reinterpret_cast<int2*>(tile_range), T, (long long)capacity);
+    GFB_CHECK_LAUNCH();
     GFB_TRY(cudaEventSynchronize(ev));  // waits for count + scan only
     *K_host = (int64_t)pinned[0];
     return (*K_host > capacity) ? GFB_E_CAPACITY : 0;

@@ -42,7 +42,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                   const float* __restrict__ intr, const float* __restrict__ extr, int N, int W, int H, float nearest,
                   float extent, float2* __restrict__ uv, float* __restrict__ depth, float* __restrict__ conic,
                   int32_t* __restrict__ radius, ushort4* __restrict__ rect, int32_t* __restrict__ counts,
-                  int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T) {
+                  int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R) {
     __shared__ float s_cam[16];
     __shared__ int s_scan[kThreads / 32];
     __shared__ int s_carry;
@@ -87,7 +87,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
         for (int base = 0; base < walk.total; base += 32) {
             int owner;
             const int t = walk.item(base, owner);
-            if (t >= 0) red_add_s32(counts + t, 1);
+            if (t >= 0) red_add_s32(counts + t * R + (blockIdx.x % R), 1);
         }
     }
     // ---- the last CTA to get here scans the tile counters (threadfence reduction pattern)
@@ -102,9 +102,10 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
     if (!s_last) return;
     __threadfence();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < T; base += kThreads) {
+    const int TR = T * R;
+    for (int base = 0; base < TR; base += kThreads) {
         const int t = base + threadIdx.x;
-        const int c = (t < T) ? __ldcg(counts + t) : 0;
+        const int c = (t < TR) ? __ldcg(counts + t) : 0;
         int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -121,19 +122,19 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
             total += sw;
         }
         const int carry = s_carry;
-        if (t < T) offsets[t] = carry + wofs + incl - c;
+        if (t < TR) offsets[t] = carry + wofs + incl - c;
         __syncthreads();
         if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        offsets[T] = s_carry;
+        offsets[TR] = s_carry;
         ctrl[CTRL_K] = s_carry;
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-scatter_kernel(const ushort4* __restrict__ rect, const float* __restrict__ depth, int N, int gx,
+scatter_kernel(const ushort4* __restrict__ rect, const float* __restrict__ depth, int N, int gx, int R,
                const int32_t* __restrict__ offsets, int32_t* __restrict__ counts,
                unsigned long long* __restrict__ keys, long long capacity) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
@@ -150,7 +151,8 @@ scatter_kernel(const ushort4* __restrict__ rect, const float* __restrict__ depth
         const int t = walk.item(base, owner);
         const unsigned int o_bits = __shfl_sync(0xffffffffu, dbits, owner);
         if (t >= 0) {
-            const long long pos = (long long)offsets[t] + (atomicSub(counts + t, 1) - 1);
+            const int slot = t * R + (blockIdx.x % R);
+            const long long pos = (long long)offsets[slot] + (atomicSub(counts + slot, 1) - 1);
             const unsigned int id = (unsigned int)(i - lane + owner);
             if (pos >= 0 && pos < capacity) keys[pos] = ((unsigned long long)o_bits << 32) | id;
         }
@@ -188,10 +190,10 @@ __device__ __forceinline__ void write_record(const PackArgs& a, long long k, int
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-tile_sort_pack_kernel(const int32_t* __restrict__ offsets, unsigned long long* __restrict__ keys,
+tile_sort_pack_kernel(const int32_t* __restrict__ offsets, int R, unsigned long long* __restrict__ keys,
                       int2* __restrict__ tile_range, int T, long long capacity, PackArgs pa) {
     __shared__ unsigned long long s_keys[kSortSmemKeys];
-    sort_tiles_cta(offsets, keys, T, capacity, s_keys, tile_range,
+    sort_tiles_cta(offsets, R, keys, T, capacity, s_keys, tile_range,
                    [pa](long long pos, unsigned long long key) { write_record(pa, pos, (int)(unsigned int)key); });
 }
 
@@ -257,35 +259,39 @@ extern "C" {
 size_t gfb_render_control_bytes(int W, int H) {
     if (W <= 0 || H <= 0) return 0;
     const size_t T = (size_t)((W + GFB_TILE - 1) / GFB_TILE) * ((H + GFB_TILE - 1) / GFB_TILE);
-    return (T + CTRL_WORDS) * sizeof(int32_t);
+    const size_t R = (size_t)gfb_tile_replicas((int)T);
+    // counts[T*R] | ctrl[4] | offsets[T*R + 1]
+    return (2 * T * R + 1 + CTRL_WORDS) * sizeof(int32_t);
 }
 
 int gfb_render_forward(const float* xyz, const float* scale, const float* rotate, const float* opacity,
                        const float* feature, int C, const float* intr, const float* extr, int N, int W, int H,
                        float bg, float nearest, float extent, float* uv, float* depth, float* conic, int32_t* radius,
-                       void* rect_ws, void* control_ws, int32_t* tile_offsets, int32_t* tile_range, int64_t capacity,
+                       void* rect_ws, void* control_ws, int32_t* tile_range, int64_t capacity,
                        void* keys_ws, int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, float* out,
                        float* final_T, int32_t* n_contrib, int64_t* K_host, void* stream) {
     if (N < 0 || W <= 0 || H <= 0 || C < 1 || C > 4 || capacity < 0) return GFB_E_BADARG;
-    if (!intr || !extr || !control_ws || !tile_offsets || !tile_range || !out || !final_T || !n_contrib || !K_host)
+    if (!intr || !extr || !control_ws || !tile_range || !out || !final_T || !n_contrib || !K_host)
         return GFB_E_BADARG;
     if (N > 0 && (!xyz || !scale || !rotate || !opacity || !feature || !uv || !depth || !conic || !radius || !rect_ws))
         return GFB_E_BADARG;
     if (capacity > 0 && (!keys_ws || !gaussian_ids_sorted || !geom_stream || !feat_stream)) return GFB_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
+    const int R = gfb_tile_replicas(T);
     int32_t* counts = (int32_t*)control_ws;
-    int32_t* ctrl = counts + T;
+    int32_t* ctrl = counts + (size_t)T * R;
+    int32_t* tile_offsets = ctrl + CTRL_WORDS;
     int32_t* pinned = nullptr;
     cudaEvent_t ev = nullptr;
     int rc = gfb_internal_host_sync(&pinned, &ev);
     if (rc) return rc;
-    GFB_TRY(cudaMemsetAsync(control_ws, 0, gfb_render_control_bytes(W, H), st));
+    GFB_TRY(cudaMemsetAsync(control_ws, 0, ((size_t)T * R + CTRL_WORDS) * sizeof(int32_t), st));
     // N == 0 still runs one CTA so the scan zeroes the offsets
     preprocess_kernel<<<max(1, gfb_div_up(N, kThreads)), kThreads, 0, st>>>(
         xyz, scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent,
         reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect_ws), counts,
-        tile_offsets, ctrl, T);
+        tile_offsets, ctrl, T, R);
     GFB_CHECK_LAUNCH();
     GFB_TRY(cudaMemcpyAsync(pinned, ctrl + CTRL_K, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GFB_TRY(cudaEventRecord(ev, st));
@@ -293,14 +299,14 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     float4* sA = reinterpret_cast<float4*>(geom_stream);
     if (N > 0 && capacity > 0) {
         scatter_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(
-            reinterpret_cast<const ushort4*>(rect_ws), depth, N, gx, tile_offsets, counts,
+            reinterpret_cast<const ushort4*>(rect_ws), depth, N, gx, R, tile_offsets, counts,
             reinterpret_cast<unsigned long long*>(keys_ws), (long long)capacity);
         GFB_CHECK_LAUNCH();
     }
     PackArgs pa{reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, sA, sA + capacity,
                 reinterpret_cast<float4*>(feat_stream), gaussian_ids_sorted};
     tile_sort_pack_kernel<<<gfb_div_up(T, kTilesPerSortCta), kSortThreads, 0, st>>>(
-        tile_offsets, reinterpret_cast<unsigned long long*>(keys_ws), reinterpret_cast<int2*>(tile_range), T,
+        tile_offsets, R, reinterpret_cast<unsigned long long*>(keys_ws), reinterpret_cast<int2*>(tile_range), T,
         (long long)capacity, pa);
     GFB_CHECK_LAUNCH();
     rc = gfb_alpha_blending_fwd(geom_stream, feat_stream, capacity, tile_range, C, 0, C, bg, W, H, out, final_T,

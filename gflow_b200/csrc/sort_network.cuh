@@ -81,51 +81,51 @@ __device__ __forceinline__ void warp_sort64(unsigned long long& k0, unsigned lon
 // stride below 32 are warp shuffles, strides of 32 and above are in-thread register exchanges, so
 // a tile segment of up to 256 keys is sorted by one warp with no shared memory and no barrier.
 template <int R>
+__device__ __forceinline__ void warp_sort_shuffle_stage(unsigned long long (&k)[R], int lane, int xor_mask, int low_bit) {
+    const bool lower = (lane & low_bit) == 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const unsigned long long p = __shfl_xor_sync(0xffffffffu, k[r], xor_mask);
+        k[r] = lower ? u64_min(k[r], p) : u64_max(k[r], p);
+    }
+}
+
+// The shuffle stages run as rolled loops (a fully unrolled network is ~14k SASS instructions and
+// thrashes the instruction cache); only the three in-register merge levels are unrolled.
+template <int R>
 __device__ __forceinline__ void warp_sort_regs(unsigned long long (&k)[R], int lane) {
+#pragma unroll 1
+    for (int size = 2; size <= 32; size <<= 1) {
+        warp_sort_shuffle_stage<R>(k, lane, size - 1, size >> 1);  // flip: partner lane ^ (size-1)
+#pragma unroll 1
+        for (int j = size >> 2; j > 0; j >>= 1) warp_sort_shuffle_stage<R>(k, lane, j, j);
+    }
 #pragma unroll
-    for (int size = 2; size <= 32 * R; size <<= 1) {
-        if (size <= 32) {
-            const bool lower = (lane & (size >> 1)) == 0;
+    for (int m = 2; m <= R; m <<= 1) {  // size = 32 m: flip partner is register r ^ (m-1), lane ^ 31
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const unsigned long long p = __shfl_xor_sync(0xffffffffu, k[r], size - 1);
-                k[r] = lower ? u64_min(k[r], p) : u64_max(k[r], p);
-            }
-        } else {
-            const int m = size / 32;  // partner: register r ^ (m-1), lane ^ 31
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if ((r & (m >> 1)) == 0) {
-                    const int r2 = r ^ (m - 1);
-                    const unsigned long long a = k[r], b = k[r2];
-                    const unsigned long long pa = __shfl_xor_sync(0xffffffffu, b, 31);
-                    const unsigned long long pb = __shfl_xor_sync(0xffffffffu, a, 31);
-                    k[r] = u64_min(a, pa);
-                    k[r2] = u64_max(b, pb);
-                }
+        for (int r = 0; r < R; ++r) {
+            if ((r & (m >> 1)) == 0) {
+                const int r2 = r ^ (m - 1);
+                const unsigned long long a = k[r], b = k[r2];
+                const unsigned long long pa = __shfl_xor_sync(0xffffffffu, b, 31);
+                const unsigned long long pb = __shfl_xor_sync(0xffffffffu, a, 31);
+                k[r] = u64_min(a, pa);
+                k[r2] = u64_max(b, pb);
             }
         }
 #pragma unroll
-        for (int j = size >> 2; j > 0; j >>= 1) {
-            if (j >= 32) {
-                const int jr = j / 32;
+        for (int jr = m >> 2; jr > 0; jr >>= 1) {  // strides 32 jr: in-thread exchanges
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if ((r & jr) == 0) {
-                        const unsigned long long a = k[r], b = k[r | jr];
-                        k[r] = u64_min(a, b);
-                        k[r | jr] = u64_max(a, b);
-                    }
-                }
-            } else {
-                const bool lower = (lane & j) == 0;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const unsigned long long p = __shfl_xor_sync(0xffffffffu, k[r], j);
-                    k[r] = lower ? u64_min(k[r], p) : u64_max(k[r], p);
+            for (int r = 0; r < R; ++r) {
+                if ((r & jr) == 0) {
+                    const unsigned long long a = k[r], b = k[r | jr];
+                    k[r] = u64_min(a, b);
+                    k[r | jr] = u64_max(a, b);
                 }
             }
         }
+#pragma unroll 1
+        for (int j = 16; j > 0; j >>= 1) warp_sort_shuffle_stage<R>(k, lane, j, j);
     }
 }
 
@@ -150,16 +150,18 @@ __device__ __forceinline__ void warp_sort_segment(const unsigned long long* __re
 // fits the register sort, then the whole CTA on every oversized segment (shared memory up to 4096
 // keys, in place on the L2-resident global segment beyond).  range(t, start, end) is called once per
 // tile by one thread.
+// `offsets` holds the exclusive scan of the (tile, replica) counters: tile t owns
+// [offsets[t*R], offsets[(t+1)*R]).
 template <class Emit>
-__device__ __forceinline__ void sort_tiles_cta(const int32_t* __restrict__ offsets, unsigned long long* __restrict__ keys,
-                                               int T, long long capacity, unsigned long long* s_keys,
-                                               int2* __restrict__ tile_range, Emit emit) {
+__device__ __forceinline__ void sort_tiles_cta(const int32_t* __restrict__ offsets, int R,
+                                               unsigned long long* __restrict__ keys, int T, long long capacity,
+                                               unsigned long long* s_keys, int2* __restrict__ tile_range, Emit emit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {
         const int t = blockIdx.x * kTilesPerSortCta + warp;
         if (t < T) {
-            const int start = offsets[t];
-            long long end = offsets[t + 1];
+            const int start = offsets[t * R];
+            long long end = offsets[(t + 1) * R];
             if (end > capacity) end = max((long long)start, capacity);  // speculative capacity too small
             const int n = (int)(end - start);
             if (lane == 0) tile_range[t] = (n > 0) ? make_int2(start, (int)end) : make_int2(0, 0);
@@ -171,8 +173,8 @@ __device__ __forceinline__ void sort_tiles_cta(const int32_t* __restrict__ offse
     for (int w = 0; w < kTilesPerSortCta; ++w) {
         const int t = blockIdx.x * kTilesPerSortCta + w;
         if (t >= T) break;
-        const int start = offsets[t];
-        long long end = offsets[t + 1];
+        const int start = offsets[t * R];
+        long long end = offsets[(t + 1) * R];
         if (end > capacity) end = max((long long)start, capacity);
         const int n = (int)(end - start);
         if (n <= kWarpSortMax) continue;  // uniform across the CTA
@@ -228,6 +230,14 @@ struct WarpTileWalk {
         return (o_y0 + row) * gx + o_x0 + (local - row * o_w);
     }
 };
+
+// Tile counters are replicated R ways (replica = CTA index mod R): atomics on one address serialise
+// in the L2 at roughly one per 50 cycles, and a 60k-Gaussian frame puts >100 of them on every tile.
+__host__ __device__ __forceinline__ int gfb_tile_replicas(int T) {
+    int r = 8;
+    while (r > 1 && (long long)T * r > 16384) r >>= 1;
+    return r;
+}
 
 __device__ __forceinline__ void red_add_s32(int32_t* p, int v) {
     asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

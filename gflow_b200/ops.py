@@ -250,14 +250,14 @@ def sort_gaussian(uv, depth, W, H, radius, tiles_touched):
     cap = _capacity_for(key, N)
     k_host = _ctypes.c_int64(0)
     with torch.cuda.device(dev):
-        tile_buf = torch.empty(2 * T + 1, device=dev, dtype=torch.int32)  # counts | offsets
+        tile_ws = torch.empty(_lib.gfb_sort_tile_workspace_bytes(W, H), device=dev, dtype=torch.uint8)
         tile_range = torch.empty(T, 2, device=dev, dtype=torch.int32)
         while True:
             keys = torch.empty(max(cap, 1), device=dev, dtype=torch.int64)
             ids = torch.empty(max(cap, 1), device=dev, dtype=torch.int32)
             rc = _lib.gfb_sort_gaussian(uv_c.data_ptr(), depth_c.data_ptr(), radius_c.data_ptr(), tiles_c.data_ptr(),
-                                        N, W, H, tile_buf.data_ptr(), tile_buf.data_ptr() + 4 * T, cap,
-                                        keys.data_ptr(), ids.data_ptr(), tile_range.data_ptr(),
+                                        N, W, H, tile_ws.data_ptr(), cap, keys.data_ptr(), ids.data_ptr(),
+                                        tile_range.data_ptr(),
                                         _ctypes.byref(k_host), _stream())
             K = int(k_host.value)
             if rc == GFB_E_CAPACITY:
@@ -468,10 +468,10 @@ class _Rasterize(torch.autograd.Function):
             gbuf = torch.empty(9 * max(N, 1), device=dev, dtype=torch.float32)
             gp = gbuf.data_ptr()
             p_uv, p_rect, p_depth, p_conic, p_radius = gp, gp + 8 * N, gp + 16 * N, gp + 20 * N, gp + 32 * N
-            # tile buffer (int32): range 2T (8-byte aligned) | offsets T+1 | control T+4
-            tbuf = torch.empty(4 * T + 8, device=dev, dtype=torch.int32)
+            # tile buffer: range 2T int32 (8-byte aligned) | control workspace
+            tbuf = torch.empty(8 * T + _lib.gfb_render_control_bytes(W, H), device=dev, dtype=torch.uint8)
             tp = tbuf.data_ptr()
-            p_rng, p_off, p_ctl = tp, tp + 8 * T, tp + 4 * (3 * T + 1)
+            p_rng, p_ctl = tp, tp + 8 * T
             out = torch.empty(C, H, W, device=dev, dtype=torch.float32)
             aux = torch.empty(2, H, W, device=dev, dtype=torch.float32)  # final_T | n_contrib (int32 bits)
             while True:
@@ -481,7 +481,7 @@ class _Rasterize(torch.autograd.Function):
                 rc = _lib.gfb_render_forward(
                     xyz_c.data_ptr(), scale_c.data_ptr(), rotate_c.data_ptr(), opacity_c.data_ptr(),
                     feature_c.data_ptr(), C, intr_c.data_ptr(), extr_c.data_ptr(), N, W, H, bg, nearest, extent,
-                    p_uv, p_depth, p_conic, p_radius, p_rect, p_ctl, p_off, p_rng, cap, kp + 48 * cap, kp + 56 * cap,
+                    p_uv, p_depth, p_conic, p_radius, p_rect, p_ctl, p_rng, cap, kp + 48 * cap, kp + 56 * cap,
                     kp, kp + 32 * cap, out.data_ptr(), aux.data_ptr(), aux.data_ptr() + 4 * H * W,
                     _ctypes.byref(k_host), _stream())
                 K = int(k_host.value)

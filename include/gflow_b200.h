@@ -77,29 +77,21 @@ int gfb_compute_sh_bwd(const float *shs, const float *dirs, const uint8_t *visib
                        const float *g_out, float *d_shs, float *d_dirs, void *stream);
 
 /* ------------------------------------------------------------------ msplat.sort_gaussian
- * call sites: render.py:52-54,138-140.  Two phases because the caller must size
- * gaussian_ids_sorted (K,) before phase 2:
- *   1. gfb_sort_count: per-tile intersection counts (tile_counts, T int32) and their
- *      exclusive scan (tile_offsets, T+1 int32; tile_offsets[T] = K).  The caller reads K back.
- *   2. gfb_sort_emit: scatter (depth bits, id) keys per tile into keys_ws
- *      (gfb_sort_workspace_bytes(K) bytes), sort every tile's segment, write
- *      gaussian_ids_sorted (K,) and tile_range (T,2).  tile_counts is consumed (counted down to 0).
- * The result equals a stable ascending sort of (tile << 32 | float bits of depth)
- * over a Gaussian-major emission. */
+ * call sites: render.py:52-54,138-140.
+ * Per-tile intersection counts -> exclusive scan (K) -> scatter of (depth bits, id) keys into every
+ * tile's segment -> one warp per tile sorts its segment.  The result equals a stable ascending sort
+ * of (tile << 32 | float bits of depth) over a Gaussian-major emission.
+ * K has to reach the host (the caller sizes gaussian_ids_sorted (K,)); to hide that read-back the
+ * caller passes a `capacity` (e.g. its previous K plus slack) for keys_ws (gfb_sort_workspace_bytes)
+ * and gaussian_ids_sorted, scatter + sort are enqueued speculatively, and the host waits only for
+ * count + scan on an internal event.  *K_host (HOST pointer) receives K.  Returns GFB_E_CAPACITY when
+ * K > capacity (outputs truncated; call again with capacity >= *K_host).
+ * tile_ws: gfb_sort_tile_workspace_bytes(W, H) bytes of scratch; tile_range (T,2) int32. */
 size_t gfb_sort_workspace_bytes(int64_t K);
-int gfb_sort_count(const float *uv, const int32_t *radius, const int32_t *tiles_touched, int N, int W, int H,
-                   int32_t *tile_counts, int32_t *tile_offsets, void *stream);
-int gfb_sort_emit(const float *uv, const float *depth, const int32_t *radius, const int32_t *tiles_touched, int N,
-                  int W, int H, int32_t *tile_counts, const int32_t *tile_offsets, int64_t K, void *keys_ws,
-                  int32_t *gaussian_ids_sorted, int32_t *tile_range, void *stream);
-
-/* One-call variant that hides the K read-back: the caller passes a capacity (e.g. its previous K
- * plus slack) for keys_ws / gaussian_ids_sorted; scatter + sort are enqueued speculatively, the
- * host waits only for count + scan, *K_host receives K.  Returns GFB_E_CAPACITY when K > capacity
- * (outputs truncated; call again with capacity >= *K_host).  Synchronises on an internal event. */
+size_t gfb_sort_tile_workspace_bytes(int W, int H);
 int gfb_sort_gaussian(const float *uv, const float *depth, const int32_t *radius, const int32_t *tiles_touched, int N,
-                      int W, int H, int32_t *tile_counts, int32_t *tile_offsets, int64_t capacity, void *keys_ws,
-                      int32_t *gaussian_ids_sorted, int32_t *tile_range, int64_t *K_host, void *stream);
+                      int W, int H, void *tile_ws, int64_t capacity, void *keys_ws, int32_t *gaussian_ids_sorted,
+                      int32_t *tile_range, int64_t *K_host, void *stream);
 
 /* ------------------------------------------------------------------ msplat.alpha_blending
  * call sites: render.py:58-64,68-74,84-90,99-105,148-154; backward via trainer.py:533.
@@ -144,7 +136,7 @@ int gfb_blend_unpack_grads(const float *grad_pack, int N, int C, int c0, int Cg,
  * operators.  1 <= C <= 4.  Buffers:
  *   uv (N,2) depth (N,1) conic (N,3) radius (N,1): per-Gaussian outputs (also msplat-visible)
  *   rect_ws   : N x 8 bytes        control_ws : gfb_render_control_bytes(W,H), any contents
- *   tile_offsets (T+1), tile_range (T,2) int32
+ *   tile_range (T,2) int32
  *   capacity  : number of intersections the K-sized buffers can hold:
  *               keys_ws (8 B), gaussian_ids_sorted (4 B), geom_stream (32 B), feat_stream (16 B) each
  *   out (C,H,W), final_T (H,W), n_contrib (H,W)
@@ -153,7 +145,7 @@ size_t gfb_render_control_bytes(int W, int H);
 int gfb_render_forward(const float *xyz, const float *scale, const float *rotate, const float *opacity,
                        const float *feature, int C, const float *intr, const float *extr, int N, int W, int H,
                        float bg, float nearest, float extent, float *uv, float *depth, float *conic, int32_t *radius,
-                       void *rect_ws, void *control_ws, int32_t *tile_offsets, int32_t *tile_range, int64_t capacity,
+                       void *rect_ws, void *control_ws, int32_t *tile_range, int64_t capacity,
                        void *keys_ws, int32_t *gaussian_ids_sorted, void *geom_stream, void *feat_stream, float *out,
                        float *final_T, int32_t *n_contrib, int64_t *K_host, void *stream);
 /* grad_ws: gfb_render_grad_bytes(N) bytes = N x 12 floats of packed per-Gaussian gradients followed by
