@@ -53,43 +53,11 @@ bin_count_kernel(const float2* __restrict__ uv, const int32_t* __restrict__ radi
     }
 }
 
-// Single CTA: exclusive scan of counts[0..T) into offsets[0..T].
+// Single CTA: exclusive scan of counts[0..n) into offsets[0..n].
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(const int32_t* __restrict__ counts, int T, int32_t* __restrict__ offsets) {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + threadIdx.x;
-        const int c = (t < T) ? counts[t] : 0;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += n;
-            }
-            s_warp[lane] = w;  // inclusive scan of warp totals
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - c;
-        if (t < T) offsets[t] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) offsets[T] = s_carry;
+tile_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets) {
+    __shared__ int s_warp[33];
+    cta_exclusive_scan(counts, n, offsets, s_warp);
 }
 
 __global__ void __launch_bounds__(kThreads)

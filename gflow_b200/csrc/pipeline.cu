@@ -44,8 +44,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                   int32_t* __restrict__ radius, ushort4* __restrict__ rect, int32_t* __restrict__ counts,
                   int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R) {
     __shared__ float s_cam[16];
-    __shared__ int s_scan[kThreads / 32];
-    __shared__ int s_carry;
+    __shared__ int s_scan[33];
     __shared__ bool s_last;
     load_camera(s_cam, intr, extr);
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
@@ -96,41 +95,12 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
     if (threadIdx.x == 0) {
         const int ticket = atomicAdd(ctrl + CTRL_DONE, 1);
         s_last = (ticket == (int)gridDim.x - 1);
-        s_carry = 0;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int TR = T * R;
-    for (int base = 0; base < TR; base += kThreads) {
-        const int t = base + threadIdx.x;
-        const int c = (t < TR) ? __ldcg(counts + t) : 0;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
-        int wofs = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) {
-            const int sw = s_scan[w];
-            if (w < warp) wofs += sw;
-            total += sw;
-        }
-        const int carry = s_carry;
-        if (t < TR) offsets[t] = carry + wofs + incl - c;
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry = carry + total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        offsets[TR] = s_carry;
-        ctrl[CTRL_K] = s_carry;
-    }
+    const int total = cta_exclusive_scan(counts, T * R, offsets, s_scan);
+    if (threadIdx.x == 0) ctrl[CTRL_K] = total;
 }
 
 __global__ void __launch_bounds__(kThreads)

@@ -242,3 +242,45 @@ __host__ __device__ __forceinline__ int gfb_tile_replicas(int T) {
 __device__ __forceinline__ void red_add_s32(int32_t* p, int v) {
     asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+
+// Exclusive scan of n int32 counters by ONE CTA (any block size that is a multiple of 32, <= 1024):
+// every thread owns a contiguous chunk, sums it (independent loads, one round of latency), the CTA
+// scans the per-thread sums, then each thread rewrites its chunk.  offsets[n] receives the total,
+// which is also returned to every thread.
+__device__ __forceinline__ int cta_exclusive_scan(const int32_t* __restrict__ counts, int n,
+                                                  int32_t* __restrict__ offsets, int* s_warp /* >= 33 ints */) {
+    const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (n + nthreads - 1) / nthreads;
+    const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += __ldcg(counts + i);
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = nthreads >> 5;
+        int w = (lane < nw) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_warp[lane] = w;  // inclusive scan of the warp totals
+        if (lane == 31) s_warp[32] = w;
+    }
+    __syncthreads();
+    int run = (warp ? s_warp[warp - 1] : 0) + incl - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int c = __ldcg(counts + i);
+        offsets[i] = run;
+        run += c;
+    }
+    const int total = s_warp[32];
+    if (tid == 0) offsets[n] = total;
+    return total;
+}

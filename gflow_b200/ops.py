@@ -28,8 +28,31 @@ TILE = 16
 
 
 # --------------------------------------------------------------------------- helpers
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device, as an int."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs ~10 us)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def _prep(t: torch.Tensor, name: str, dtype=torch.float32, shape=None) -> torch.Tensor:
@@ -43,7 +66,8 @@ def _prep(t: torch.Tensor, name: str, dtype=torch.float32, shape=None) -> torch.
     if shape is not None:
         if t.dim() != len(shape) or any(s is not None and int(d) != s for d, s in zip(t.shape, shape)):
             raise RuntimeError(f"gflow_b200: {name} must have shape {shape}, got {tuple(t.shape)}")
-    t = t.detach()
+    if t.requires_grad:
+        t = t.detach()
     if not t.is_contiguous():
         t = t.contiguous()
     if t.data_ptr() % 16 != 0:
@@ -95,7 +119,7 @@ class _ProjectPoint(torch.autograd.Function):
         extr_c = _prep(extr, "extr", shape=(3, 4))
         dev = _same_device(xyz_c, intr_c, extr_c)
         N = xyz_c.shape[0]
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             uv = torch.empty(N, 2, device=dev, dtype=torch.float32)
             depth = torch.empty(N, 1, device=dev, dtype=torch.float32)
             capi.check(_lib.gfb_project_point_fwd(xyz_c.data_ptr(), intr_c.data_ptr(), extr_c.data_ptr(), N, W, H,
@@ -111,7 +135,7 @@ class _ProjectPoint(torch.autograd.Function):
         W, H, nearest, extent = ctx.meta
         N = xyz.shape[0]
         dev = xyz.device
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             g_uv = torch.zeros(N, 2, device=dev) if g_uv is None else _prep(g_uv, "grad uv")
             g_depth = None if g_depth is None else _prep(g_depth, "grad depth")
             d_xyz = torch.empty(N, 3, device=dev, dtype=torch.float32)
@@ -138,7 +162,7 @@ class _ComputeCov3D(torch.autograd.Function):
         if rotate_c.shape[0] != N:
             raise RuntimeError("gflow_b200: scale and rotate must have the same number of rows")
         vis = _vis(visible, N, dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             cov3d = torch.empty(N, 6, device=dev, dtype=torch.float32)
             capi.check(_lib.gfb_compute_cov3d_fwd(scale_c.data_ptr(), rotate_c.data_ptr(), _ptr(vis), N,
                                                   cov3d.data_ptr(), _stream()), "compute_cov3d forward")
@@ -151,7 +175,7 @@ class _ComputeCov3D(torch.autograd.Function):
         scale, rotate = ctx.saved_tensors
         N = scale.shape[0]
         dev = scale.device
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             g_cov = _prep(g_cov, "grad cov3d")
             d_scale = torch.empty(N, 3, device=dev, dtype=torch.float32)
             d_rotate = torch.empty(N, 4, device=dev, dtype=torch.float32)
@@ -178,7 +202,7 @@ class _EwaProject(torch.autograd.Function):
         uv_c = _prep(uv, "uv", shape=(N, 2))
         dev = _same_device(xyz_c, cov_c, intr_c, extr_c, uv_c)
         vis = _vis(visible, N, dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             conic = torch.empty(N, 3, device=dev, dtype=torch.float32)
             radius = torch.empty(N, 1, device=dev, dtype=torch.int32)
             tiles = torch.empty(N, 1, device=dev, dtype=torch.int32)
@@ -198,7 +222,7 @@ class _EwaProject(torch.autograd.Function):
         W, H = ctx.meta
         N = xyz.shape[0]
         dev = xyz.device
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             g_conic = _prep(g_conic, "grad conic")
             d_xyz = torch.empty(N, 3, device=dev, dtype=torch.float32)
             d_cov = torch.empty(N, 6, device=dev, dtype=torch.float32)
@@ -249,7 +273,7 @@ def sort_gaussian(uv, depth, W, H, radius, tiles_touched):
     key = (dev.index, N, W, H)
     cap = _capacity_for(key, N)
     k_host = _ctypes.c_int64(0)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         tile_ws = torch.empty(_lib.gfb_sort_tile_workspace_bytes(W, H), device=dev, dtype=torch.uint8)
         tile_range = torch.empty(T, 2, device=dev, dtype=torch.int32)
         while True:
@@ -331,7 +355,7 @@ class _AlphaBlending(torch.autograd.Function):
         dev = _same_device(uv_c, conic_c, opacity_c, feature_c, ids_c, tr_c)
         K = ids_c.numel()
         st = _stream
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             if geom_stream is None:
                 geom_stream = _pack_geometry(uv_c, conic_c, opacity_c, ids_c, K)
             out = torch.empty(C, H, W, device=dev, dtype=torch.float32)
@@ -358,7 +382,7 @@ class _AlphaBlending(torch.autograd.Function):
         N, C, K, bg, W, H = ctx.meta
         dev = geom_stream.device
         st = _stream
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             g_out = _prep(g_out, "grad feature_map", shape=(C, H, W))
             d_uv = torch.empty(N, 2, device=dev, dtype=torch.float32)
             d_conic = torch.empty(N, 3, device=dev, dtype=torch.float32)
@@ -391,7 +415,7 @@ def alpha_blending(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range,
         if geom_stream is None and uv.dtype == conic.dtype == opacity.dtype == torch.float32 \
                 and gaussian_ids_sorted.dtype == torch.int32 and uv.dim() == 2 and conic.dim() == 2 \
                 and conic.shape == (uv.shape[0], 3) and opacity.numel() == uv.shape[0]:
-            with torch.no_grad(), torch.cuda.device(uv.device):
+            with torch.no_grad(), _on_device(uv.device):
                 geom_stream = _pack_geometry(_prep(uv, "uv", shape=(None, 2)), _prep(conic, "conic"),
                                              _prep(opacity, "opacity").reshape(-1),
                                              _prep(gaussian_ids_sorted, "gaussian_ids_sorted", dtype=torch.int32)
@@ -412,7 +436,7 @@ class _ComputeSH(torch.autograd.Function):
         dirs_c = _prep(dirs, "dirs", shape=(N, 3))
         dev = _same_device(shs_c, dirs_c)
         vis = _vis(visible, N, dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             out = torch.empty(N, C, device=dev, dtype=torch.float32)
             capi.check(_lib.gfb_compute_sh_fwd(shs_c.data_ptr(), dirs_c.data_ptr(), _ptr(vis), N, C, K,
                                                out.data_ptr(), _stream()), "compute_sh forward")
@@ -425,7 +449,7 @@ class _ComputeSH(torch.autograd.Function):
         shs, dirs = ctx.saved_tensors
         N, C, K = shs.shape
         dev = shs.device
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             g_out = _prep(g_out, "grad sh colour", shape=(N, C))
             d_shs = torch.empty(N, C, K, device=dev, dtype=torch.float32)
             d_dirs = torch.empty(N, 3, device=dev, dtype=torch.float32)
@@ -463,7 +487,7 @@ class _Rasterize(torch.autograd.Function):
         key = (dev.index, N, W, H)
         cap = _capacity_for(key, N)
         k_host = _ctypes.c_int64(0)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             # per-Gaussian buffer (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N
             gbuf = torch.empty(9 * max(N, 1), device=dev, dtype=torch.float32)
             gp = gbuf.data_ptr()
@@ -500,7 +524,7 @@ class _Rasterize(torch.autograd.Function):
         xyz, scale, rotate, intr, extr, kbuf, tbuf, aux = ctx.saved_tensors
         N, C, T, cap, W, H, bg, nearest, extent = ctx.meta
         dev = xyz.device
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             g_out = _prep(g_out, "grad feature_map", shape=(C, H, W))
             grad_ws = torch.empty(12 * N + 16, device=dev, dtype=torch.float32)
             # d_rotate 4N | d_xyz 3N | d_scale 3N | d_opacity N | d_feature CN
