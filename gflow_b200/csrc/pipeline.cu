@@ -44,7 +44,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                   int32_t* __restrict__ radius, ushort4* __restrict__ rect, int32_t* __restrict__ counts,
                   int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R) {
     __shared__ float s_cam[16];
-    __shared__ int s_scan[33];
+    __shared__ int s_scan[34];
     __shared__ bool s_last;
     load_camera(s_cam, intr, extr);
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;

@@ -243,44 +243,55 @@ __device__ __forceinline__ void red_add_s32(int32_t* p, int v) {
     asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Exclusive scan of n int32 counters by ONE CTA (any block size that is a multiple of 32, <= 1024):
-// every thread owns a contiguous chunk, sums it (independent loads, one round of latency), the CTA
-// scans the per-thread sums, then each thread rewrites its chunk.  offsets[n] receives the total,
-// which is also returned to every thread.
+// Exclusive scan of n int32 counters by ONE CTA (block size a multiple of 32, <= 1024), in rounds of
+// blockDim * 16 counters: every thread loads its 16 contiguous counters at once (independent loads,
+// one round of memory latency, 64-byte vector-friendly), the CTA scans the per-thread sums, and the
+// thread writes its 16 offsets from registers.  offsets[n] receives the total, which is returned.
 __device__ __forceinline__ int cta_exclusive_scan(const int32_t* __restrict__ counts, int n,
-                                                  int32_t* __restrict__ offsets, int* s_warp /* >= 33 ints */) {
-    const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chunk = (n + nthreads - 1) / nthreads;
-    const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += __ldcg(counts + i);
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp[warp] = incl;
+                                                  int32_t* __restrict__ offsets, int* s_warp /* >= 34 ints */) {
+    constexpr int kPer = 16;
+    const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+    if (tid == 0) s_warp[33] = 0;  // running carry
     __syncthreads();
-    if (warp == 0) {
-        const int nw = nthreads >> 5;
-        int w = (lane < nw) ? s_warp[lane] : 0;
+    for (int round0 = 0; round0 < n; round0 += nthreads * kPer) {
+        const int lo = round0 + tid * kPer;
+        int c[kPer];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            c[k] = (lo + k < n) ? __ldcg(counts + lo + k) : 0;
+            sum += c[k];
+        }
+        int incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += v;
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        s_warp[lane] = w;  // inclusive scan of the warp totals
-        if (lane == 31) s_warp[32] = w;
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = (lane < nw) ? s_warp[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            s_warp[lane] = w;  // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        const int carry = s_warp[33];
+        int run = carry + (warp ? s_warp[warp - 1] : 0) + incl - sum;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            if (lo + k < n) offsets[lo + k] = run;
+            run += c[k];
+        }
+        __syncthreads();
+        if (tid == 0) s_warp[33] = carry + s_warp[31];
+        __syncthreads();
     }
-    __syncthreads();
-    int run = (warp ? s_warp[warp - 1] : 0) + incl - sum;
-    for (int i = lo; i < hi; ++i) {
-        const int c = __ldcg(counts + i);
-        offsets[i] = run;
-        run += c;
-    }
-    const int total = s_warp[32];
+    const int total = s_warp[33];
     if (tid == 0) offsets[n] = total;
     return total;
 }
