@@ -54,10 +54,11 @@ bin_count_kernel(const float2* __restrict__ uv, const int32_t* __restrict__ radi
 }
 
 // Single CTA: exclusive scan of counts[0..n) into offsets[0..n].
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets) {
+    __shared__ int s_buf[kScanRound];
     __shared__ int s_warp[34];
-    cta_exclusive_scan(counts, n, offsets, s_warp);
+    cta_exclusive_scan(counts, n, offsets, s_buf, s_warp);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -130,7 +131,7 @@ int gfb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
                                                                        tiles_touched, N, gx, gy, R, counts);
         GFB_CHECK_LAUNCH();
     }
-    tile_scan_kernel<<<1, 1024, 0, st>>>(counts, T * R, offsets);
+    tile_scan_kernel<<<1, kScanThreads, 0, st>>>(counts, T * R, offsets);
     GFB_CHECK_LAUNCH();
     GFB_TRY(cudaMemcpyAsync(pinned, offsets + (size_t)T * R, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GFB_TRY(cudaEventRecord(ev, st));

@@ -45,6 +45,8 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                   int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R) {
     __shared__ float s_cam[16];
     __shared__ int s_scan[34];
+    __shared__ int s_buf[kScanRound];
+    static_assert(kThreads == kScanThreads, "the last CTA of preprocess runs the scan");
     __shared__ bool s_last;
     load_camera(s_cam, intr, extr);
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
@@ -99,7 +101,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int total = cta_exclusive_scan(counts, T * R, offsets, s_scan);
+    const int total = cta_exclusive_scan(counts, T * R, offsets, s_buf, s_scan);
     if (threadIdx.x == 0) ctrl[CTRL_K] = total;
 }
 

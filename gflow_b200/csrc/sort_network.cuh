@@ -243,23 +243,35 @@ __device__ __forceinline__ void red_add_s32(int32_t* p, int v) {
     asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Exclusive scan of n int32 counters by ONE CTA (block size a multiple of 32, <= 1024), in rounds of
-// blockDim * 16 counters: every thread loads its 16 contiguous counters at once (independent loads,
-// one round of memory latency, 64-byte vector-friendly), the CTA scans the per-thread sums, and the
-// thread writes its 16 offsets from registers.  offsets[n] receives the total, which is returned.
+// Exclusive scan of n int32 counters by ONE CTA of kScanThreads threads, in rounds of 4096 counters
+// staged through shared memory: coalesced global loads (one 128-byte line per warp instruction;
+// per-thread contiguous chunks read straight from global would touch 16 lines per instruction),
+// each thread scans 16 contiguous counters out of shared memory, the CTA scans the per-thread sums,
+// and the offsets go back through shared memory with coalesced stores.  offsets[n] receives the
+// total, which is returned to every thread.
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 16;
+constexpr int kScanRound = kScanThreads * kScanPer;  // 4096 ints = 16 KB of shared memory
+
 __device__ __forceinline__ int cta_exclusive_scan(const int32_t* __restrict__ counts, int n,
-                                                  int32_t* __restrict__ offsets, int* s_warp /* >= 34 ints */) {
-    constexpr int kPer = 16;
-    const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+                                                  int32_t* __restrict__ offsets, int* s_buf /* kScanRound */,
+                                                  int* s_warp /* >= 34 ints */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nw = kScanThreads / 32;
     if (tid == 0) s_warp[33] = 0;  // running carry
     __syncthreads();
-    for (int round0 = 0; round0 < n; round0 += nthreads * kPer) {
-        const int lo = round0 + tid * kPer;
-        int c[kPer];
+    for (int round0 = 0; round0 < n; round0 += kScanRound) {
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) {
+            const int i = round0 + k * kScanThreads + tid;
+            s_buf[k * kScanThreads + tid] = (i < n) ? __ldcg(counts + i) : 0;
+        }
+        __syncthreads();
+        int c[kScanPer];
         int sum = 0;
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            c[k] = (lo + k < n) ? __ldcg(counts + lo + k) : 0;
+        for (int k = 0; k < kScanPer; ++k) {
+            c[k] = s_buf[tid * kScanPer + k];
             sum += c[k];
         }
         int incl = sum;
@@ -277,17 +289,22 @@ __device__ __forceinline__ int cta_exclusive_scan(const int32_t* __restrict__ co
                 const int v = __shfl_up_sync(0xffffffffu, w, o);
                 if (lane >= o) w += v;
             }
-            s_warp[lane] = w;  // inclusive scan of the warp totals
+            s_warp[lane] = w;  // inclusive scan of the warp totals (entries >= nw repeat the total)
         }
         __syncthreads();
         const int carry = s_warp[33];
         int run = carry + (warp ? s_warp[warp - 1] : 0) + incl - sum;
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            if (lo + k < n) offsets[lo + k] = run;
+        for (int k = 0; k < kScanPer; ++k) {
+            s_buf[tid * kScanPer + k] = run;
             run += c[k];
         }
         __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) {
+            const int i = round0 + k * kScanThreads + tid;
+            if (i < n) offsets[i] = s_buf[k * kScanThreads + tid];
+        }
         if (tid == 0) s_warp[33] = carry + s_warp[31];
         __syncthreads();
     }

@@ -11,6 +11,7 @@ echo "== build" ; timeout 600 python __graft_entry__.py > $OUT/build_${TAG}.log 
 echo "== smoke" ; timeout 300 python __graft_entry__.py smoke > $OUT/smoke_${TAG}.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke_${TAG}.log
 echo "== pytest gpu" ; timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > $OUT/pytest_${TAG}.log 2>&1; echo "pytest rc=$?"; tail -25 $OUT/pytest_${TAG}.log
 echo "== bench" ; timeout 600 python bench.py --steps 100 --warmup 10 > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err; echo "bench rc=$?"; cat $OUT/bench_${TAG}.json; tail -5 $OUT/bench_${TAG}.err
+echo "== in-situ kernel times"; timeout 300 python tools/kernel_times.py fused 20 cfg2 synthetic flush > $OUT/kernel_times_fused_${TAG}.txt 2>&1; tail -12 $OUT/kernel_times_fused_${TAG}.txt; timeout 300 python tools/kernel_times.py chain 20 cfg2 synthetic flush > $OUT/kernel_times_chain_${TAG}.txt 2>&1; tail -32 $OUT/kernel_times_chain_${TAG}.txt
 if [ -z "$QUICK" ]; then
 echo "== bench gflow profile" ; timeout 600 python bench.py --steps 50 --warmup 5 --profile gflow --no-cpu-baseline > $OUT/bench_gflow_${TAG}.json 2>> $OUT/bench_${TAG}.err; cat $OUT/bench_gflow_${TAG}.json
 echo "== ncu launch list (fused step)" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches_fused_${TAG}.csv python tools/run_steps.py fused 4 > $OUT/ncu_list_${TAG}.log 2>&1; echo "rc=$?"
