@@ -264,7 +264,9 @@ __device__ __forceinline__ int cta_exclusive_scan(const int32_t* __restrict__ co
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
             const int i = round0 + k * kScanThreads + tid;
-            s_buf[k * kScanThreads + tid] = (i < n) ? __ldcg(counts + i) : 0;
+            // plain (coalescing) load: the counters were only ever touched by L2 atomics, so no SM holds
+            // a stale L1 copy; ld.cg compiles to LDG.STRONG.GPU here, which does not coalesce (13 us for 13k)
+            s_buf[k * kScanThreads + tid] = (i < n) ? counts[i] : 0;
         }
         __syncthreads();
         int c[kScanPer];

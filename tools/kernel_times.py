@@ -47,7 +47,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 tot = collections.OrderedDict()
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:
-        name = e.name.split("(")[0].replace("void ", "").replace("(anonymous namespace)::", "")[:70]
+        name = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:70]
         d = tot.setdefault(name, [0.0, 0])
         d[0] += e.device_time if hasattr(e, "device_time") else e.cuda_time
         d[1] += 1
