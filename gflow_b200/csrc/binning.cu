@@ -56,7 +56,7 @@ bin_count_kernel(const float2* __restrict__ uv, const int32_t* __restrict__ radi
 // Single CTA: exclusive scan of counts[0..n) into offsets[0..n].
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets) {
-    __shared__ int s_buf[kScanRound];
+    __shared__ int s_buf[kScanSmemInts];
     __shared__ int s_warp[34];
     cta_exclusive_scan(counts, n, offsets, s_buf, s_warp);
 }

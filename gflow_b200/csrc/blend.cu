@@ -16,16 +16,15 @@
 //  * One CTA per 16x16 tile.  Batches of 128 records are staged into shared memory by
 //    1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx), double buffered, issued by
 //    one thread; no thread does scattered global gathers inside the blend loop.
-//  * Each warp owns an 8x4 pixel block split into two independent 4x4 half-warp blocks.  Per 32
-//    records, the lanes test the records' bboxes against both blocks in parallel (one LDS.128
-//    each), ballot twice, and the two half-warps then walk their own surviving records in lock
-//    step (one warp instruction serves two different records).  With sigma ~ 1 px splats this
-//    removes ~9/10 of the (pixel, Gaussian) evaluations of a 256-pixel-per-Gaussian tile walk;
-//    results are unchanged because a culled pair has alpha < 1/255 and would have been skipped.
-//  * Backward: same staging back to front; the per-lane gradients of a (half-warp, Gaussian) pair
-//    are reduced with a transposed butterfly (8 shuffles for 8 values instead of 32) and added with
-//    one RED per value into a packed 48-byte-per-Gaussian gradient record, so the (up to) ten
-//    atomics of a record hit one or two L2 sectors.
+//  * Each warp owns an 8x4 pixel block.  Per 32 records, the lanes test the records' bboxes
+//    against the warp's block in parallel (one LDS.128 each), ballot, and the warp then walks
+//    only the surviving records.  With sigma ~ 1 px splats this removes ~4/5 of the
+//    (pixel, Gaussian) evaluations of a 256-pixel-per-Gaussian tile walk; results are
+//    unchanged because a culled pair has alpha < 1/255 and would have been skipped.
+//  * Backward: same staging back to front; the per-lane gradients of a (warp, Gaussian) pair
+//    are reduced with a transposed butterfly (9 shuffles for 8 values instead of 40) and
+//    added with one RED per value into a packed 48-byte-per-Gaussian gradient record, so
+//    the (up to) ten atomics of a warp hit one or two L2 sectors.
 //  No tensor cores: this is a gather / scatter bounded by issue rate and L2 atomics.
 #include "splat_math.cuh"
 
@@ -146,13 +145,10 @@ blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
     const int2 range = tile_range[tile];
     const int n = range.y - range.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // a warp covers 8x4 pixels as two independent 4x4 half-warp blocks (lanes 0-15 | 16-31)
-    const int half = lane >> 4, hl = lane & 15;
-    const int wx0 = tx * GFB_TILE + (warp & 1) * 8, by0 = ty * GFB_TILE + (warp >> 1) * 4;
-    const int px = wx0 + half * 4 + (hl & 3), py = by0 + (hl >> 2);
+    const int bx0 = tx * GFB_TILE + (warp & 1) * 8, by0 = ty * GFB_TILE + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = (px < W) && (py < H);
-    const float ax0 = (float)wx0, ax1 = (float)(wx0 + 3), bx0 = (float)(wx0 + 4), bx1 = (float)(wx0 + 7);
-    const float fy0 = (float)by0, fy1 = (float)(by0 + 3);
+    const float fx0 = (float)bx0, fx1 = (float)(bx0 + 7), fy0 = (float)by0, fy1 = (float)(by0 + 3);
     const float pxf = (float)px, pyf = (float)py;
 
     float T = 1.0f;
@@ -183,22 +179,17 @@ blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
             if (!__all_sync(kFull, done)) {
                 for (int base = 0; base < cnt; base += 32) {
                     const int j = base + lane;
-                    bool hit0 = false, hit1 = false;
+                    bool hit = false;
                     if (j < cnt) {
                         const float4 a4 = st.A[j];
-                        const bool hy = (a4.y + a4.w >= fy0) && (a4.y - a4.w <= fy1);
-                        hit0 = hy && (a4.x + a4.z >= ax0) && (a4.x - a4.z <= ax1);
-                        hit1 = hy && (a4.x + a4.z >= bx0) && (a4.x - a4.z <= bx1);
+                        hit = (a4.x + a4.z >= fx0) && (a4.x - a4.z <= fx1) && (a4.y + a4.w >= fy0) &&
+                              (a4.y - a4.w <= fy1);
                     }
-                    unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-                    // the two half-warps walk their own survivor lists in lock step: one iteration
-                    // serves one record per half (two different records per warp instruction)
-                    while (m0 | m1) {
-                        const unsigned mine = half ? m1 : m0;
-                        const int jj = base + __ffs(mine) - 1;
-                        m0 &= m0 - 1;
-                        m1 &= m1 - 1;
-                        if (mine != 0 && !done) {
+                    unsigned m = __ballot_sync(kFull, hit);
+                    while (m) {
+                        const int jj = base + __ffs(m) - 1;
+                        m &= m - 1;
+                        if (!done) {
                             const float4 a4 = st.A[jj];
                             const float4 b4 = st.B[jj];
                             const float dx = a4.x - pxf, dy = a4.y - pyf;
@@ -242,38 +233,33 @@ blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
 }
 
 // ------------------------------------------------------------------ backward
-// Transposed butterfly inside each 16-lane half: every lane contributes v[0..7]; afterwards lane 2k of
-// the half holds the half's total of slot k (k = 0..7).  4 + 2 + 1 + 1 = 8 shuffles.
-__device__ __forceinline__ float half_reduce8(const float (&v)[8], int lane) {
+// Transposed butterfly: every lane contributes v[0..7]; afterwards lane 4k holds the warp
+// total of slot k (k = 0..7).  4 + 2 + 1 + 1 + 1 = 9 shuffles.
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
     float r4[4], r2[2], r1;
-    const bool up8 = (lane & 8) != 0;
+    const bool up16 = (lane & 16) != 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float send = up8 ? v[i] : v[i + 4];
-        const float keep = up8 ? v[i + 4] : v[i];
-        r4[i] = keep + __shfl_xor_sync(kFull, send, 8);
+        const float send = up16 ? v[i] : v[i + 4];
+        const float keep = up16 ? v[i + 4] : v[i];
+        r4[i] = keep + __shfl_xor_sync(kFull, send, 16);
     }
-    const bool up4 = (lane & 4) != 0;
+    const bool up8 = (lane & 8) != 0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const float send = up4 ? r4[i] : r4[i + 2];
-        const float keep = up4 ? r4[i + 2] : r4[i];
-        r2[i] = keep + __shfl_xor_sync(kFull, send, 4);
+        const float send = up8 ? r4[i] : r4[i + 2];
+        const float keep = up8 ? r4[i + 2] : r4[i];
+        r2[i] = keep + __shfl_xor_sync(kFull, send, 8);
     }
-    const bool up2 = (lane & 2) != 0;
+    const bool up4 = (lane & 4) != 0;
     {
-        const float send = up2 ? r2[0] : r2[1];
-        const float keep = up2 ? r2[1] : r2[0];
-        r1 = keep + __shfl_xor_sync(kFull, send, 2);
+        const float send = up4 ? r2[0] : r2[1];
+        const float keep = up4 ? r2[1] : r2[0];
+        r1 = keep + __shfl_xor_sync(kFull, send, 4);
     }
+    r1 += __shfl_xor_sync(kFull, r1, 2);
     r1 += __shfl_xor_sync(kFull, r1, 1);
-    return r1;  // slot ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1)
-}
-
-__device__ __forceinline__ float half_sum(float v) {
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    return v;
+    return r1;  // slot ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1)
 }
 
 template <int CG>
@@ -292,13 +278,10 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
     const int n = range.y - range.x;
     if (n <= 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = lane >> 4, hl = lane & 15;
-    const unsigned half_mask = half ? 0xffff0000u : 0x0000ffffu;
-    const int wx0 = tx * GFB_TILE + (warp & 1) * 8, by0 = ty * GFB_TILE + (warp >> 1) * 4;
-    const int px = wx0 + half * 4 + (hl & 3), py = by0 + (hl >> 2);
+    const int bx0 = tx * GFB_TILE + (warp & 1) * 8, by0 = ty * GFB_TILE + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = (px < W) && (py < H);
-    const float ax0 = (float)wx0, ax1 = (float)(wx0 + 3), bx0 = (float)(wx0 + 4), bx1 = (float)(wx0 + 7);
-    const float fy0 = (float)by0, fy1 = (float)(by0 + 3);
+    const float fx0 = (float)bx0, fx1 = (float)(bx0 + 7), fy0 = (float)by0, fy1 = (float)(by0 + 3);
     const float pxf = (float)px, pyf = (float)py;
 
     float Tf = 1.0f;
@@ -318,10 +301,7 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
 #pragma unroll
     for (int c = 0; c < CG; ++c) bgdot = fmaf(bg, go[c], bgdot);
 
-    // last contributor per half-warp block (cull bound) and per tile (batch bound)
-    const int hmax = __reduce_max_sync(half_mask, last);
-    const int hmax0 = __shfl_sync(kFull, hmax, 0), hmax1 = __shfl_sync(kFull, hmax, 16);
-    const int wmax = max(hmax0, hmax1);
+    const int wmax = __reduce_max_sync(kFull, last);
     if (tid == 0) {
         s_max_last = 0;
         mbar_init(&s_bar[0], 1);
@@ -344,7 +324,6 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
     float accum[CG], lastc[CG];
 #pragma unroll
     for (int c = 0; c < CG; ++c) accum[c] = lastc[c] = 0.0f;
-    constexpr int kSlots8 = 6 + (CG > 1 ? 2 : 1);  // values that ride the 8-slot butterfly
 
     for (int it = 0; it < nb; ++it) {
         const int b = nb - 1 - it;
@@ -359,28 +338,24 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
         if (pos0 < wmax) {
             for (int base = ((cnt - 1) >> 5) << 5; base >= 0; base -= 32) {
                 const int j = base + lane;
-                bool hit0 = false, hit1 = false;
-                if (j < cnt) {
+                bool hit = false;
+                if (j < cnt && pos0 + j < wmax) {
                     const float4 a4 = st.A[j];
-                    const bool hy = (a4.y + a4.w >= fy0) && (a4.y - a4.w <= fy1);
-                    hit0 = hy && (pos0 + j < hmax0) && (a4.x + a4.z >= ax0) && (a4.x - a4.z <= ax1);
-                    hit1 = hy && (pos0 + j < hmax1) && (a4.x + a4.z >= bx0) && (a4.x - a4.z <= bx1);
+                    hit = (a4.x + a4.z >= fx0) && (a4.x - a4.z <= fx1) && (a4.y + a4.w >= fy0) &&
+                          (a4.y - a4.w <= fy1);
                 }
-                unsigned m0 = __ballot_sync(kFull, hit0), m1 = __ballot_sync(kFull, hit1);
-                // back to front; each half-warp walks its own survivors, one record per half per iteration
-                while (m0 | m1) {
-                    const unsigned mine = half ? m1 : m0;
-                    const int bit = 31 - __clz(mine);  // -1 when this half has nothing left
-                    if (m0) m0 &= ~(1u << (31 - __clz(m0)));
-                    if (m1) m1 &= ~(1u << (31 - __clz(m1)));
-                    const int jj = base + max(bit, 0);
+                unsigned m = __ballot_sync(kFull, hit);
+                while (m) {
+                    const int bit = 31 - __clz(m);
+                    m &= ~(1u << bit);
+                    const int jj = base + bit;
                     const int pos = pos0 + jj;
                     float v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = 0.0f;
                     float v8 = 0.0f, v9 = 0.0f;
                     bool act = false;
-                    if (bit >= 0 && pos < last) {
+                    if (pos < last) {
                         const float4 a4 = st.A[jj];
                         const float4 b4 = st.B[jj];
                         const float dx = a4.x - pxf, dy = a4.y - pyf;
@@ -422,22 +397,19 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                             }
                         }
                     }
-                    const unsigned am = __ballot_sync(kFull, act);
-                    if (am == 0) continue;
-                    const float r = half_reduce8(v, lane);
-                    if (CG > 2) v8 = half_sum(v8);
-                    if (CG > 3) v9 = half_sum(v9);
-                    if (am & half_mask) {
-                        const int id = ids[(long long)range.x + pos];
-                        float* gp = grad_pack + (size_t)id * 12;
-                        if ((hl & 1) == 0) {
-                            const int slot = hl >> 1;
-                            if (slot < kSlots8) atomicAdd(gp + slot, r);
-                        } else if (hl == 1) {
-                            if (CG > 2) atomicAdd(gp + 8, v8);
-                        } else if (hl == 3) {
-                            if (CG > 3) atomicAdd(gp + 9, v9);
-                        }
+                    if (!__any_sync(kFull, act)) continue;
+                    const float r = warp_reduce8(v, lane);
+                    if (CG > 2) v8 = gfb_warp_sum(v8);
+                    if (CG > 3) v9 = gfb_warp_sum(v9);
+                    const int id = ids[(long long)range.x + pos];
+                    float* gp = grad_pack + (size_t)id * 12;
+                    if ((lane & 3) == 0) {
+                        const int slot = lane >> 2;
+                        if (slot < 6 + (CG > 1 ? 2 : 1)) atomicAdd(gp + slot, r);
+                    } else if (lane == 1) {
+                        if (CG > 2) atomicAdd(gp + 8, v8);
+                    } else if (lane == 2) {
+                        if (CG > 3) atomicAdd(gp + 9, v9);
                     }
                 }
             }

@@ -45,7 +45,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                   int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R) {
     __shared__ float s_cam[16];
     __shared__ int s_scan[34];
-    __shared__ int s_buf[kScanRound];
+    __shared__ int s_buf[kScanSmemInts];
     static_assert(kThreads == kScanThreads, "the last CTA of preprocess runs the scan");
     __shared__ bool s_last;
     load_camera(s_cam, intr, extr);

@@ -251,10 +251,12 @@ __device__ __forceinline__ void red_add_s32(int32_t* p, int v) {
 // total, which is returned to every thread.
 constexpr int kScanThreads = 256;
 constexpr int kScanPer = 16;
-constexpr int kScanRound = kScanThreads * kScanPer;  // 4096 ints = 16 KB of shared memory
+constexpr int kScanRound = kScanThreads * kScanPer;  // 4096 counters per round
+constexpr int kScanPitch = kScanPer + 1;                // per-thread row pitch 17: conflict-free
+constexpr int kScanSmemInts = kScanThreads * kScanPitch;
 
 __device__ __forceinline__ int cta_exclusive_scan(const int32_t* __restrict__ counts, int n,
-                                                  int32_t* __restrict__ offsets, int* s_buf /* kScanRound */,
+                                                  int32_t* __restrict__ offsets, int* s_buf /* kScanSmemInts */,
                                                   int* s_warp /* >= 34 ints */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nw = kScanThreads / 32;
@@ -263,17 +265,17 @@ __device__ __forceinline__ int cta_exclusive_scan(const int32_t* __restrict__ co
     for (int round0 = 0; round0 < n; round0 += kScanRound) {
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
-            const int i = round0 + k * kScanThreads + tid;
+            const int e = k * kScanThreads + tid, i = round0 + e;
             // plain (coalescing) load: the counters were only ever touched by L2 atomics, so no SM holds
             // a stale L1 copy; ld.cg compiles to LDG.STRONG.GPU here, which does not coalesce (13 us for 13k)
-            s_buf[k * kScanThreads + tid] = (i < n) ? counts[i] : 0;
+            s_buf[(e >> 4) * kScanPitch + (e & 15)] = (i < n) ? counts[i] : 0;
         }
         __syncthreads();
         int c[kScanPer];
         int sum = 0;
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
-            c[k] = s_buf[tid * kScanPer + k];
+            c[k] = s_buf[tid * kScanPitch + k];
             sum += c[k];
         }
         int incl = sum;
@@ -298,14 +300,14 @@ __device__ __forceinline__ int cta_exclusive_scan(const int32_t* __restrict__ co
         int run = carry + (warp ? s_warp[warp - 1] : 0) + incl - sum;
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
-            s_buf[tid * kScanPer + k] = run;
+            s_buf[tid * kScanPitch + k] = run;
             run += c[k];
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
-            const int i = round0 + k * kScanThreads + tid;
-            if (i < n) offsets[i] = s_buf[k * kScanThreads + tid];
+            const int e = k * kScanThreads + tid, i = round0 + e;
+            if (i < n) offsets[i] = s_buf[(e >> 4) * kScanPitch + (e & 15)];
         }
         if (tid == 0) s_warp[33] = carry + s_warp[31];
         __syncthreads();
