@@ -14,9 +14,10 @@
 //   3. bin_scatter : one thread per Gaussian, claims a slot in each tile's segment (the
 //                    counters of step 1 count back down) and writes the 64-bit key
 //                    (depth bits << 32 | id)
-//   4. tile_sort   : one WARP per tile sorts its segment in registers (direction-free bitonic
-//                    network, shuffles below stride 32, in-thread exchanges above; <= 256 keys);
-//                    oversized segments fall to a CTA-wide shared-memory / in-place pass
+//   4. tile_sort   : one 128-thread CTA per tile sorts its segment in registers (direction-free
+//                    bitonic network: shuffles below stride 32, double-buffered shared-memory
+//                    exchanges across warps, in-thread above 128; <= 512 keys); larger segments
+//                    fall to a generic shared-memory / in-place pass
 // Steps 1 and 3 walk the flattened (Gaussian, tile) list 32 pairs per warp round (WarpTileWalk), so
 // their atomics are load balanced and each lane waits for one atomic per round, not one per tile of
 // its own Gaussian in sequence.
@@ -90,8 +91,8 @@ bin_scatter_kernel(const float2* __restrict__ uv, const float* __restrict__ dept
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_kernel(const int32_t* __restrict__ offsets, int R, unsigned long long* __restrict__ keys,
                  int32_t* __restrict__ ids_sorted, int2* __restrict__ tile_range, int T, long long capacity) {
-    __shared__ unsigned long long s_keys[kSortSmemKeys];
-    sort_tiles_cta(offsets, R, keys, T, capacity, s_keys, tile_range,
+    __shared__ unsigned long long s_keys[kSortSmemSmall];
+    sort_tile_cta(offsets, R, keys, capacity, s_keys, tile_range,
                    [ids_sorted](long long pos, unsigned long long key) { ids_sorted[pos] = (int32_t)(unsigned int)key; });
 }
 
@@ -142,7 +143,7 @@ int gfb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
             (long long)capacity);
         GFB_CHECK_LAUNCH();
     }
-    tile_sort_kernel<<<gfb_div_up(T, kTilesPerSortCta), kSortThreads, 0, st>>>(
+    tile_sort_kernel<<<T, kSortThreads, 0, st>>>(
         offsets, R, keys, gaussian_ids_sorted, reinterpret_cast<int2*>(tile_range), T, (long long)capacity);
     GFB_CHECK_LAUNCH();
     GFB_TRY(cudaEventSynchronize(ev));  // waits for count + scan only

@@ -164,8 +164,8 @@ __device__ __forceinline__ void write_record(const PackArgs& a, long long k, int
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_pack_kernel(const int32_t* __restrict__ offsets, int R, unsigned long long* __restrict__ keys,
                       int2* __restrict__ tile_range, int T, long long capacity, PackArgs pa) {
-    __shared__ unsigned long long s_keys[kSortSmemKeys];
-    sort_tiles_cta(offsets, R, keys, T, capacity, s_keys, tile_range,
+    __shared__ unsigned long long s_keys[kSortSmemSmall];
+    sort_tile_cta(offsets, R, keys, capacity, s_keys, tile_range,
                    [pa](long long pos, unsigned long long key) { write_record(pa, pos, (int)(unsigned int)key); });
 }
 
@@ -277,7 +277,7 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     }
     PackArgs pa{reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, sA, sA + capacity,
                 reinterpret_cast<float4*>(feat_stream), gaussian_ids_sorted};
-    tile_sort_pack_kernel<<<gfb_div_up(T, kTilesPerSortCta), kSortThreads, 0, st>>>(
+    tile_sort_pack_kernel<<<T, kSortThreads, 0, st>>>(
         tile_offsets, R, reinterpret_cast<unsigned long long*>(keys_ws), reinterpret_cast<int2*>(tile_range), T,
         (long long)capacity, pa);
     GFB_CHECK_LAUNCH();

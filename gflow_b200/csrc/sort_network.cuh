@@ -4,7 +4,6 @@
 #include "common.cuh"
 
 constexpr int kSortThreads = 128;
-constexpr int kSortSmemKeys = 4096;  // 32 KB of 64-bit keys per CTA
 
 // Direction-free bitonic network: every compare-exchange puts the smaller key at the lower
 // index ("flip" first stage of each merge, then plain half-cleaners).  Because all exchanges are
@@ -129,10 +128,103 @@ __device__ __forceinline__ void warp_sort_regs(unsigned long long (&k)[R], int l
     }
 }
 
-constexpr int kWarpSortMax = 256;   // largest segment sorted by one warp (R = 8)
-constexpr int kTilesPerSortCta = kSortThreads / 32;
+// ------------------------------------------------------------------ CTA-wide register sort
+// 128 threads, R keys per thread, element e = r*128 + tid (up to 512 keys).  Strides below 32 are
+// warp shuffles, strides 32..64 (and the flips that cross warps) go through a double-buffered
+// shared-memory exchange (one barrier per layer), strides of 128 and above are in-thread.  Four
+// warps share one tile's network, so the dependent chain per warp is ~4x shorter than a one-warp
+// sort and four times as many warps are in flight.
+template <int R>
+struct CtaSort {
+    unsigned long long (&k)[R];
+    unsigned long long* sx;  // 2 * 128 * R keys
+    int tid, buf;
+    __device__ __forceinline__ CtaSort(unsigned long long (&k_)[R], unsigned long long* sx_, int tid_)
+        : k(k_), sx(sx_), tid(tid_), buf(0) {}
+    __device__ __forceinline__ void shfl_stage(int mask, int lowbit) {
+        const bool lower = (tid & lowbit) == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned long long p = __shfl_xor_sync(0xffffffffu, k[r], mask);
+            k[r] = lower ? u64_min(k[r], p) : u64_max(k[r], p);
+        }
+    }
+    __device__ __forceinline__ unsigned long long* publish() {
+        unsigned long long* b = sx + buf * (kSortThreads * R);
+        buf ^= 1;
+#pragma unroll
+        for (int r = 0; r < R; ++r) b[r * kSortThreads + tid] = k[r];
+        __syncthreads();
+        return b;
+    }
+    __device__ __forceinline__ void smem_stage(int mask, int lowbit) {
+        const unsigned long long* b = publish();
+        const bool lower = (tid & lowbit) == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned long long p = b[r * kSortThreads + (tid ^ mask)];
+            k[r] = lower ? u64_min(k[r], p) : u64_max(k[r], p);
+        }
+    }
+    __device__ __forceinline__ void low_stages() {  // strides 16..1
+#pragma unroll 1
+        for (int j = 16; j > 0; j >>= 1) shfl_stage(j, j);
+    }
+    __device__ __forceinline__ void run() {
+#pragma unroll 1
+        for (int size = 2; size <= 32; size <<= 1) {
+            shfl_stage(size - 1, size >> 1);
+#pragma unroll 1
+            for (int j = size >> 2; j > 0; j >>= 1) shfl_stage(j, j);
+        }
+        smem_stage(63, 32);  // size 64
+        low_stages();
+        smem_stage(127, 64);  // size 128
+        smem_stage(32, 32);
+        low_stages();
+#pragma unroll
+        for (int m = 2; m <= R; m <<= 1) {  // size 128 m: flip partner is register r ^ (m-1), thread ^ 127
+            const unsigned long long* b = publish();
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const unsigned long long p = b[(r ^ (m - 1)) * kSortThreads + (tid ^ 127)];
+                k[r] = ((r & (m >> 1)) == 0) ? u64_min(k[r], p) : u64_max(k[r], p);
+            }
+#pragma unroll
+            for (int jr = m >> 2; jr > 0; jr >>= 1) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & jr) == 0) {
+                        const unsigned long long x = k[r], y = k[r | jr];
+                        k[r] = u64_min(x, y);
+                        k[r | jr] = u64_max(x, y);
+                    }
+                }
+            }
+            smem_stage(64, 64);
+            smem_stage(32, 32);
+            low_stages();
+        }
+    }
+};
 
-// Sort one tile segment keys[start, start+n) with one warp (n <= 256) and hand every sorted key to
+template <int R, class Emit>
+__device__ __forceinline__ void cta_sort_segment(const unsigned long long* __restrict__ keys, long long start, int n,
+                                                 unsigned long long* sx, Emit emit) {
+    const int tid = threadIdx.x;
+    unsigned long long k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r] = (r * kSortThreads + tid < n) ? keys[start + r * kSortThreads + tid] : ~0ull;
+    CtaSort<R>(k, sx, tid).run();
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (r * kSortThreads + tid < n) emit(start + r * kSortThreads + tid, k[r]);
+}
+
+constexpr int kCtaSortMax = 4 * kSortThreads;  // 512 keys: R = 4
+constexpr int kSortSmemSmall = 1024;           // 8 KB: exchange buffers (2 x 512) or the generic smem path
+
+// Sort one tile segment keys[start, start+n) with one warp (n <= 64) and hand every sorted key to
 // emit(position, key).  All 32 lanes must call.
 template <int R, class Emit>
 __device__ __forceinline__ void warp_sort_segment(const unsigned long long* __restrict__ keys, long long start, int n,
@@ -146,49 +238,40 @@ __device__ __forceinline__ void warp_sort_segment(const unsigned long long* __re
         if (r * 32 + lane < n) emit(start + r * 32 + lane, k[r]);
 }
 
-// One CTA of 128 threads handles kTilesPerSortCta consecutive tiles: a warp each while the segment
-// fits the register sort, then the whole CTA on every oversized segment (shared memory up to 4096
-// keys, in place on the L2-resident global segment beyond).  range(t, start, end) is called once per
-// tile by one thread.
-// `offsets` holds the exclusive scan of the (tile, replica) counters: tile t owns
-// [offsets[t*R], offsets[(t+1)*R]).
+// One CTA of 128 threads per tile: one warp for <= 64 keys, the CTA-wide register network up to 512
+// keys, a generic shared-memory bitonic pass up to 1024 keys and an in-place pass on the L2-resident
+// global segment beyond.  `offsets` holds the exclusive scan of the (tile, replica) counters: tile t
+// owns [offsets[t*R], offsets[(t+1)*R]).
 template <class Emit>
-__device__ __forceinline__ void sort_tiles_cta(const int32_t* __restrict__ offsets, int R,
-                                               unsigned long long* __restrict__ keys, int T, long long capacity,
-                                               unsigned long long* s_keys, int2* __restrict__ tile_range, Emit emit) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {
-        const int t = blockIdx.x * kTilesPerSortCta + warp;
-        if (t < T) {
-            const int start = offsets[t * R];
-            long long end = offsets[(t + 1) * R];
-            if (end > capacity) end = max((long long)start, capacity);  // speculative capacity too small
-            const int n = (int)(end - start);
-            if (lane == 0) tile_range[t] = (n > 0) ? make_int2(start, (int)end) : make_int2(0, 0);
-            if (n > 0 && n <= 64) warp_sort_segment<2>(keys, start, n, lane, emit);
-            else if (n > 64 && n <= 128) warp_sort_segment<4>(keys, start, n, lane, emit);
-            else if (n > 128 && n <= kWarpSortMax) warp_sort_segment<8>(keys, start, n, lane, emit);
-        }
-    }
-    for (int w = 0; w < kTilesPerSortCta; ++w) {
-        const int t = blockIdx.x * kTilesPerSortCta + w;
-        if (t >= T) break;
-        const int start = offsets[t * R];
-        long long end = offsets[(t + 1) * R];
-        if (end > capacity) end = max((long long)start, capacity);
-        const int n = (int)(end - start);
-        if (n <= kWarpSortMax) continue;  // uniform across the CTA
-        __syncthreads();
-        int n_pad = 512;
+__device__ __forceinline__ void sort_tile_cta(const int32_t* __restrict__ offsets, int R,
+                                              unsigned long long* __restrict__ keys, long long capacity,
+                                              unsigned long long* s_keys /* kSortSmemSmall */,
+                                              int2* __restrict__ tile_range, Emit emit) {
+    const int t = blockIdx.x;
+    const int start = offsets[t * R];
+    long long end = offsets[(t + 1) * R];
+    if (end > capacity) end = max((long long)start, capacity);  // speculative capacity too small: host retries
+    const int n = (int)(end - start);
+    if (threadIdx.x == 0) tile_range[t] = (n > 0) ? make_int2(start, (int)end) : make_int2(0, 0);
+    if (n <= 0) return;
+    if (n <= 64) {
+        if (threadIdx.x < 32) warp_sort_segment<2>(keys, start, n, threadIdx.x, emit);
+    } else if (n <= kSortThreads) {
+        cta_sort_segment<1>(keys, start, n, s_keys, emit);
+    } else if (n <= 2 * kSortThreads) {
+        cta_sort_segment<2>(keys, start, n, s_keys, emit);
+    } else if (n <= kCtaSortMax) {
+        cta_sort_segment<4>(keys, start, n, s_keys, emit);
+    } else {
+        int n_pad = 1024;
         while (n_pad < n) n_pad <<= 1;
-        unsigned long long* buf = (n <= kSortSmemKeys) ? s_keys : (keys + start);
-        if (n <= kSortSmemKeys) {
+        unsigned long long* buf = (n <= kSortSmemSmall) ? s_keys : (keys + start);
+        if (n <= kSortSmemSmall) {
             for (int i = threadIdx.x; i < n; i += kSortThreads) s_keys[i] = keys[start + i];
             __syncthreads();
         }
         bitonic_sort_block(buf, n, n_pad);
         for (int i = threadIdx.x; i < n; i += kSortThreads) emit((long long)start + i, buf[i]);
-        __syncthreads();
     }
 }
 
