@@ -32,6 +32,7 @@ SIGNATURES = {
     "gfb_sort_tile_workspace_bytes": (c_size_t, [I, I]),
     "gfb_sort_gaussian": (I, [P, P, P, P, I, I, I, P, L, P, P, P, P, P]),
     "gfb_render_control_bytes": (c_size_t, [I, I]),
+    "gfb_wait_k": (I, [P]),
     "gfb_render_forward": (I, [P, P, P, P, P, I, P, P, I, I, I, F, F, F, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P,
                                P, P]),
     "gfb_render_grad_bytes": (c_size_t, [I]),

@@ -56,10 +56,15 @@ bin_count_kernel(const float2* __restrict__ uv, const int32_t* __restrict__ radi
 
 // Single CTA: exclusive scan of counts[0..n) into offsets[0..n].
 __global__ void __launch_bounds__(kScanThreads)
-tile_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets) {
+tile_scan_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets,
+                 int32_t* __restrict__ k_mapped) {
     __shared__ int s_buf[kScanSmemInts];
     __shared__ int s_warp[34];
-    cta_exclusive_scan(counts, n, offsets, s_buf, s_warp);
+    const int total = cta_exclusive_scan(counts, n, offsets, s_buf, s_warp);
+    if (threadIdx.x == 0 && k_mapped) {
+        *k_mapped = total;  // mapped pinned host word
+        __threadfence_system();
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -122,9 +127,9 @@ int gfb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
     int32_t* counts = (int32_t*)tile_ws;
     int32_t* offsets = counts + (size_t)T * R;
     unsigned long long* keys = (unsigned long long*)keys_ws;
-    int32_t* pinned = nullptr;
+    int32_t *pinned = nullptr, *mapped = nullptr;
     cudaEvent_t ev = nullptr;
-    int rc = gfb_internal_host_sync(&pinned, &ev);
+    int rc = gfb_internal_host_sync(&pinned, &mapped, &ev);
     if (rc) return rc;
     GFB_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)T * R, st));
     if (N > 0) {
@@ -132,9 +137,8 @@ int gfb_sort_gaussian(const float* uv, const float* depth, const int32_t* radius
                                                                        tiles_touched, N, gx, gy, R, counts);
         GFB_CHECK_LAUNCH();
     }
-    tile_scan_kernel<<<1, kScanThreads, 0, st>>>(counts, T * R, offsets);
+    tile_scan_kernel<<<1, kScanThreads, 0, st>>>(counts, T * R, offsets, mapped);
     GFB_CHECK_LAUNCH();
-    GFB_TRY(cudaMemcpyAsync(pinned, offsets + (size_t)T * R, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GFB_TRY(cudaEventRecord(ev, st));
     // speculative: scatter + per-tile sort are enqueued with the caller's capacity before K is known
     if (N > 0 && capacity > 0) {

@@ -13,8 +13,9 @@
 
 // host-side counter of kernels launched by this library (gfb_kernel_launch_count)
 void gfb_internal_count_launch();
-// per-device pinned int32[4] + event used to hand K to the host without draining the stream
-int gfb_internal_host_sync(int32_t** pinned, cudaEvent_t* ev);
+// per-device mapped pinned int32[4] (host + device view) and event used to hand K to the host
+// without draining the stream or putting a copy into it
+int gfb_internal_host_sync(int32_t** pinned, int32_t** mapped, cudaEvent_t* ev);
 
 // follows every kernel launch: error check + launch accounting
 #define GFB_CHECK_LAUNCH()                      \

@@ -17,8 +17,8 @@
 //                             gradients block-reduced
 //
 // K is not known on the host when the sort / pack / blend kernels are enqueued: the caller passes a
-// capacity (its previous K plus slack), the kernels clamp to it, and K is copied to pinned host
-// memory right after `preprocess`.  The host waits on that copy only -- the GPU keeps working on
+// capacity (its previous K plus slack), the kernels clamp to it, and `preprocess` stores K straight
+// into mapped pinned host memory.  The host waits on that copy only -- the GPU keeps working on
 // the speculatively enqueued kernels -- and a call whose K exceeded the capacity returns
 // GFB_E_CAPACITY so the caller can retry with a larger buffer.
 #include "sort_network.cuh"
@@ -42,7 +42,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                   const float* __restrict__ intr, const float* __restrict__ extr, int N, int W, int H, float nearest,
                   float extent, float2* __restrict__ uv, float* __restrict__ depth, float* __restrict__ conic,
                   int32_t* __restrict__ radius, ushort4* __restrict__ rect, int32_t* __restrict__ counts,
-                  int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R) {
+                  int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int32_t* __restrict__ k_mapped, int T, int R) {
     __shared__ float s_cam[16];
     __shared__ int s_scan[34];
     __shared__ int s_buf[kScanSmemInts];
@@ -102,7 +102,11 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
     if (!s_last) return;
     __threadfence();
     const int total = cta_exclusive_scan(counts, T * R, offsets, s_buf, s_scan);
-    if (threadIdx.x == 0) ctrl[CTRL_K] = total;
+    if (threadIdx.x == 0) {
+        ctrl[CTRL_K] = total;
+        *k_mapped = total;  // mapped pinned host word: no D2H copy in the stream
+        __threadfence_system();
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -243,7 +247,7 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
                        void* keys_ws, int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, float* out,
                        float* final_T, int32_t* n_contrib, int64_t* K_host, void* stream) {
     if (N < 0 || W <= 0 || H <= 0 || C < 1 || C > 4 || capacity < 0) return GFB_E_BADARG;
-    if (!intr || !extr || !control_ws || !tile_range || !out || !final_T || !n_contrib || !K_host)
+    if (!intr || !extr || !control_ws || !tile_range || !out || !final_T || !n_contrib)
         return GFB_E_BADARG;
     if (N > 0 && (!xyz || !scale || !rotate || !opacity || !feature || !uv || !depth || !conic || !radius || !rect_ws))
         return GFB_E_BADARG;
@@ -254,18 +258,17 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     int32_t* counts = (int32_t*)control_ws;
     int32_t* ctrl = counts + (size_t)T * R;
     int32_t* tile_offsets = ctrl + CTRL_WORDS;
-    int32_t* pinned = nullptr;
+    int32_t *pinned = nullptr, *mapped = nullptr;
     cudaEvent_t ev = nullptr;
-    int rc = gfb_internal_host_sync(&pinned, &ev);
+    int rc = gfb_internal_host_sync(&pinned, &mapped, &ev);
     if (rc) return rc;
     GFB_TRY(cudaMemsetAsync(control_ws, 0, ((size_t)T * R + CTRL_WORDS) * sizeof(int32_t), st));
     // N == 0 still runs one CTA so the scan zeroes the offsets
     preprocess_kernel<<<max(1, gfb_div_up(N, kThreads)), kThreads, 0, st>>>(
         xyz, scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent,
         reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect_ws), counts,
-        tile_offsets, ctrl, T, R);
+        tile_offsets, ctrl, mapped, T, R);
     GFB_CHECK_LAUNCH();
-    GFB_TRY(cudaMemcpyAsync(pinned, ctrl + CTRL_K, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     GFB_TRY(cudaEventRecord(ev, st));
     // speculative part: enqueued before K is known on the host
     float4* sA = reinterpret_cast<float4*>(geom_stream);
@@ -284,6 +287,7 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     rc = gfb_alpha_blending_fwd(geom_stream, feat_stream, capacity, tile_range, C, 0, C, bg, W, H, out, final_T,
                                 n_contrib, stream);
     if (rc) return rc;
+    if (!K_host) return 0;  // the caller overlaps host work, then calls gfb_wait_k()
     GFB_TRY(cudaEventSynchronize(ev));  // waits for `preprocess` only
     *K_host = (int64_t)pinned[0];
     return (*K_host > capacity) ? GFB_E_CAPACITY : 0;

@@ -498,6 +498,7 @@ class _Rasterize(torch.autograd.Function):
             p_rng, p_ctl = tp, tp + 8 * T
             out = torch.empty(C, H, W, device=dev, dtype=torch.float32)
             aux = torch.empty(2, H, W, device=dev, dtype=torch.float32)  # final_T | n_contrib (int32 bits)
+            bufs = None
             while True:
                 # K-sized buffer (bytes): geom 32c | feat 16c | keys 8c | ids 4c
                 kbuf = torch.empty(15 * max(cap, 1), device=dev, dtype=torch.float32)
@@ -507,28 +508,37 @@ class _Rasterize(torch.autograd.Function):
                     feature_c.data_ptr(), C, intr_c.data_ptr(), extr_c.data_ptr(), N, W, H, bg, nearest, extent,
                     p_uv, p_depth, p_conic, p_radius, p_rect, p_ctl, p_rng, cap, kp + 48 * cap, kp + 56 * cap,
                     kp, kp + 32 * cap, out.data_ptr(), aux.data_ptr(), aux.data_ptr() + 4 * H * W,
-                    _ctypes.byref(k_host), _stream())
+                    None, _stream())
+                capi.check(rc, "rasterization forward")
+                # everything is enqueued; do the host-side bookkeeping while `preprocess` runs, then
+                # pick up K (stored by the kernel into mapped pinned memory)
+                if bufs is None:
+                    # backward buffers: grad pack 12N+16 | d_rotate 4N | d_xyz 3N | d_scale 3N | d_opacity N | d_feature CN
+                    bufs = (torch.empty(12 * N + 16, device=dev, dtype=torch.float32),
+                            torch.empty((11 + C) * max(N, 1), device=dev, dtype=torch.float32))
+                    ctx.save_for_backward(xyz_c, scale_c, rotate_c, intr_c, extr_c)
+                capi.check(_lib.gfb_wait_k(_ctypes.byref(k_host)), "rasterization forward (K)")
                 K = int(k_host.value)
-                if rc == GFB_E_CAPACITY:
+                if K > cap:
                     cap = K + K // 8 + 1024
                     continue
-                capi.check(rc, "rasterization forward")
                 break
         _K_HINT[key] = K
-        ctx.save_for_backward(xyz_c, scale_c, rotate_c, intr_c, extr_c, kbuf, tbuf, aux)
+        ctx.bufs = (kbuf, tbuf, aux) + bufs
         ctx.meta = (N, C, T, cap, W, H, bg, nearest, extent)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        xyz, scale, rotate, intr, extr, kbuf, tbuf, aux = ctx.saved_tensors
+        xyz, scale, rotate, intr, extr = ctx.saved_tensors
+        kbuf, tbuf, aux, grad_ws, dbuf = ctx.bufs
         N, C, T, cap, W, H, bg, nearest, extent = ctx.meta
         dev = xyz.device
         with _on_device(dev):
+            if getattr(ctx, "bwd_done", False):  # retain_graph: earlier gradients alias the first buffers
+                grad_ws, dbuf = torch.empty_like(grad_ws), torch.empty_like(dbuf)
+            ctx.bwd_done = True
             g_out = _prep(g_out, "grad feature_map", shape=(C, H, W))
-            grad_ws = torch.empty(12 * N + 16, device=dev, dtype=torch.float32)
-            # d_rotate 4N | d_xyz 3N | d_scale 3N | d_opacity N | d_feature CN
-            dbuf = torch.empty((11 + C) * max(N, 1), device=dev, dtype=torch.float32)
             dp = dbuf.data_ptr()
             kp, tp = kbuf.data_ptr(), tbuf.data_ptr()
             capi.check(_lib.gfb_render_backward(

@@ -140,8 +140,11 @@ int gfb_blend_unpack_grads(const float *grad_pack, int N, int C, int c0, int Cg,
  *   capacity  : number of intersections the K-sized buffers can hold:
  *               keys_ws (8 B), gaussian_ids_sorted (4 B), geom_stream (32 B), feat_stream (16 B) each
  *   out (C,H,W), final_T (H,W), n_contrib (H,W)
- * K is delivered to *K_host (HOST pointer); GFB_E_CAPACITY as in gfb_sort_gaussian. */
+ * K is delivered to *K_host (HOST pointer); GFB_E_CAPACITY as in gfb_sort_gaussian.  With K_host == NULL
+ * the call returns without waiting; the caller overlaps host work and then calls gfb_wait_k(&K), which
+ * blocks until the most recent K of the current device has landed (compare it with capacity). */
 size_t gfb_render_control_bytes(int W, int H);
+int gfb_wait_k(int64_t *K_host);
 int gfb_render_forward(const float *xyz, const float *scale, const float *rotate, const float *opacity,
                        const float *feature, int C, const float *intr, const float *extr, int N, int W, int H,
                        float bg, float nearest, float extent, float *uv, float *depth, float *conic, int32_t *radius,

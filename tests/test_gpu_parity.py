@@ -275,6 +275,18 @@ def test_fused_rasterization_equals_operator_chain(G, N, W, H, Cf):
         assert_close(a, b, 1e-4, "fused grad " + name)
 
 
+def test_fused_backward_twice_with_retain_graph(G):
+    sc = make_scene(3000, 160, 120, seed=4)
+    ps = [t.to(DEV).requires_grad_(True) for t in (sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb)]
+    img = G.rasterization(*ps, *cu(sc.intr, sc.extr), sc.W, sc.H, 0.0)
+    g = cu(make_grad_image(3, sc.W, sc.H))
+    img.backward(g, retain_graph=True)
+    first = [p.grad.clone() for p in ps]
+    img.backward(g)
+    for p, f in zip(ps, first):
+        assert_close(p.grad, 2.0 * f, 1e-5, "accumulated grad")
+
+
 def test_speculative_capacity_retry(G):
     """A stale / tiny K hint must trigger the GFB_E_CAPACITY retry, not truncate the result."""
     from gflow_b200 import ops

@@ -59,3 +59,18 @@ for name, (t, n) in tot.items():
     print(f"{t / steps:9.2f} us/step  x{n / steps:4.1f}  {name}")
     s += t / steps
 print(f"{s:9.2f} us/step  total GPU busy")
+# timeline of the last step: start offset, duration and the idle gap before each GPU activity
+evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA],
+             key=lambda e: e.time_range.start)
+starts = [i for i, e in enumerate(evs) if "preprocess_kernel" in e.name or "project_point_fwd" in e.name]
+if len(starts) >= 2:
+    a, b = starts[-2], starts[-1]
+    t0 = evs[a].time_range.start
+    prev_end = t0
+    print("# timeline of one step (us from the first kernel): start  dur  gap_before  name")
+    for e in evs[a:b]:
+        st, en = e.time_range.start, e.time_range.end
+        nm = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:50]
+        print(f"  {st - t0:8.1f} {en - st:7.1f} {st - prev_end:7.1f}  {nm}")
+        prev_end = max(prev_end, en)
+
