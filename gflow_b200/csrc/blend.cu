@@ -79,6 +79,21 @@ __device__ __forceinline__ float splat_power(float a, float b, float c, float dx
     return __fmaf_rn(-0.5f, q, -r);
 }
 
+// exp(power) as one FMUL + MUFU.EX2 (ex2.approx.ftz): power is in [-5.6, 0] wherever alpha can
+// reach 1/255, far from the denormal range __expf() guards against with three extra instructions.
+// Forward and backward share it, so they agree on every alpha >= 1/255 decision.
+__device__ __forceinline__ float splat_exp(float power) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(power * 1.4426950408889634f));
+    return r;
+}
+// 1 / x for x = 1 - alpha in [0.01, 1]: one MUFU.RCP, no range fix-up
+__device__ __forceinline__ float splat_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ------------------------------------------------------------------ pack kernels
 __global__ void __launch_bounds__(256)
 pack_geometry_kernel(const float2* __restrict__ uv, const float* __restrict__ conic,
@@ -195,7 +210,7 @@ blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                             const float dx = a4.x - pxf, dy = a4.y - pyf;
                             const float power = splat_power(b4.x, b4.y, b4.z, dx, dy);
                             if (power <= 0.0f) {
-                                const float alpha = fminf(GFB_ALPHA_MAX, b4.w * __expf(power));
+                                const float alpha = fminf(GFB_ALPHA_MAX, b4.w * splat_exp(power));
                                 if (alpha >= GFB_ALPHA_MIN) {
                                     const float test_T = T * (1.0f - alpha);
                                     if (test_T < GFB_T_EPS) {
@@ -320,10 +335,8 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
         issue_batch(&s_stage[0], &s_bar[0], gA, gB, gF, (long long)range.x + (long long)(nb - 1) * kBatch,
                     max_last - (nb - 1) * kBatch);
 
-    float T = Tf, last_alpha = 0.0f;
-    float accum[CG], lastc[CG];
-#pragma unroll
-    for (int c = 0; c < CG; ++c) accum[c] = lastc[c] = 0.0f;
+    float T = Tf;
+    float S = Tf * bgdot;
 
     for (int it = 0; it < nb; ++it) {
         const int b = nb - 1 - it;
@@ -361,27 +374,25 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                         const float dx = a4.x - pxf, dy = a4.y - pyf;
                         const float power = splat_power(b4.x, b4.y, b4.z, dx, dy);
                         if (power <= 0.0f) {
-                            const float G = __expf(power);
+                            const float G = splat_exp(power);
                             const float alpha = fminf(GFB_ALPHA_MAX, b4.w * G);
                             if (alpha >= GFB_ALPHA_MIN) {
                                 act = true;
                                 const float4 f4 = st.F[jj];
-                                const float inv1ma = __fdividef(1.0f, 1.0f - alpha);
-                                T = T * inv1ma;
+                                const float inv1ma = splat_rcp(1.0f - alpha);
+                                T = T * inv1ma;  // transmittance in front of this Gaussian
                                 const float w = alpha * T;
-                                float dalpha = 0.0f;
+                                // S = sum_{k behind j} w_k (f_k . g) + T_final (bg . g): one scalar carries what
+                                // the 3DGS formulation keeps as accum_rec[C] / last_color[C] / last_alpha
+                                float fg = 0.0f;
                                 float df[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                                 for (int c = 0; c < CG; ++c) {
-                                    const float f = f4_get(f4, c);
-                                    accum[c] = fmaf(last_alpha, lastc[c], (1.0f - last_alpha) * accum[c]);
-                                    lastc[c] = f;
-                                    dalpha = fmaf(f - accum[c], go[c], dalpha);
+                                    fg = fmaf(f4_get(f4, c), go[c], fg);
                                     df[c] = w * go[c];
                                 }
-                                dalpha *= T;
-                                last_alpha = alpha;
-                                dalpha = fmaf(-Tf * inv1ma, bgdot, dalpha);
+                                const float dalpha = fmaf(T, fg, -S * inv1ma);
+                                S = fmaf(w, fg, S);
                                 const float dG = b4.w * dalpha;
                                 const float gdx = G * dx, gdy = G * dy;
                                 v[0] = dG * (-gdx * b4.x - gdy * b4.y);
@@ -403,14 +414,12 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                     if (CG > 3) v9 = gfb_warp_sum(v9);
                     const int id = ids[(long long)range.x + pos];
                     float* gp = grad_pack + (size_t)id * 12;
-                    if ((lane & 3) == 0) {
-                        const int slot = lane >> 2;
-                        if (slot < 6 + (CG > 1 ? 2 : 1)) atomicAdd(gp + slot, r);
-                    } else if (lane == 1) {
-                        if (CG > 2) atomicAdd(gp + 8, v8);
-                    } else if (lane == 2) {
-                        if (CG > 3) atomicAdd(gp + 9, v9);
-                    }
+                    // lanes 0,4,..,28 hold slots 0..7; lanes 1 / 2 carry slots 8 / 9: one RED instruction
+                    constexpr int kSlots8 = 6 + (CG > 1 ? 2 : 1);
+                    const bool lead = (lane & 3) == 0;
+                    const int slot = lead ? (lane >> 2) : (7 + lane);
+                    const float val = lead ? r : (lane == 1 ? v8 : v9);
+                    if (lead ? (slot < kSlots8) : ((lane == 1 && CG > 2) || (lane == 2 && CG > 3))) atomicAdd(gp + slot, val);
                 }
             }
         }
