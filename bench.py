@@ -234,12 +234,20 @@ def run_ours(args):
     Gimg = make_grad_image(3, W, H, seed=1 + rank).to(dev)
     params = [state[k].clone().requires_grad_(True) for k in ("xyz", "scale", "rotate", "opacity", "rgb")]
     extr_p = extr.clone().requires_grad_(True)
+    use_sh = args.workload == "cfg5"  # BASELINE config 5: colour from degree-3 spherical harmonics
+    if use_sh:
+        gsh = torch.Generator().manual_seed(7)
+        shs = (torch.randn(N, 3, 16, generator=gsh) * 0.2).to(dev).requires_grad_(True)
+        params[4] = shs
+        cam_center = -(extr[:, :3].T @ extr[:, 3])
 
     def step(raster=G.rasterization):
         for p in params:
             p.grad = None
         extr_p.grad = None
         xyz, scale, rot, op, rgb = params
+        if use_sh:
+            rgb = (G.compute_sh(rgb, xyz - cam_center) + 0.5).clamp_min(0.0)
         img = raster(xyz, scale, rot, op, rgb, intr, extr_p, W, H, sc.bg)
         # loss = sum(out * G) with a fixed random G: dL/dout = G is fed to autograd directly
         img.backward(Gimg)
@@ -296,24 +304,38 @@ def run_ours(args):
     chain_ms = sum(a.elapsed_time(b) for a, b in ev3) / n_chain
 
     # ---- e2e: same step through the public API with HOST buffers (pinned), H2D of the step's
-    #      inputs and D2H of loss + gradients inside the timed region
-    host_in = [p.detach().cpu().pin_memory() for p in params] + [intr.cpu().pin_memory(), extr.cpu().pin_memory()]
-    host_out = [torch.empty_like(h).pin_memory() for h in host_in[:5]] + [torch.empty(3, 4).pin_memory(),
-                                                                         torch.empty(()).pin_memory()]
-    h2d = sum(h.numel() * 4 for h in host_in)
-    d2h = sum(h.numel() * 4 for h in host_out)
+    #      inputs and D2H of loss + gradients inside the timed region.  The host keeps the Gaussian
+    #      state in one pinned staging block (xyz | scale | rotate | opacity | rgb | intr | extr), so
+    #      the step's inputs travel as one H2D copy; results come back into one pinned block.
+    csz = params[4][0].numel()  # 3 (rgb) or 48 (degree-3 SH)
+    sizes = [3 * N, 3 * N, 4 * N, N, csz * N, 4, 12]
+    offs = [0]
+    for sz in sizes:
+        offs.append(offs[-1] + sz)
+    host_in = torch.empty(offs[-1], dtype=torch.float32).pin_memory()
+    for t, o in zip([p.detach() for p in params] + [intr, extr], offs):
+        host_in[o:o + t.numel()].copy_(t.reshape(-1).cpu())
+    dev_in = torch.empty(offs[-1], dtype=torch.float32, device=dev)
+    out_sizes = [3 * N, 3 * N, 4 * N, N, csz * N, 12, 1]
+    ooffs = [0]
+    for sz in out_sizes:
+        ooffs.append(ooffs[-1] + sz)
+    host_out = torch.empty(ooffs[-1], dtype=torch.float32).pin_memory()
+    h2d = host_in.numel() * 4
+    d2h = host_out.numel() * 4
+    shapes = [(N, 3), (N, 3), (N, 4), (N, 1), tuple(params[4].shape), (4,), (3, 4)]
 
     def step_e2e():
-        dv = [h.to(dev, non_blocking=True) for h in host_in]
-        ps = [d.requires_grad_(True) for d in dv[:5]]
-        ex = dv[6].requires_grad_(True)
-        img = G.rasterization(ps[0], ps[1], ps[2], ps[3], ps[4], dv[5], ex, W, H, sc.bg)
+        dev_in.copy_(host_in, non_blocking=True)
+        dv = [dev_in[offs[i]:offs[i + 1]].view(shapes[i]) for i in range(7)]
+        ps = [d.detach().requires_grad_(True) for d in dv[:5]]
+        ex = dv[6].detach().requires_grad_(True)
+        col = (G.compute_sh(ps[4], ps[0] - cam_center) + 0.5).clamp_min(0.0) if use_sh else ps[4]
+        img = G.rasterization(ps[0], ps[1], ps[2], ps[3], col, dv[5], ex, W, H, sc.bg)
         loss = (img * Gimg).sum()
         loss.backward()
-        for o, p in zip(host_out[:5], ps):
-            o.copy_(p.grad, non_blocking=True)
-        host_out[5].copy_(ex.grad, non_blocking=True)
-        host_out[6].copy_(loss.detach(), non_blocking=True)
+        for i, t in enumerate([p.grad for p in ps] + [ex.grad, loss.detach()]):
+            host_out[ooffs[i]:ooffs[i + 1]].copy_(t.reshape(-1), non_blocking=True)
 
     n_e2e = max(5, min(args.steps, 50))
     for _ in range(3):
@@ -388,6 +410,8 @@ def kernel_roofline(G, lib, params, intr, extr, Gimg, bg, N, W, H, T, P, flush_l
     peak, peak_src = load_peaks()
     with torch.no_grad():
         xyz, scale, rot, op, rgb = [p.detach() for p in params]
+        if rgb.dim() == 3:
+            rgb = (G.compute_sh(rgb, xyz) + 0.5).clamp_min(0.0).contiguous()
         uv, depth = G.project_point(xyz, intr, extr, W, H)
         vis = depth != 0
         cov = G.compute_cov3d(scale, rot, vis)
