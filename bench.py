@@ -459,7 +459,7 @@ def kernel_roofline(G, lib, params, intr, extr, Gimg, bg, N, W, H, T, P, flush_l
     ab = algorithmic_bytes(N, K, P, T)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and (N, W, H) == WORKLOADS["cfg2"]:
         try:
             with open(tp) as fh:
                 traffic = json.load(fh).get("blend_bwd_dram_bytes_per_launch")
