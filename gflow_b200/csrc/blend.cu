@@ -155,6 +155,7 @@ blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
     __shared__ __align__(128) Stage s_stage[2];
     __shared__ __align__(8) uint64_t s_bar[2];
 
+    gfb_pdl_wait();  // fused pipeline: tile_sort_pack may still be draining
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int2 range = tile_range[tile];
@@ -287,6 +288,7 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_max_last;
 
+    gfb_pdl_launch_dependents();  // fused pipeline: geometry_bwd may queue behind the last wave
     const int tile = blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int2 range = tile_range[tile];
@@ -490,9 +492,11 @@ int gfb_blend_pack_feature(const float* feature, int C, int c0, int Cg, const in
     return 0;
 }
 
-int gfb_alpha_blending_fwd(const void* geom_stream, const void* feat_stream, int64_t K, const int32_t* tile_range,
+}  // extern "C"
+
+int gfb_internal_blend_fwd(const void* geom_stream, const void* feat_stream, int64_t K, const int32_t* tile_range,
                            int C, int c0, int Cg, float bg, int W, int H, float* out, float* final_T,
-                           int32_t* n_contrib, void* stream) {
+                           int32_t* n_contrib, void* stream, bool pdl) {
     if (W <= 0 || H <= 0 || K < 0 || C <= 0 || c0 < 0 || Cg < 1 || Cg > 4 || c0 + Cg > C) return GFB_E_BADARG;
     if (!tile_range || !out || !final_T || !n_contrib) return GFB_E_BADARG;
     if (K > 0 && (!geom_stream || !feat_stream)) return GFB_E_BADARG;
@@ -502,14 +506,26 @@ int gfb_alpha_blending_fwd(const void* geom_stream, const void* feat_stream, int
     const float4* gF = reinterpret_cast<const float4*>(feat_stream);
     const int2* tr = reinterpret_cast<const int2*>(tile_range);
     cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(gx * gy), block(kBlendThreads);
+    cudaError_t le;
     switch (Cg) {
-        case 1: blend_fwd_kernel<1><<<gx * gy, kBlendThreads, 0, st>>>(gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
-        case 2: blend_fwd_kernel<2><<<gx * gy, kBlendThreads, 0, st>>>(gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
-        case 3: blend_fwd_kernel<3><<<gx * gy, kBlendThreads, 0, st>>>(gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
-        default: blend_fwd_kernel<4><<<gx * gy, kBlendThreads, 0, st>>>(gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
+        case 1: le = gfb_launch_pdl(blend_fwd_kernel<1>, grid, block, st, pdl, gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
+        case 2: le = gfb_launch_pdl(blend_fwd_kernel<2>, grid, block, st, pdl, gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
+        case 3: le = gfb_launch_pdl(blend_fwd_kernel<3>, grid, block, st, pdl, gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
+        default: le = gfb_launch_pdl(blend_fwd_kernel<4>, grid, block, st, pdl, gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
     }
+    if (le != cudaSuccess) return (int)le;
     GFB_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" {
+
+int gfb_alpha_blending_fwd(const void* geom_stream, const void* feat_stream, int64_t K, const int32_t* tile_range,
+                           int C, int c0, int Cg, float bg, int W, int H, float* out, float* final_T,
+                           int32_t* n_contrib, void* stream) {
+    return gfb_internal_blend_fwd(geom_stream, feat_stream, K, tile_range, C, c0, Cg, bg, W, H, out, final_T, n_contrib,
+                                  stream, false);
 }
 
 int gfb_alpha_blending_bwd(const void* geom_stream, const void* feat_stream, int64_t K,

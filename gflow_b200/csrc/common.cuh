@@ -33,6 +33,30 @@ int gfb_internal_host_sync(int32_t** pinned, int32_t** mapped, cudaEvent_t* ev);
 
 static inline int gfb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with gfb_launch_pdl may start while
+// its predecessor in the stream is still draining; it must call gfb_pdl_wait() before touching
+// anything the predecessor wrote.  gfb_pdl_launch_dependents() in the predecessor lets the
+// successor's CTAs take SM slots as soon as every predecessor CTA has started.  Both are no-ops in a
+// kernel launched the ordinary way.
+__device__ __forceinline__ void gfb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gfb_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gfb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl,
+                                         Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // camera-space point with the oracle's operation order: ((e0*x + e1*y) + e2*z) + e3
 // (geometry.cu is compiled with -fmad=false so no multiply-add is fused).
 __device__ __forceinline__ void gfb_cam_point(const float* __restrict__ e, float x, float y, float z, float& xc,

@@ -25,8 +25,8 @@
 #include "splat_math.cuh"
 
 // blend.cu
-extern "C" int gfb_alpha_blending_fwd(const void*, const void*, int64_t, const int32_t*, int, int, int, float, int,
-                                      int, float*, float*, int32_t*, void*);
+int gfb_internal_blend_fwd(const void*, const void*, int64_t, const int32_t*, int, int, int, float, int, int, float*,
+                           float*, int32_t*, void*, bool pdl);
 extern "C" int gfb_alpha_blending_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int,
                                       float, int, int, const float*, const int32_t*, const float*, float*, void*);
 
@@ -43,6 +43,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                   float extent, float2* __restrict__ uv, float* __restrict__ depth, float* __restrict__ conic,
                   int32_t* __restrict__ radius, ushort4* __restrict__ rect, int32_t* __restrict__ counts,
                   int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int32_t* __restrict__ k_mapped, int T, int R) {
+    gfb_pdl_launch_dependents();  // scatter may take SM slots while the counting tail drains
     __shared__ float s_cam[16];
     __shared__ int s_scan[34];
     __shared__ int s_buf[kScanSmemInts];
@@ -113,6 +114,8 @@ __global__ void __launch_bounds__(kThreads)
 scatter_kernel(const ushort4* __restrict__ rect, const float* __restrict__ depth, int N, int gx, int R,
                const int32_t* __restrict__ offsets, int32_t* __restrict__ counts,
                unsigned long long* __restrict__ keys, long long capacity) {
+    gfb_pdl_launch_dependents();
+    gfb_pdl_wait();  // rect / depth / offsets come from preprocess
     const int i = blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     ushort4 rc = make_ushort4(0, 0, 0, 0);
@@ -169,6 +172,8 @@ __global__ void __launch_bounds__(kSortThreads)
 tile_sort_pack_kernel(const int32_t* __restrict__ offsets, int R, unsigned long long* __restrict__ keys,
                       int2* __restrict__ tile_range, int T, long long capacity, PackArgs pa) {
     __shared__ unsigned long long s_keys[kSortSmemSmall];
+    gfb_pdl_launch_dependents();
+    gfb_pdl_wait();  // keys come from scatter
     sort_tile_cta(offsets, R, keys, capacity, s_keys, tile_range,
                    [pa](long long pos, unsigned long long key) { write_record(pa, pos, (int)(unsigned int)key); });
 }
@@ -182,6 +187,7 @@ geometry_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ sca
                     float* __restrict__ d_feature, float* __restrict__ d_cam) {
     __shared__ float s_cam[16];
     load_camera(s_cam, intr, extr);
+    gfb_pdl_wait();  // grad_pack comes from blend_bwd
     const float* e = s_cam;
     const float* in = s_cam + 12;
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
@@ -273,19 +279,19 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     // speculative part: enqueued before K is known on the host
     float4* sA = reinterpret_cast<float4*>(geom_stream);
     if (N > 0 && capacity > 0) {
-        scatter_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(
-            reinterpret_cast<const ushort4*>(rect_ws), depth, N, gx, R, tile_offsets, counts,
-            reinterpret_cast<unsigned long long*>(keys_ws), (long long)capacity);
+        GFB_TRY(gfb_launch_pdl(scatter_kernel, dim3(gfb_div_up(N, kThreads)), dim3(kThreads), st, true,
+                               reinterpret_cast<const ushort4*>(rect_ws), depth, N, gx, R, tile_offsets, counts,
+                               reinterpret_cast<unsigned long long*>(keys_ws), (long long)capacity));
         GFB_CHECK_LAUNCH();
     }
     PackArgs pa{reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, sA, sA + capacity,
                 reinterpret_cast<float4*>(feat_stream), gaussian_ids_sorted};
-    tile_sort_pack_kernel<<<T, kSortThreads, 0, st>>>(
-        tile_offsets, R, reinterpret_cast<unsigned long long*>(keys_ws), reinterpret_cast<int2*>(tile_range), T,
-        (long long)capacity, pa);
+    GFB_TRY(gfb_launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(kSortThreads), st, true, tile_offsets, R,
+                           reinterpret_cast<unsigned long long*>(keys_ws), reinterpret_cast<int2*>(tile_range), T,
+                           (long long)capacity, pa));
     GFB_CHECK_LAUNCH();
-    rc = gfb_alpha_blending_fwd(geom_stream, feat_stream, capacity, tile_range, C, 0, C, bg, W, H, out, final_T,
-                                n_contrib, stream);
+    rc = gfb_internal_blend_fwd(geom_stream, feat_stream, capacity, tile_range, C, 0, C, bg, W, H, out, final_T,
+                                n_contrib, stream, true);
     if (rc) return rc;
     if (!K_host) return 0;  // the caller overlaps host work, then calls gfb_wait_k()
     GFB_TRY(cudaEventSynchronize(ev));  // waits for `preprocess` only
@@ -315,10 +321,10 @@ int gfb_render_backward(const float* xyz, const float* scale, const float* rotat
                                         bg, W, H, final_T, n_contrib, g_out, grad_pack, stream);
         if (rc) return rc;
     }
-    geometry_bwd_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(
-        xyz, scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent, C,
-        reinterpret_cast<const float4*>(grad_pack), d_xyz, d_scale, reinterpret_cast<float4*>(d_rotate), d_opacity,
-        d_feature, d_cam);
+    GFB_TRY(gfb_launch_pdl(geometry_bwd_kernel, dim3(gfb_div_up(N, kThreads)), dim3(kThreads), st, capacity > 0, xyz,
+                           scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent, C,
+                           reinterpret_cast<const float4*>(grad_pack), d_xyz, d_scale,
+                           reinterpret_cast<float4*>(d_rotate), d_opacity, d_feature, d_cam));
     GFB_CHECK_LAUNCH();
     return 0;
 }
