@@ -382,7 +382,7 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: {N} Gaussians, {W}x{H}, render step fwd+bwd (C=3), profile {args.profile}",
                        "K": roof.pop("K"), "sharding": "one frame (camera + target) per rank, no in-loop collective",
                        "l2": "256 MiB written between timed steps" if not args.no_flush else "not flushed (working set < L2)",
-                       "api": "msplat.rasterization (gflow_b200.ops, fused pipeline) -> C ABI"},
+                       "api": f"msplat.rasterization (gflow_b200.ops, fused pipeline, {G.BACKEND} binding) -> C ABI"},
             "operator_chain": {"value": world * 1e3 / chain_ms, "unit": UNIT, "ms_per_step": chain_ms,
                                "what": "same step through project_point/compute_cov3d/ewa_project/sort_gaussian/"
                                        "alpha_blending called one by one (render.py:21-64 pattern)"},

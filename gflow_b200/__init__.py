@@ -8,6 +8,7 @@ import os as _os
 import sys as _sys
 
 from . import capi  # noqa: F401  (fails loudly if libgflow_b200.so cannot be built / loaded)
+from .ops import BACKEND  # noqa: F401  "cpp_extension" when the in-tree C++ binding is built, else "ctypes"
 from .ops import (  # noqa: F401
     alpha_blending,
     compute_cov3d,

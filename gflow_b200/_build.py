@@ -84,7 +84,69 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+# ---------------------------------------------------------------------------------------------
+# Thin C++/pybind11 binding (csrc/torch_ext.cpp): host-only C++ against the torch headers, linked to
+# libgflow_b200.so.  Optional accelerator for the Python operator surface: when it cannot be built
+# the ctypes path in ops.py is used (same kernels either way).
+EXT_NAME = "_gfb_torch"
+EXT_PATH = os.path.join(LIB_DIR, EXT_NAME + ".so")
+_EXT_STAMP = os.path.join(LIB_DIR, "torch_ext.stamp")
+
+
+def _ext_fingerprint() -> str:
+    import torch
+
+    h = hashlib.sha256()
+    for f in (os.path.join(CSRC, "torch_ext.cpp"), os.path.join(INCLUDE, "gflow_b200.h")):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(torch.__version__.encode())
+    return h.hexdigest()
+
+
+def ext_needs_build() -> bool:
+    if not os.path.exists(EXT_PATH) or not os.path.exists(_EXT_STAMP):
+        return True
+    with open(_EXT_STAMP) as fh:
+        return fh.read().strip() != _ext_fingerprint()
+
+
+def build_torch_ext(force: bool = False) -> str:
+    """g++ csrc/torch_ext.cpp -> _lib/_gfb_torch.so (needs libgflow_b200.so to exist)."""
+    if not force and not ext_needs_build():
+        return EXT_PATH
+    import sysconfig
+    import warnings
+
+    import torch
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from torch.utils import cpp_extension as ce
+    build()
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    inc = [os.path.join(os.path.dirname(torch.__file__), "include"),
+           os.path.join(os.path.dirname(torch.__file__), "include", "torch", "csrc", "api", "include"),
+           "/usr/local/cuda/include", sysconfig.get_paths()["include"], INCLUDE]
+    abi = getattr(torch._C, "_GLIBCXX_USE_CXX11_ABI", True)
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    extra = list(getattr(ce, "_get_pybind11_abi_build_flags", lambda: [])())
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={int(bool(abi))}",
+           f"-DTORCH_EXTENSION_NAME={EXT_NAME}", "-DTORCH_API_INCLUDE_EXTENSION_H", *extra,
+           *[f"-I{i}" for i in inc], os.path.join(CSRC, "torch_ext.cpp"), "-o", EXT_PATH,
+           f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
+           f"-L{LIB_DIR}", "-lgflow_b200", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    with open(os.path.join(LIB_DIR, "torch_ext.log"), "w") as fh:
+        fh.write("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("torch extension build failed:\n" + (res.stdout + res.stderr)[-4000:])
+    with open(_EXT_STAMP, "w") as fh:
+        fh.write(_ext_fingerprint())
+    return EXT_PATH
+
+
 if __name__ == "__main__":
     import sys
 
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_torch_ext(force="--force" in sys.argv))

@@ -574,3 +574,85 @@ def rasterization(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):
     if isinstance(feature, torch.Tensor) and feature.dim() == 2 and 1 <= feature.shape[1] <= 4:
         return _Rasterize.apply(xyz, scale, rotate, opacity, feature, intr, extr, int(W), int(H), float(bg), 0.2, 1.3)
     return rasterization_unfused(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg)
+
+
+# --------------------------------------------------------------------------- C++ binding (optional)
+# csrc/torch_ext.cpp implements the same operators as torch::autograd::Function in C++ on top of the
+# same C ABI.  When the in-tree extension has been built (__graft_entry__.build()), the public names
+# are rebound to it: identical kernels and results, ~5x less host time per operator.  The ctypes
+# implementations above stay importable as `<name>_py` (tests run both).
+def debug_set_k_hints(value: int) -> None:
+    """Test hook: make every remembered K look like `value` (forces the GFB_E_CAPACITY retry)."""
+    for k in list(_K_HINT):
+        _K_HINT[k] = int(value)
+    if _C is not None:
+        _C.set_all_k_hints(int(value))
+
+
+def _load_extension():
+    import importlib.util
+    import os
+
+    from . import _build
+
+    if os.environ.get("GFLOW_B200_NO_EXT") == "1" or not os.path.exists(_build.EXT_PATH) or _build.ext_needs_build():
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location(_build.EXT_NAME, _build.EXT_PATH)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception as e:  # pragma: no cover - a stale / ABI-mismatched build falls back to ctypes, loudly
+        import warnings
+
+        warnings.warn(f"gflow_b200: C++ binding present but not loadable ({e}); using the ctypes path")
+        return None
+
+
+project_point_py, compute_cov3d_py, ewa_project_py = project_point, compute_cov3d, ewa_project
+sort_gaussian_py, alpha_blending_py, compute_sh_py = sort_gaussian, alpha_blending, compute_sh
+rasterization_py, rasterization_unfused_py = rasterization, rasterization_unfused
+_C = _load_extension()
+BACKEND = "ctypes"
+if _C is not None:
+    BACKEND = "cpp_extension"
+
+    def project_point(xyz, intr, extr, W, H, nearest=0.2, extent=1.3):  # noqa: F811
+        """msplat.project_point -- /root/reference/gflow/utils/render.py:21-24, trainer.py:955."""
+        return _C.project_point(xyz, intr, extr, int(W), int(H), float(nearest), float(extent))
+
+    def compute_cov3d(scale, rotate, visible=None):  # noqa: F811
+        """msplat.compute_cov3d -- /root/reference/gflow/utils/render.py:37-41."""
+        return _C.compute_cov3d(scale, rotate, visible)
+
+    def ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible=None):  # noqa: F811
+        """msplat.ewa_project -- /root/reference/gflow/utils/render.py:44-49."""
+        return _C.ewa_project(xyz, cov3d, intr, extr, uv, int(W), int(H), visible)
+
+    def sort_gaussian(uv, depth, W, H, radius, tiles_touched):  # noqa: F811
+        """msplat.sort_gaussian -- /root/reference/gflow/utils/render.py:52-54."""
+        return _C.sort_gaussian(uv, depth, int(W), int(H), radius, tiles_touched)
+
+    def alpha_blending(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range, bg, W, H, ndc=None):  # noqa: F811
+        """msplat.alpha_blending -- /root/reference/gflow/utils/render.py:58-64 (and 68-105, 148-154)."""
+        return _C.alpha_blending(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range, float(bg), int(W),
+                                 int(H), ndc)
+
+    def compute_sh(shs, dirs, visible=None):  # noqa: F811
+        """msplat.compute_sh (north_star surface; not called by GFlow): shs (N,C,K), dirs (N,3)."""
+        return _C.compute_sh(shs, dirs, visible)
+
+    def rasterization_unfused(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):  # noqa: F811
+        """The five operators one after the other, exactly as /root/reference/gflow/utils/render.py:21-64 calls them."""
+        uv, depth = project_point(xyz, intr, extr, W, H)
+        visible = depth != 0
+        cov3d = compute_cov3d(scale, rotate, visible)
+        conic, radius, tiles_touched = ewa_project(xyz, cov3d, intr, extr, uv, W, H, visible)
+        ids, tile_range = sort_gaussian(uv, depth, W, H, radius, tiles_touched)
+        return alpha_blending(uv, conic, opacity, feature, ids, tile_range, bg, W, H)
+
+    def rasterization(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):  # noqa: F811
+        """Upstream's convenience `msplat.rasterization`: fused pipeline up to four channels, operator chain beyond."""
+        if isinstance(feature, torch.Tensor) and feature.dim() == 2 and 1 <= feature.shape[1] <= 4:
+            return _C.rasterization_fused(xyz, scale, rotate, opacity, feature, intr, extr, int(W), int(H), float(bg))
+        return rasterization_unfused(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg)
