@@ -26,12 +26,14 @@
 //    added with one RED per value into a packed 48-byte-per-Gaussian gradient record, so
 //    the (up to) ten atomics of a warp hit one or two L2 sectors.
 //  No tensor cores: this is a gather / scatter bounded by issue rate and L2 atomics.
+#include <cstdlib>
+
 #include "splat_math.cuh"
 
 namespace {
 
 constexpr int kBatch = 128;          // records per TMA stage
-constexpr int kBlendThreads = 256;   // 8 warps, each an 8x4 pixel block
+constexpr int kBlendThreads = 256;   // up to 8 warps per CTA, each an 8x4 pixel block
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -156,11 +158,14 @@ blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
     __shared__ __align__(8) uint64_t s_bar[2];
 
     gfb_pdl_wait();  // fused pipeline: tile_sort_pack may still be draining
-    const int tile = blockIdx.x;
+    // a CTA of `wpc` warps covers wpc of the tile's eight 8x4 pixel blocks (8 / wpc CTAs per tile)
+    const int wpc = blockDim.x >> 5, per_tile = 8 / wpc;
+    const int tile = blockIdx.x / per_tile;
     const int tx = tile % gx, ty = tile / gx;
     const int2 range = tile_range[tile];
     const int n = range.y - range.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = (blockIdx.x % per_tile) * wpc + (tid >> 5);  // block index inside the tile
     const int bx0 = tx * GFB_TILE + (warp & 1) * 8, by0 = ty * GFB_TILE + (warp >> 1) * 4;
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = (px < W) && (py < H);
@@ -231,7 +236,7 @@ blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                     if (__all_sync(kFull, done)) break;
                 }
             }
-            if (__syncthreads_count(done) == kBlendThreads) {
+            if (__syncthreads_count(done) == (int)blockDim.x) {
                 // drain the copy already in flight before the CTA (and its shared memory) retires
                 if (tid == 0 && b + 1 < nb) mbar_wait(&s_bar[s ^ 1], (uint32_t)((b + 1) >> 1) & 1u);
                 break;
@@ -289,12 +294,14 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
     __shared__ int s_max_last;
 
     gfb_pdl_launch_dependents();  // fused pipeline: geometry_bwd may queue behind the last wave
-    const int tile = blockIdx.x;
+    const int wpc = blockDim.x >> 5, per_tile = 8 / wpc;
+    const int tile = blockIdx.x / per_tile;
     const int tx = tile % gx, ty = tile / gx;
     const int2 range = tile_range[tile];
     const int n = range.y - range.x;
     if (n <= 0) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = (blockIdx.x % per_tile) * wpc + (tid >> 5);
     const int bx0 = tx * GFB_TILE + (warp & 1) * 8, by0 = ty * GFB_TILE + (warp >> 1) * 4;
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = (px < W) && (py < H);
@@ -461,6 +468,18 @@ unpack_grads_kernel(const float4* __restrict__ grad_pack, int N, int C, int c0, 
 
 }  // namespace
 
+// warps per CTA for the blend kernels (2, 4 or 8): fewer warps per CTA = less waiting at the per-batch
+// CTA barrier when the tile's pixel blocks see different numbers of splats, at the price of staging
+// the tile's records 8 / wpc times.  GFB_BLEND_WPC overrides the default.
+static int blend_warps_per_cta() {
+    static int wpc = [] {
+        const char* e = getenv("GFB_BLEND_WPC");
+        const int v = e ? atoi(e) : 8;
+        return (v == 2 || v == 4 || v == 8) ? v : 8;
+    }();
+    return wpc;
+}
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -506,7 +525,8 @@ int gfb_internal_blend_fwd(const void* geom_stream, const void* feat_stream, int
     const float4* gF = reinterpret_cast<const float4*>(feat_stream);
     const int2* tr = reinterpret_cast<const int2*>(tile_range);
     cudaStream_t st = (cudaStream_t)stream;
-    const dim3 grid(gx * gy), block(kBlendThreads);
+    const int wpc = blend_warps_per_cta();
+    const dim3 grid(gx * gy * (8 / wpc)), block(32 * wpc);
     cudaError_t le;
     switch (Cg) {
         case 1: le = gfb_launch_pdl(blend_fwd_kernel<1>, grid, block, st, pdl, gA, gB, gF, tr, gx, c0, bg, W, H, out, final_T, n_contrib); break;
@@ -543,11 +563,12 @@ int gfb_alpha_blending_bwd(const void* geom_stream, const void* feat_stream, int
     const float4* gF = reinterpret_cast<const float4*>(feat_stream);
     const int2* tr = reinterpret_cast<const int2*>(tile_range);
     cudaStream_t st = (cudaStream_t)stream;
+    const int wpc = blend_warps_per_cta();
     switch (Cg) {
-        case 1: blend_bwd_kernel<1><<<gx * gy, kBlendThreads, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, grad_pack); break;
-        case 2: blend_bwd_kernel<2><<<gx * gy, kBlendThreads, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, grad_pack); break;
-        case 3: blend_bwd_kernel<3><<<gx * gy, kBlendThreads, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, grad_pack); break;
-        default: blend_bwd_kernel<4><<<gx * gy, kBlendThreads, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, grad_pack); break;
+        case 1: blend_bwd_kernel<1><<<gx * gy * (8 / wpc), 32 * wpc, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, grad_pack); break;
+        case 2: blend_bwd_kernel<2><<<gx * gy * (8 / wpc), 32 * wpc, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, grad_pack); break;
+        case 3: blend_bwd_kernel<3><<<gx * gy * (8 / wpc), 32 * wpc, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, grad_pack); break;
+        default: blend_bwd_kernel<4><<<gx * gy * (8 / wpc), 32 * wpc, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, grad_pack); break;
     }
     GFB_CHECK_LAUNCH();
     return 0;
