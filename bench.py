@@ -207,6 +207,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if distributed:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = capi.load()
     N, W, H = WORKLOADS[args.workload]

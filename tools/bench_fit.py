@@ -32,6 +32,8 @@ world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1")
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
 W, H = 854, 480
 sc = make_scene(args.points, W, H, seed=0, profile="gflow")
