@@ -1,0 +1,127 @@
+"""Kernel-logic tests that need no GPU: gflow_b200/csrc/*.cu compiled for the host against the SIMT shim
+(tests/simt/) and driven through the C ABI with host pointers, compared with the CPU oracle.
+
+What this checks: thread / tile indexing, warp collectives, CTA barriers, the double-buffered
+cp.async.bulk + mbarrier staging protocol (poisoned until waited on), the segmented sort networks, the
+scan, the gradient reductions.  What it cannot check: inline PTX itself, the memory model, FMA
+contraction and MUFU rounding (hence image / gradient tolerances as on the GPU) -- the `-m gpu` tests
+stay the parity tests of record.  The emulated library is test infrastructure, never a fallback.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import assert_close
+from gflow_b200.synthetic import make_grad_image, make_scene
+from oracle import c_oracle as C
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "simt"))
+import emu  # noqa: E402
+
+IMG_OUTLIERS = dict(outlier_frac=2e-5, outlier_rel=2e-2)
+GRAD_OUTLIERS = dict(outlier_frac=1e-4, outlier_rel=5e-2)
+
+
+def _oracle(sc, Gimg, feature=None):
+    feature = sc.rgb if feature is None else feature
+    uv, depth = C.project_point(sc.xyz, sc.intr, sc.extr, sc.W, sc.H)
+    vis = depth != 0
+    cov = C.compute_cov3d(sc.scale, sc.rotate, vis)
+    conic, radius, tiles = C.ewa_project(sc.xyz, cov, sc.intr, sc.extr, uv, sc.W, sc.H, vis)
+    ids, rng = C.sort_gaussian(uv, depth, sc.W, sc.H, radius, tiles)
+    img, grads, info = C.render_step_fwd_bwd(sc.xyz, sc.scale, sc.rotate, sc.opacity, feature, sc.intr, sc.extr, sc.bg,
+                                             sc.W, sc.H, Gimg)
+    return dict(uv=uv, depth=depth, cov3d=cov, conic=conic, radius=radius, tiles=tiles, ids=ids, tile_range=rng,
+                image=img, grads=grads, K=info["K"])
+
+
+def _check(r, o, what):
+    assert r["K"] == o["K"], f"{what}: K {r['K']} vs oracle {o['K']}"
+    for k in ("uv", "depth", "conic", "radius", "ids", "tile_range"):
+        assert torch.equal(r[k], o[k]), f"{what}: {k} must be bit-exact"
+    assert_close(r["image"], o["image"], 1e-4, f"{what} image", **IMG_OUTLIERS)
+    for k in ("xyz", "scale", "rotate", "opacity", "feature", "intr", "extr"):
+        assert_close(r["grads"][k].reshape(o["grads"][k].shape), o["grads"][k], 1e-3, f"{what} grad {k}",
+                     **GRAD_OUTLIERS)
+
+
+@pytest.fixture(params=[0, 1, 2], ids=["ascending", "descending", "shuffled"])
+def schedule(request):
+    emu.set_schedule(request.param, seed=7)
+    yield request.param
+    emu.set_schedule(0)
+
+
+SCENES = [(300, 64, 48, 0, "synthetic", 0.0), (1500, 100, 70, 1, "gflow", 0.25), (800, 33, 17, 2, "synthetic", 1.0)]
+
+
+@pytest.mark.parametrize("N,W,H,seed,profile,bg", SCENES)
+def test_operator_chain_matches_oracle(N, W, H, seed, profile, bg, schedule):
+    sc = make_scene(N, W, H, seed=seed, profile=profile, bg=bg)
+    Gimg = make_grad_image(3, W, H, seed=seed + 1)
+    o = _oracle(sc, Gimg)
+    r = emu.operator_chain(sc, Gimg)
+    assert torch.equal(r["cov3d"], o["cov3d"]) and torch.equal(r["tiles"], o["tiles"])
+    _check(r, o, "operator chain")
+
+
+@pytest.mark.parametrize("N,W,H,seed,profile,bg", SCENES)
+def test_fused_pipeline_matches_oracle(N, W, H, seed, profile, bg, schedule):
+    sc = make_scene(N, W, H, seed=seed, profile=profile, bg=bg)
+    Gimg = make_grad_image(3, W, H, seed=seed + 1)
+    o = _oracle(sc, Gimg)
+    r = emu.fused_pipeline(sc, Gimg)
+    assert r["rc"] == 0
+    _check(r, o, "fused pipeline")
+
+
+def test_dense_tiles_take_every_sort_path(schedule):
+    """Many splats per tile: segments of <=64, <=128, <=256, <=512, <=1024 and >1024 keys (every branch of
+    sort_tile_cta), several TMA batches per tile and early termination (opaque splats)."""
+    seen = set()
+    for N, W, H, seed in [(4000, 48, 32, 5), (2000, 48, 32, 8), (2500, 112, 80, 6), (700, 96, 64, 7)]:
+        sc = make_scene(N, W, H, seed=seed, profile="synthetic")
+        sc.opacity.clamp_(min=0.6)
+        Gimg = make_grad_image(3, W, H, seed=9)
+        o = _oracle(sc, Gimg)
+        counts = (o["tile_range"][:, 1] - o["tile_range"][:, 0])
+        for c in counts.tolist():
+            seen.add(next(i for i, lim in enumerate([64, 128, 256, 512, 1024, 1 << 30]) if c <= lim))
+        _check(emu.operator_chain(sc, Gimg), o, "dense operator chain")
+        _check(emu.fused_pipeline(sc, Gimg), o, "dense fused pipeline")
+    assert seen == {0, 1, 2, 3, 4, 5}, seen
+
+
+@pytest.mark.parametrize("C", [1, 2, 4, 5])
+def test_channel_groups(C):
+    N, W, H = 400, 48, 40
+    sc = make_scene(N, W, H, seed=3, bg=0.5)
+    gen = torch.Generator().manual_seed(11)
+    feature = torch.rand(N, C, generator=gen)
+    Gimg = make_grad_image(C, W, H, seed=4)
+    o = _oracle(sc, Gimg, feature)
+    _check(emu.operator_chain(sc, Gimg, feature=feature), o, f"C={C} operator chain")
+    if C <= 4:
+        _check(emu.fused_pipeline(sc, Gimg, feature=feature), o, f"C={C} fused pipeline")
+
+
+def test_fused_pipeline_capacity_overflow_is_reported():
+    sc = make_scene(500, 64, 64, seed=1)
+    Gimg = make_grad_image(3, 64, 64)
+    full = emu.fused_pipeline(sc, Gimg)
+    assert full["rc"] == 0 and full["K"] > 100
+    r = emu.fused_pipeline(sc, Gimg, capacity=full["K"] // 2)
+    assert r["rc"] == -3 and r["K"] == full["K"]  # GFB_E_CAPACITY, K still delivered for the retry
+
+
+def test_empty_inputs():
+    sc = make_scene(10, 32, 32, seed=0, bg=0.3)
+    for k in ("xyz", "scale", "rotate", "opacity", "rgb"):
+        setattr(sc, k, getattr(sc, k)[:0].contiguous())
+    Gimg = make_grad_image(3, 32, 32)
+    r = emu.fused_pipeline(sc, Gimg, capacity=0)
+    assert r["rc"] == 0 and r["K"] == 0
+    assert torch.allclose(r["image"], torch.full_like(r["image"], 0.3))
+    assert int(r["tile_range"].abs().sum()) == 0
