@@ -21,8 +21,9 @@ _STAMP = os.path.join(LIB_DIR, "build.stamp")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC]
 # geometry.cu must not fuse multiply-adds: its float32 results are bit-compared with the oracle
-PER_FILE_FLAGS = {"geometry.cu": ["-fmad=false"], "binning.cu": ["-fmad=false"], "pipeline.cu": ["-fmad=false"]}
-SOURCES = ["capi.cu", "geometry.cu", "binning.cu", "blend.cu", "pipeline.cu"]
+PER_FILE_FLAGS = {"geometry.cu": ["-fmad=false"], "binning.cu": ["-fmad=false"], "pipeline.cu": ["-fmad=false"],
+                  "fit.cu": ["-fmad=false"]}
+SOURCES = ["capi.cu", "geometry.cu", "binning.cu", "blend.cu", "pipeline.cu", "fit.cu"]
 
 
 def _nvcc() -> str:

@@ -45,7 +45,26 @@ SIGNATURES = {
     "gfb_alpha_blending_fwd": (I, [P, P, L, P, I, I, I, F, I, I, P, P, P, P]),
     "gfb_alpha_blending_bwd": (I, [P, P, L, P, P, I, I, I, F, I, I, P, P, P, P, P]),
     "gfb_blend_unpack_grads": (I, [P, I, I, I, I, P, P, P, P, I, P]),
+    "gfb_fit_get_layout": (I, [I, I, I, L, I, P]),
+    "gfb_fit_init": (I, [P, P, L, I, P]),
+    "gfb_fit_iterate": (I, [P, P, L, I, I, I, P]),
 }
+
+
+class FitProblem(ctypes.Structure):
+    """struct gfb_fit_problem of include/gflow_b200.h, field by field."""
+    _fields_ = [(n, P) for n in ("xyz", "scale", "rotate", "opacity", "rgb", "pose", "depth_ab", "intr", "gt_image",
+                                 "gt_depth", "pixel_mask", "still_mask", "dbg_grads", "dbg_act")] + \
+               [(n, ctypes.c_int32) for n in ("N", "W", "H", "n_still", "total_iters", "camera_only", "freeze_rgb",
+                                              "use_ssim")] + \
+               [(n, F) for n in ("bg", "nearest", "extent", "lr", "lr_camera", "lambda_rgb", "lambda_depth",
+                                 "lambda_var", "lambda_scale", "beta1", "beta2", "eps", "depth_den_min")]
+
+
+class FitLayout(ctypes.Structure):
+    """struct gfb_fit_layout of include/gflow_b200.h."""
+    _fields_ = [(n, c_size_t) for n in ("status", "loss_hist", "cam", "adam_m", "adam_v", "uv", "depth", "conic",
+                                        "radius", "tile_range", "ids", "out", "g_out", "total")]
 
 
 def library_path() -> str:

@@ -33,6 +33,9 @@ int gfb_internal_host_sync(int32_t** pinned, int32_t** mapped, cudaEvent_t* ev);
 
 static inline int gfb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// control buffer of the fused pipelines (gfb_render_control_bytes): counts[T*R] | ctrl[4] | offsets[T*R + 1]
+enum { GFB_CTRL_DONE = 0, GFB_CTRL_K = 1, GFB_CTRL_WORDS = 4 };
+
 // ---- programmatic dependent launch (PDL): a kernel launched with gfb_launch_pdl may start while
 // its predecessor in the stream is still draining; it must call gfb_pdl_wait() before touching
 // anything the predecessor wrote.  gfb_pdl_launch_dependents() in the predecessor lets the

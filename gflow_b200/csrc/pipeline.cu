@@ -35,7 +35,7 @@ namespace {
 using namespace gfbm;
 
 // ctrl words that follow the T tile counters in the control buffer
-enum { CTRL_DONE = 0, CTRL_K = 1, CTRL_WORDS = 4 };
+enum { CTRL_DONE = GFB_CTRL_DONE, CTRL_K = GFB_CTRL_K, CTRL_WORDS = GFB_CTRL_WORDS };
 
 __global__ void __launch_bounds__(kThreads)
 preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale, const float4* __restrict__ rotate,
@@ -236,6 +236,35 @@ geometry_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ sca
 
 }  // namespace
 
+// Second and third forward kernels for a caller that has run its own preprocess (gfb_render_forward
+// above, the native fit iteration in fit.cu): claim slots + write keys, then per-tile sort + pack.
+// control_ws is laid out as gfb_render_control_bytes() describes and holds the scanned offsets.
+int gfb_internal_scatter_sort_pack(const void* rect_ws, const float* depth, int N, int W, int H, void* control_ws,
+                                   int64_t capacity, void* keys_ws, int32_t* tile_range, const float* uv,
+                                   const float* conic, const float* opacity, const float* feature, int C,
+                                   int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, void* stream,
+                                   bool pdl) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
+    const int R = gfb_tile_replicas(T);
+    int32_t* counts = (int32_t*)control_ws;
+    int32_t* tile_offsets = counts + (size_t)T * R + CTRL_WORDS;
+    float4* sA = reinterpret_cast<float4*>(geom_stream);
+    if (N > 0 && capacity > 0) {
+        GFB_TRY(gfb_launch_pdl(scatter_kernel, dim3(gfb_div_up(N, kThreads)), dim3(kThreads), st, pdl,
+                               reinterpret_cast<const ushort4*>(rect_ws), depth, N, gx, R, tile_offsets, counts,
+                               reinterpret_cast<unsigned long long*>(keys_ws), (long long)capacity));
+        GFB_CHECK_LAUNCH();
+    }
+    PackArgs pa{reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, sA, sA + capacity,
+                reinterpret_cast<float4*>(feat_stream), gaussian_ids_sorted};
+    GFB_TRY(gfb_launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(kSortThreads), st, pdl, tile_offsets, R,
+                           reinterpret_cast<unsigned long long*>(keys_ws), reinterpret_cast<int2*>(tile_range), T,
+                           (long long)capacity, pa));
+    GFB_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" {
 
 size_t gfb_render_control_bytes(int W, int H) {
@@ -277,19 +306,10 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     GFB_CHECK_LAUNCH();
     GFB_TRY(cudaEventRecord(ev, st));
     // speculative part: enqueued before K is known on the host
-    float4* sA = reinterpret_cast<float4*>(geom_stream);
-    if (N > 0 && capacity > 0) {
-        GFB_TRY(gfb_launch_pdl(scatter_kernel, dim3(gfb_div_up(N, kThreads)), dim3(kThreads), st, true,
-                               reinterpret_cast<const ushort4*>(rect_ws), depth, N, gx, R, tile_offsets, counts,
-                               reinterpret_cast<unsigned long long*>(keys_ws), (long long)capacity));
-        GFB_CHECK_LAUNCH();
-    }
-    PackArgs pa{reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, sA, sA + capacity,
-                reinterpret_cast<float4*>(feat_stream), gaussian_ids_sorted};
-    GFB_TRY(gfb_launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(kSortThreads), st, true, tile_offsets, R,
-                           reinterpret_cast<unsigned long long*>(keys_ws), reinterpret_cast<int2*>(tile_range), T,
-                           (long long)capacity, pa));
-    GFB_CHECK_LAUNCH();
+    rc = gfb_internal_scatter_sort_pack(rect_ws, depth, N, W, H, control_ws, capacity, keys_ws, tile_range, uv, conic,
+                                        opacity, feature, C, gaussian_ids_sorted, geom_stream, feat_stream, stream,
+                                        true);
+    if (rc) return rc;
     rc = gfb_internal_blend_fwd(geom_stream, feat_stream, capacity, tile_range, C, 0, C, bg, W, H, out, final_T,
                                 n_contrib, stream, true);
     if (rc) return rc;

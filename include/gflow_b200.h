@@ -161,6 +161,69 @@ int gfb_render_backward(const float *xyz, const float *scale, const float *rotat
                         const int32_t *n_contrib, const float *g_out, void *grad_ws, float *d_xyz, float *d_scale,
                         float *d_rotate, float *d_opacity, float *d_feature, void *stream);
 
+/* ------------------------------------------------------------------ native per-frame optimisation loop
+ * The inner loop GFlow runs per frame, /root/reference/gflow/trainer.py:387-558 (driven by
+ * /root/reference/gflow/fit_video.py:119-142,256-315), as ONE stream of kernels per iteration with no host
+ * synchronisation inside it:
+ *   raw parameters -> activations (trainer.py:62-69) + project_point + compute_cov3d + ewa_project + tile
+ *   binning (one kernel) -> scatter -> per-tile sort + pack -> ONE 4-channel blend that renders rgb and the
+ *   depth map together (render.py:58-74 issues two blends over the same sort) -> photometric loss
+ *   (mean squared error [+ 1 - SSIM, pytorch_ssim.py:17-37]) + scale/shift invariant depth loss
+ *   (trainer.py:476-488) and dL/d(image) -> blend backward -> geometry backward through the activations,
+ *   gradient masks (trainer.py:535-551) and the Adam update (torch.optim.Adam defaults, LinearLR
+ *   1.0 -> 0.1, trainer.py:123-153,383-384,554-555) of every attribute in the same kernel -> pose
+ *   (roma xyzw quaternion + translation, trainer.py:115-121) and depth_a/depth_b update.
+ * All pointers are device pointers.  Raw parameters, pose and depth_ab are updated in place. */
+typedef struct gfb_fit_problem {
+    float *xyz, *scale, *rotate, *opacity, *rgb; /* raw attributes (N,3) (N,3) (N,4) (N,1) (N,3), trainer.py:81-88 */
+    float *pose;                 /* 7: qx qy qz qw tx ty tz (raw; normalised inside, trainer.py:119) */
+    float *depth_ab;             /* 2: depth_a, depth_b (trainer.py:146-149) */
+    const float *intr;           /* 4: fx fy cx cy */
+    const float *gt_image;       /* (H,W,3) in [0,1] */
+    const float *gt_depth;       /* (H,W,1) or NULL (no depth term) */
+    const uint8_t *pixel_mask;   /* (H,W) 1 = pixel takes part in the losses, or NULL (trainer.py:452-455,484) */
+    const uint8_t *still_mask;   /* (n_still) 1 = xyz gradient zeroed (trainer.py:542-546), or NULL */
+    float *dbg_grads;            /* NULL, or (N,14) raw-attribute gradients of the last iteration before masking */
+    float *dbg_act;              /* NULL, or (N,14) activated attributes of the last iteration */
+    int32_t N, W, H, n_still;
+    int32_t total_iters;         /* LinearLR horizon (`iterations` of trainer.train) */
+    int32_t camera_only;         /* attribute gradients zeroed, pose still optimised (trainer.py:548-551) */
+    int32_t freeze_rgb;          /* rgb gradient zeroed (frames >= 1, trainer.py:537-540) */
+    int32_t use_ssim;            /* loss_rgb = mse + (1 - SSIM) as in trainer.py:459-462; 0 = mse only */
+    float bg, nearest, extent;
+    float lr, lr_camera, lambda_rgb, lambda_depth, lambda_var, lambda_scale;
+    float beta1, beta2, eps;     /* Adam; torch defaults 0.9, 0.999, 1e-8 */
+    float depth_den_min;         /* lower clamp of the depth-loss denominator (0 = reference behaviour) */
+} gfb_fit_problem;
+
+/* byte offsets of the pieces of the fit workspace a caller may want to read back */
+typedef struct gfb_fit_layout {
+    size_t status;      /* int32[16]: [0] iterations done, [1] K of the last iteration, [2] max K seen,
+                           [8..14] float bits of dL/d(pose) of the last iteration (diagnostics) */
+    size_t loss_hist;   /* float[max_iters][8]: total, mse, ssim, depth, var, scale, -, - per iteration */
+    size_t cam;         /* float[16]: extr (3x4) + intr used by the NEXT iteration */
+    size_t adam_m;      /* float[14 N + 12]: xyz | scale | rotate | opacity | rgb | pose(7) | depth_ab(2) */
+    size_t adam_v;
+    size_t uv;          /* float (N,2) of the last iteration */
+    size_t depth;       /* float (N,1) */
+    size_t conic;       /* float (N,3) */
+    size_t radius;      /* int32 (N,1) */
+    size_t tile_range;  /* int32 (T,2) */
+    size_t ids;         /* int32 (capacity) gaussian_ids_sorted */
+    size_t out;         /* float (C,H,W), C = 4 with a depth term (rgb + depth map) else 3 */
+    size_t g_out;       /* float (C,H,W) dL/d(out) */
+    size_t total;       /* workspace size in bytes */
+} gfb_fit_layout;
+
+int gfb_fit_get_layout(int N, int W, int H, int64_t capacity, int max_iters, gfb_fit_layout *layout);
+/* zeroes the Adam state / status / loss history and derives the camera of iteration 0 from the pose */
+int gfb_fit_init(const gfb_fit_problem *problem, void *workspace, int64_t capacity, int max_iters, void *stream);
+/* enqueues iterations [first_iter, first_iter + n_iters) and returns without synchronising.  K is not
+ * known on the host: the kernels clamp at `capacity`; status[2] (max K) > capacity after the fact means the
+ * iterations since the last check rendered truncated tiles and must be redone with a larger workspace. */
+int gfb_fit_iterate(const gfb_fit_problem *problem, void *workspace, int64_t capacity, int max_iters, int first_iter,
+                    int n_iters, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
