@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--profile", default="synthetic", choices=["synthetic", "gflow"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-fit-loop", action="store_true", help="skip the config-3 Adam-loop section")
     return ap.parse_args()
 
 
@@ -372,6 +373,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         t_gather = time.perf_counter() - t0
 
+    # ---- BASELINE config 3 (300-iteration per-frame Adam loop), operator path and native path, each in a
+    #      process of its own (tools/bench_fit.py) so a fault there cannot touch the numbers above
+    fit_loop = None
+    if rank == 0 and world == 1 and args.workload == "cfg2" and not args.no_fit_loop:
+        fit_loop = fit_loop_section()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(N, W, H, args.profile, None, 1, budget_s=12.0)
@@ -399,11 +406,40 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if fit_loop is not None:
+            line["fit_loop"] = fit_loop
         if distributed:
             line["collectives_ms"] = {"broadcast_state": 1e3 * t_bcast, "gather_frames": 1e3 * t_gather}
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
+
+
+def fit_loop_section():
+    """BASELINE config 3: 60k Gaussians, 854x480, per-frame Adam loop with rgb + depth loss, iterations/s.
+    `operator_path` = msplat operators + autograd + torch.optim.Adam (how gflow/trainer.py drives them);
+    `native` = the same iteration as nine kernels (csrc/fit.cu)."""
+    import subprocess
+
+    out = {"what": "BASELINE config 3: 60k Gaussians, 854x480, per-frame Adam loop (mse + depth loss), iterations/s",
+           "unit": "iters/s"}
+    tool = os.path.join(ROOT, "tools", "bench_fit.py")
+    for key, extra, iters in (("operator_path", [], 100), ("native", ["--native"], 300)):
+        try:
+            res = subprocess.run([sys.executable, tool, "--iters", str(iters), *extra], capture_output=True, text=True,
+                                 timeout=240)
+            rec = None
+            for ln in res.stdout.splitlines():
+                if ln.startswith("{"):
+                    rec = json.loads(ln)
+            if rec is None:
+                out[key] = {"error": (res.stderr or res.stdout)[-300:]}
+            else:
+                out[key] = {"value": rec["value"], "iterations": rec["iterations"], "seconds": rec["seconds"],
+                            "loss_first": rec["loss_first"], "loss_last": rec["loss_last"]}
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": repr(e)[:300]}
+    return out
 
 
 def kernel_roofline(G, lib, params, intr, extr, Gimg, bg, N, W, H, T, P, flush_l2, dev, reps=30):

@@ -6,16 +6,30 @@ parameters -> activations -> render rgb + depth map from ONE sort -> photometric
 invariant depth loss -> Adam with a LinearLR 1.0 -> 0.1 schedule.  It exists so the frame-sharded
 mode of SURVEY.md 8e has something to shard and so BASELINE config 3 (300-iteration Adam loop) can
 be timed on the GPU box, where /root/reference is not available; GFlow's own trainer runs unmodified
-on the drop-in `msplat` module.  Deliberately NOT rebuilt here: SSIM, flow / still /
-variance terms, densification, masks, logging, checkpoints (SURVEY.md 8f "next" rows).
+on the drop-in `msplat` module.
+
+Two execution modes with the same semantics:
+  * operator path (default): the msplat operators one by one + torch autograd + torch.optim.Adam, the way
+    trainer.py drives them (~150 launches and 2-3 ms of host work per iteration);
+  * native path (FitConfig.native): the whole iteration as nine kernels with no host synchronisation
+    (csrc/fit.cu through gfb_fit_init / gfb_fit_iterate): activations + geometry + binning, one 4-channel
+    blend for rgb and the depth map, fused losses, blend backward, geometry backward with the Adam update
+    in the same kernel.
+Terms covered: mse [+ 1 - SSIM], depth, scale-variance and scale/depth regularisers, the camera-only /
+frozen-rgb / still-xyz gradient masks and the pixel mask (trainer.py:452-551).  Not rebuilt: flow / still
+position terms, densification, logging, checkpoints (SURVEY.md 8f "next" rows).
 """
 from __future__ import annotations
 
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import ctypes
+import math
+
 import torch
 
+from . import capi
 from . import frames as _frames
 from . import ops
 
@@ -86,6 +100,33 @@ class FitConfig:
     camera_only: bool = False
     background: float = 0.0
     fused: bool = False  # True: render rgb through msplat.rasterization (single feature map only)
+    native: bool = False  # True: the whole iteration runs natively (csrc/fit.cu), no autograd / torch.optim
+    use_ssim: bool = False  # loss_rgb = mse + (1 - SSIM) as in trainer.py:459-462 (False: mse only)
+    lambda_var: float = 0.0  # trainer.py:490-492
+    lambda_scale: float = 0.0  # trainer.py:495-501
+    freeze_rgb: bool = False  # frames >= 1: rgb gradient zeroed (trainer.py:537-540)
+    check_every: int = 50  # native path: iterations enqueued between two looks at the intersection count
+
+
+_SSIM_WINDOW = None
+
+
+def ssim(img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
+    """SSIM of two (1,C,H,W) images exactly as /root/reference/gflow/utils/pytorch_ssim.py:7-37 computes it
+    (11x11 Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2, mean over all elements)."""
+    global _SSIM_WINDOW
+    C = img1.shape[1]
+    if _SSIM_WINDOW is None:
+        g = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)], dtype=torch.float32)
+        g = g / g.sum()
+        _SSIM_WINDOW = g[:, None] @ g[None, :]
+    win = _SSIM_WINDOW.to(img1.device, img1.dtype).expand(C, 1, 11, 11).contiguous()
+    conv = lambda x: torch.nn.functional.conv2d(x, win, padding=5, groups=C)  # noqa: E731
+    mu1, mu2 = conv(img1), conv(img2)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1 * mu1, mu2 * mu2, mu1 * mu2
+    s1, s2, s12 = conv(img1 * img1) - mu1_sq, conv(img2 * img2) - mu2_sq, conv(img1 * img2) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    return (((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean()
 
 
 @dataclass
@@ -117,7 +158,7 @@ class FrameFitter:
     def state(self) -> Dict[str, torch.Tensor]:
         return {k: v.detach() for k, v in self.attrs.items()}
 
-    def render(self, bg: float = 0.0, want_depth: bool = True):
+    def render(self, bg: float = 0.0, want_depth: bool = True, with_depth: bool = False):
         """rgb (3,H,W) and depth map (1,H,W) from one projection + one sort, the way
         /root/reference/gflow/utils/render.py:21-74 chains the operators."""
         xyz, scale, rotate = self.get_attribute("xyz"), self.get_attribute("scale"), self.get_attribute("rotate")
@@ -130,10 +171,17 @@ class FrameFitter:
         ids, tile_range = ops.sort_gaussian(uv, depth, self.W, self.H, radius, tiles)
         img = ops.alpha_blending(uv, conic, opacity, rgb, ids, tile_range, bg, self.W, self.H)
         dmap = ops.alpha_blending(uv, conic, opacity, depth, ids, tile_range, bg, self.W, self.H) if want_depth else None
+        if with_depth:
+            return img, dmap, uv, depth
         return img, dmap, uv
 
-    def train(self, gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor], cfg: FitConfig) -> FitResult:
-        """gt_image (H,W,3) in [0,1]; gt_depth (H,W,1) or None.  Returns per-iteration losses and the final render."""
+    def train(self, gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor], cfg: FitConfig,
+              pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None) -> FitResult:
+        """gt_image (H,W,3) in [0,1]; gt_depth (H,W,1) or None; pixel_mask (H,W) bool (True = pixel counts,
+        trainer.py:452-455); still_mask (n,) bool (True = xyz frozen, trainer.py:542-546).
+        Returns per-iteration losses and the final render."""
+        if cfg.native:
+            return self._train_native(gt_image, gt_depth, cfg, pixel_mask, still_mask)
         groups = [{"params": list(self.attrs.values()), "lr": cfg.lr},
                   {"params": [self.pose], "lr": cfg.lr_camera},
                   {"params": [self.depth_a, self.depth_b], "lr": cfg.lr}]
@@ -142,23 +190,44 @@ class FrameFitter:
         use_depth = gt_depth is not None and cfg.lambda_depth > 0
         res = FitResult()
         loss_hist = []
+        pm = None if pixel_mask is None else pixel_mask.to(gt_image.dtype)
+        gt = gt_image if pm is None else gt_image * pm[..., None]
         for _ in range(cfg.iterations):
-            if cfg.fused and not use_depth:
+            uv = depth = None
+            if cfg.fused and not use_depth and not cfg.lambda_scale:
                 img = ops.rasterization(self.get_attribute("xyz"), self.get_attribute("scale"),
                                         self.get_attribute("rotate"), self.get_attribute("opacity"),
                                         self.get_attribute("rgb"), self.intr, self.get_extr(), self.W, self.H,
                                         cfg.background)
                 dmap = None
             else:
-                img, dmap, _ = self.render(cfg.background, want_depth=use_depth)
-            loss = cfg.lambda_rgb * torch.mean((img.permute(1, 2, 0) - gt_image) ** 2)
+                img, dmap, uv, depth = self.render(cfg.background, want_depth=use_depth, with_depth=True)
+            if pm is not None:
+                img = img * pm[None]
+            loss_rgb = torch.mean((img.permute(1, 2, 0) - gt) ** 2)
+            if cfg.use_ssim:
+                loss_rgb = loss_rgb + (1.0 - ssim(img[None], gt.permute(2, 0, 1)[None]))
+            loss = cfg.lambda_rgb * loss_rgb
             if use_depth:
                 d = self.depth_a * dmap.permute(1, 2, 0) + self.depth_b
                 # (a D + b - D_gt)^2 / (a D + b + D_gt), /root/reference/gflow/trainer.py:476-488; the clamp only
                 # protects pixels where both depths are 0 (uncovered synthetic targets)
-                loss = loss + cfg.lambda_depth * torch.mean((d - gt_depth) ** 2 / (d + gt_depth).clamp_min(1e-6))
+                ld = (d - gt_depth) ** 2 / (d + gt_depth).clamp_min(1e-6)
+                if pm is not None:
+                    ld = ld * pm[..., None]
+                loss = loss + cfg.lambda_depth * torch.mean(ld)
+            if cfg.lambda_var:
+                loss = loss + cfg.lambda_var * torch.mean(torch.std(self.get_attribute("scale"), dim=1))
+            if cfg.lambda_scale:
+                within = (uv[:, 0] > 0) & (uv[:, 0] < self.W - 1) & (uv[:, 1] > 0) & (uv[:, 1] < self.H - 1)
+                ls = torch.norm(self.get_attribute("scale")[within], dim=1) * (1.0 / depth[within]).squeeze(-1)
+                loss = loss + cfg.lambda_scale * ls.mean()
             opt.zero_grad(set_to_none=True)
             loss.backward()
+            if cfg.freeze_rgb and self.attrs["rgb"].grad is not None:  # trainer.py:537-540
+                self.attrs["rgb"].grad.zero_()
+            if still_mask is not None and self.attrs["xyz"].grad is not None:  # trainer.py:542-546
+                self.attrs["xyz"].grad[: still_mask.shape[0]][still_mask] = 0.0
             if cfg.camera_only:  # /root/reference/gflow/trainer.py:548-551
                 for p in self.attrs.values():
                     if p.grad is not None:
@@ -171,6 +240,163 @@ class FrameFitter:
             res.image, _, res.uv = self.render(cfg.background, want_depth=False)
             res.pose = self.pose.detach().clone()
         return res
+
+    def _train_native(self, gt_image, gt_depth, cfg: FitConfig, pixel_mask, still_mask) -> FitResult:
+        loop = NativeFitLoop(self, gt_image, gt_depth, cfg, pixel_mask=pixel_mask, still_mask=still_mask)
+        loop.run(cfg.iterations)
+        res = FitResult()
+        res.losses = [float(v) for v in loop.loss_history()[:, 0].cpu()]
+        with torch.no_grad():
+            res.image, _, res.uv = self.render(cfg.background, want_depth=False)
+            res.pose = self.pose.detach().clone()
+        return res
+
+
+class NativeFitLoop:
+    """Host driver of the native iteration (csrc/fit.cu): owns the workspace, enqueues iterations in chunks
+    and only looks at the device between chunks (intersection count against the workspace capacity).
+
+    The raw attributes / pose / depth_a,b of `fitter` are updated IN PLACE by the kernels.  There is no
+    CPU fallback: everything must live on one CUDA device."""
+
+    def __init__(self, fitter: "FrameFitter", gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor], cfg: FitConfig,
+                 pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None,
+                 capacity: Optional[int] = None, debug: bool = False):
+        dev = fitter.attrs["xyz"].device
+        self._require_device(dev)
+        self.lib = self._library()
+        self.fitter, self.cfg, self.dev = fitter, cfg, dev
+        self.N, self.W, self.H = int(fitter.attrs["xyz"].shape[0]), fitter.W, fitter.H
+        if self.N <= 0:
+            raise RuntimeError("gflow_b200: the native fit loop needs at least one Gaussian")
+        for k, w in _frames.STATE_KEYS:
+            t = fitter.attrs[k].data
+            if tuple(t.shape) != (self.N, w) or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError(f"gflow_b200: attribute {k} must be a contiguous float32 ({self.N}, {w}) tensor")
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.gt_image = gt_image.detach().to(**f32).contiguous()
+        if tuple(self.gt_image.shape) != (self.H, self.W, 3):
+            raise RuntimeError(f"gflow_b200: gt_image must be ({self.H}, {self.W}, 3), got {tuple(gt_image.shape)}")
+        self.use_depth = gt_depth is not None and cfg.lambda_depth > 0
+        self.gt_depth = gt_depth.detach().to(**f32).contiguous() if self.use_depth else None
+        if self.use_depth and self.gt_depth.numel() != self.W * self.H:
+            raise RuntimeError("gflow_b200: gt_depth must have H*W elements")
+        self.pixel_mask = None if pixel_mask is None else pixel_mask.to(dev).to(torch.uint8).contiguous()
+        self.still_mask = None if still_mask is None else still_mask.to(dev).to(torch.uint8).contiguous()
+        if self.still_mask is not None and self.still_mask.numel() > self.N:
+            raise RuntimeError("gflow_b200: still_mask is longer than the number of Gaussians")
+        # depth_a / depth_b live in one 2-float tensor on the device side; copied back after every run()
+        self.depth_ab = torch.cat([fitter.depth_a.data.reshape(1), fitter.depth_b.data.reshape(1)]).contiguous()
+        self.dbg_grads = torch.zeros(self.N, 14, **f32) if debug else None
+        self.dbg_act = torch.zeros(self.N, 14, **f32) if debug else None
+        self.iters = int(cfg.iterations)
+        self.done = 0
+        self.capacity = int(capacity) if capacity is not None else 6 * self.N + 65536
+        self.ws = None
+        self._alloc(self.capacity)
+        with self._device_guard():
+            capi.check(self.lib.gfb_fit_init(ctypes.addressof(self.problem), self.ws.data_ptr(), self.capacity, self.iters,
+                                             self._stream()), "fit init")
+
+    # ------------------------------------------------------------------ plumbing
+    # (separate methods so the CPU test-suite can drive this host logic against the emulated kernel library;
+    #  the product class itself only accepts CUDA tensors and only loads libgflow_b200.so)
+    def _require_device(self, dev) -> None:
+        if dev.type != "cuda":
+            raise RuntimeError("gflow_b200: the native fit loop needs CUDA tensors (no CPU fallback exists)")
+
+    def _library(self):
+        return capi.load()
+
+    def _stream(self) -> int:
+        return ops._stream()
+
+    def _device_guard(self):
+        return ops._on_device(self.dev)
+
+    def _alloc(self, capacity: int) -> None:
+        lay = capi.FitLayout()
+        capi.check(self.lib.gfb_fit_get_layout(self.N, self.W, self.H, capacity, self.iters, ctypes.addressof(lay)),
+                   "fit layout")
+        old, old_lay = self.ws, getattr(self, "lay", None)
+        self.ws = torch.empty(lay.total, dtype=torch.uint8, device=self.dev)
+        if old is not None:  # everything before `uv` (status, losses, camera, Adam state) is capacity independent
+            self.ws[: lay.uv].copy_(old[: old_lay.uv])
+        self.lay, self.capacity = lay, capacity
+        f, c, pr = self.fitter, self.cfg, capi.FitProblem()
+        for k in ATTRS:
+            setattr(pr, k, f.attrs[k].data.data_ptr())
+        pr.pose, pr.depth_ab, pr.intr = f.pose.data.data_ptr(), self.depth_ab.data_ptr(), f.intr.data_ptr()
+        pr.gt_image, pr.gt_depth = self.gt_image.data_ptr(), ops._ptr(self.gt_depth)
+        pr.pixel_mask, pr.still_mask = ops._ptr(self.pixel_mask), ops._ptr(self.still_mask)
+        pr.dbg_grads, pr.dbg_act = ops._ptr(self.dbg_grads), ops._ptr(self.dbg_act)
+        pr.N, pr.W, pr.H = self.N, self.W, self.H
+        pr.n_still = 0 if self.still_mask is None else self.still_mask.numel()
+        pr.total_iters = self.iters
+        pr.camera_only, pr.freeze_rgb, pr.use_ssim = int(c.camera_only), int(c.freeze_rgb), int(c.use_ssim)
+        pr.bg, pr.nearest, pr.extent = float(c.background), 0.2, 1.3
+        pr.lr, pr.lr_camera = float(c.lr), float(c.lr_camera)
+        pr.lambda_rgb, pr.lambda_depth = float(c.lambda_rgb), float(c.lambda_depth if self.use_depth else 0.0)
+        pr.lambda_var, pr.lambda_scale = float(c.lambda_var), float(c.lambda_scale)
+        pr.beta1, pr.beta2, pr.eps = 0.9, 0.999, 1e-8
+        pr.depth_den_min = 1e-6
+        self.problem = pr
+
+    def _view(self, off: int, count: int, dtype=torch.float32) -> torch.Tensor:
+        return self.ws[off: off + 4 * count].view(dtype)
+
+    def _snapshot(self):
+        f = self.fitter
+        return ([f.attrs[k].data.clone() for k in ATTRS], f.pose.data.clone(), self.depth_ab.clone(),
+                self.ws[: self.lay.uv].clone(), self.done)
+
+    def _restore(self, snap) -> None:
+        attrs, pose, ab, head, done = snap
+        for k, t in zip(ATTRS, attrs):
+            self.fitter.attrs[k].data.copy_(t)
+        self.fitter.pose.data.copy_(pose)
+        self.depth_ab.copy_(ab)
+        self.ws[: self.lay.uv].copy_(head)
+        self.done = done
+
+    # ------------------------------------------------------------------ public
+    def run(self, n_iters: int) -> None:
+        """Enqueues `n_iters` iterations in chunks of cfg.check_every.  After each chunk the largest
+        intersection count seen is compared with the workspace capacity; a chunk that overflowed is
+        rolled back and redone with a larger workspace (its tiles were truncated)."""
+        end = min(self.iters, self.done + int(n_iters))
+        with self._device_guard():
+            while self.done < end:
+                n = min(max(1, int(self.cfg.check_every)), end - self.done)
+                snap = self._snapshot()
+                capi.check(self.lib.gfb_fit_iterate(ctypes.addressof(self.problem), self.ws.data_ptr(), self.capacity,
+                                                    self.iters, self.done, n, self._stream()), "fit iterate")
+                self.done += n
+                k_max = int(self._view(self.lay.status, 16, torch.int32)[2])  # synchronises: one read per chunk
+                if k_max > self.capacity:
+                    self._restore(snap)
+                    self._view(self.lay.status, 16, torch.int32)[2] = 0
+                    self._alloc(int(1.5 * k_max) + 65536)
+        self.fitter.depth_a.data.copy_(self.depth_ab[0:1])
+        self.fitter.depth_b.data.copy_(self.depth_ab[1:2])
+
+    def loss_history(self) -> torch.Tensor:
+        """(iterations done, 8): total, mse, ssim, depth, var, scale, -, - per iteration."""
+        return self._view(self.lay.loss_hist, self.iters * 8).reshape(self.iters, 8)[: self.done]
+
+    def status(self) -> torch.Tensor:
+        return self._view(self.lay.status, 16, torch.int32)
+
+    def d_pose(self) -> torch.Tensor:
+        return self._view(self.lay.status + 32, 7)
+
+    def camera(self) -> torch.Tensor:
+        return self._view(self.lay.cam, 16)
+
+    def rendered(self) -> torch.Tensor:
+        """(C,H,W) output of the last iteration's blend: rgb, plus the depth map as channel 3 with a depth term."""
+        C = 4 if self.use_depth else 3
+        return self._view(self.lay.out, C * self.H * self.W).reshape(C, self.H, self.W)
 
 
 def fit_sequence_sharded(state0: Optional[Dict[str, torch.Tensor]], intr: torch.Tensor, frame_targets, W: int, H: int,

@@ -1,0 +1,161 @@
+"""Shared checker of the native fit iteration (csrc/fit.cu) against oracle/fit_ref.py, used with the emulated
+kernel library on the CPU (tests/test_simt_fit.py) and with the real library on the GPU
+(tests/test_zz_native_fit_gpu.py).
+
+Every iteration is checked at the kernel's own current parameters, so the comparison does not drift:
+  * losses of the iteration (mse / SSIM / depth / regularisers) against the oracle's forward,
+  * raw-attribute gradients (before masking), dL/d(pose) and the depth_a / depth_b update against autograd,
+  * the in-kernel Adam + LinearLR update against torch.optim.Adam fed with the kernel's gradients.
+"""
+import torch
+
+from conftest import assert_close
+from gflow_b200 import fit
+from gflow_b200.synthetic import make_scene
+from oracle import fit_ref as FR
+
+ATTRS = FR.ATTRS
+WIDTH = {"xyz": 3, "scale": 3, "rotate": 4, "opacity": 1, "rgb": 3}
+
+
+def raw_state(sc, seed):
+    g = torch.Generator().manual_seed(seed)
+    sign = torch.where(torch.rand(sc.scale.shape, generator=g) < 0.3, -1.0, 1.0)  # abs() must see both signs
+    return {"xyz": sc.xyz.clone(), "scale": sc.scale * sign,
+            "rotate": sc.rotate * (0.5 + torch.rand(sc.rotate.shape[0], 1, generator=g)),
+            "opacity": torch.logit(sc.opacity.clamp(0.02, 0.98)) / 10.0, "rgb": torch.logit(sc.rgb.clamp(0.02, 0.98))}
+
+
+def make_problem(N=350, W=64, H=48, seed=0):
+    sc = make_scene(N, W, H, seed=seed, profile="synthetic")
+    raw = raw_state(sc, seed)
+    pose = fit.extr_to_pose(sc.extr) * 1.7  # un-normalised quaternion: the normalisation backward matters
+    pose[4:] /= 1.7
+    # target: the same Gaussians with other colours, seen from a slightly shifted camera
+    sc2 = make_scene(N, W, H, seed=seed + 50, profile="synthetic")
+    raw2 = dict(raw, rgb=torch.logit(sc2.rgb.clamp(0.02, 0.98)))
+    pose2 = pose.clone()
+    pose2[4] += 0.03
+    with torch.no_grad():
+        img, dmap, _, _ = FR.render(raw2, pose2, sc.intr, W, H, 0.0)
+    gt_image = img.permute(1, 2, 0).contiguous()
+    gt_depth = (dmap.permute(1, 2, 0) * 1.1 + 0.05).contiguous()
+    return sc, raw, pose, gt_image, gt_depth
+
+
+def ref_config(cfg: fit.FitConfig) -> FR.FitRefConfig:
+    return FR.FitRefConfig(iterations=cfg.iterations, lr=cfg.lr, lr_camera=cfg.lr_camera, lambda_rgb=cfg.lambda_rgb,
+                           use_ssim=cfg.use_ssim, lambda_depth=cfg.lambda_depth, lambda_var=cfg.lambda_var,
+                           lambda_scale=cfg.lambda_scale, camera_only=cfg.camera_only, freeze_rgb=cfg.freeze_rgb,
+                           background=cfg.background)
+
+
+def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=48, seed=0, pixel_mask=None,
+                  still_mask=None, capacity=None):
+    """Returns (loop, fitter, raw0, pose0) after `n_iters` checked iterations."""
+    sc, raw, pose, gt_image, gt_depth = make_problem(N, W, H, seed)
+    use_depth = cfg.lambda_depth > 0
+    rcfg = ref_config(cfg)
+    dev = torch.device(device)
+    fitter = fit.FrameFitter({k: v.to(dev) for k, v in raw.items()}, sc.intr.to(dev), pose.to(dev), W, H)
+    loop = loop_cls(fitter, gt_image.to(dev), gt_depth.to(dev) if use_depth else None, cfg,
+                    pixel_mask=None if pixel_mask is None else pixel_mask.to(dev),
+                    still_mask=None if still_mask is None else still_mask.to(dev), capacity=capacity or 40 * N, debug=True)
+    # shadow optimiser: torch.optim.Adam fed with the KERNEL's gradients
+    shadow = {k: raw[k].clone().requires_grad_(True) for k in ATTRS}
+    sh_pose = pose.clone().requires_grad_(True)
+    sh_ab = torch.tensor([1.0, 0.0], requires_grad=True)
+    opt = torch.optim.Adam([{"params": list(shadow.values()), "lr": rcfg.lr}, {"params": [sh_pose], "lr": rcfg.lr_camera},
+                            {"params": [sh_ab], "lr": rcfg.lr}])
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.1, total_iters=rcfg.iterations)
+    for it in range(n_iters):
+        # oracle forward + autograd at the kernel's current parameters
+        cur = {k: fitter.attrs[k].data.cpu().clone().requires_grad_(True) for k in ATTRS}
+        cur_pose = fitter.pose.data.cpu().clone().requires_grad_(True)
+        cur_ab = torch.cat([fitter.depth_a.data.cpu(), fitter.depth_b.data.cpu()]).clone().requires_grad_(True)
+        loss, parts = FR.iteration_loss(cur, cur_pose, cur_ab, sc.intr, gt_image, gt_depth if use_depth else None,
+                                        pixel_mask, W, H, rcfg)
+        loss.backward()
+        assert torch.allclose(loop.camera().cpu()[:12].reshape(3, 4), FR.pose_to_extr(cur_pose.detach()), atol=2e-6)
+        loop.run(1)
+        h = loop.loss_history()[it].cpu()
+        assert abs(float(h[0]) - float(parts["total"])) <= 2e-4 * max(1.0, abs(float(parts["total"]))), (it, h, parts)
+        assert abs(float(h[1]) - float(parts["mse"])) <= 2e-4 * float(parts["mse"]) + 1e-7
+        if rcfg.use_ssim:
+            assert abs(float(h[2]) - float(parts["ssim"])) <= 2e-4
+        if use_depth:
+            assert abs(float(h[3]) - float(parts["depth"])) <= 5e-4 * float(parts["depth"]) + 1e-7
+        if rcfg.lambda_var:
+            assert abs(float(h[4]) - float(parts["var"])) <= 1e-5 * float(parts["var"]) + 1e-9
+        if rcfg.lambda_scale:
+            assert abs(float(h[5]) - float(parts["scale"])) <= 1e-5 * float(parts["scale"]) + 1e-9
+        st = loop.status().cpu()
+        assert int(st[0]) == it + 1 and 0 < int(st[1]) <= loop.capacity
+        # gradients
+        kg = loop.dbg_grads.cpu().clone()
+        col = 0
+        for k in ATTRS:
+            og = cur[k].grad if cur[k].grad is not None else torch.zeros_like(cur[k])
+            assert_close(kg[:, col:col + WIDTH[k]], og.reshape(-1, WIDTH[k]), 1e-3, f"iter {it} grad {k}", outlier_frac=2e-3,
+                         outlier_rel=5e-2)
+            col += WIDTH[k]
+        d_pose = loop.d_pose().cpu().clone()
+        assert_close(d_pose, cur_pose.grad, 2e-3, f"iter {it} d_pose")
+        # the kernel's update == torch Adam fed with the kernel's gradients and the reference's masks
+        col = 0
+        for k in ATTRS:
+            g = kg[:, col:col + WIDTH[k]].reshape(shadow[k].shape).clone()
+            col += WIDTH[k]
+            if rcfg.camera_only or (k == "rgb" and rcfg.freeze_rgb):
+                g.zero_()
+            if k == "xyz" and still_mask is not None:
+                g[: still_mask.shape[0]][still_mask] = 0.0
+            shadow[k].grad = g
+        sh_pose.grad = d_pose
+        sh_ab.grad = cur_ab.grad.clone() if use_depth else None
+        opt.step()
+        sched.step()
+        for k in ATTRS:
+            assert torch.allclose(fitter.attrs[k].data.cpu(), shadow[k].detach(), rtol=1e-5, atol=2e-6), \
+                f"iter {it} Adam update of {k}"
+        assert torch.allclose(fitter.pose.data.cpu(), sh_pose.detach(), rtol=1e-5, atol=2e-6), f"iter {it} pose update"
+        ab = torch.cat([fitter.depth_a.data.cpu(), fitter.depth_b.data.cpu()])
+        assert torch.allclose(ab, sh_ab.detach(), rtol=1e-4, atol=2e-5), f"iter {it} depth_a / depth_b"
+    return loop, fitter, raw, pose
+
+
+def case_list():
+    """(name, FitConfig, kwargs) shared by the CPU-emulated and the GPU run."""
+    C = fit.FitConfig
+    g = torch.Generator().manual_seed(9)
+    N, W, H = 350, 64, 48
+    pixel_mask = torch.rand(H, W, generator=g) > 0.3
+    still = torch.rand(N - 50, generator=g) > 0.5
+    return [
+        ("mse_depth", C(iterations=10, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, native=True), dict(n_iters=4)),
+        ("mse_only_bg", C(iterations=5, lr=1e-2, lambda_depth=0.0, background=0.3, native=True), dict(n_iters=2, seed=2)),
+        ("ssim", C(iterations=5, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, use_ssim=True, native=True),
+         dict(n_iters=2, W=70, H=37, seed=3)),
+        ("regularisers", C(iterations=5, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, lambda_var=0.7, lambda_scale=0.4,
+                           native=True), dict(n_iters=2, seed=4)),
+        ("camera_only", C(iterations=6, lr=4e-3, lr_camera=2e-3, lambda_depth=0.1, camera_only=True, native=True),
+         dict(n_iters=3, seed=5)),
+        ("masks", C(iterations=6, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, freeze_rgb=True, use_ssim=True, native=True),
+         dict(n_iters=2, N=N, W=W, H=H, seed=6, pixel_mask=pixel_mask, still_mask=still)),
+    ]
+
+
+def post_checks(name, loop, fitter, raw0, pose0, kwargs):
+    cur = {k: fitter.attrs[k].data.cpu() for k in ATTRS}
+    if name == "mse_depth":
+        h = loop.loss_history().cpu()
+        assert float(h[-1, 0]) < float(h[0, 0]), "the loss goes down"
+    if name == "camera_only":
+        assert all(torch.equal(cur[k], raw0[k]) for k in ATTRS)
+        assert not torch.equal(fitter.pose.data.cpu(), pose0)
+    if name == "masks":
+        still = kwargs["still_mask"]
+        n = still.shape[0]
+        assert torch.equal(cur["rgb"], raw0["rgb"])
+        assert torch.equal(cur["xyz"][:n][still], raw0["xyz"][:n][still])
+        assert not torch.equal(cur["xyz"][:n][~still], raw0["xyz"][:n][~still])

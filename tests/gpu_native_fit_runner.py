@@ -1,0 +1,64 @@
+"""Runs the native-fit GPU checks in a process of its own and prints one JSON object {case: "ok" | message}.
+
+tests/test_zz_native_fit_gpu.py launches this file: a CUDA fault in a kernel that has not yet run on
+hardware would otherwise poison the CUDA context of the whole pytest process."""
+import json
+import os
+import sys
+import traceback
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import torch  # noqa: E402
+
+import fit_check  # noqa: E402
+from gflow_b200 import fit  # noqa: E402
+from gflow_b200.synthetic import make_scene  # noqa: E402
+
+
+def native_vs_operator_path():
+    """FrameFitter.train through both execution modes from the same start: same loss curve to a few percent
+    (the two paths round differently and Adam's first steps are sign-like, so this is a trajectory check;
+    per-iteration parity is what fit_check.run_and_check asserts)."""
+    dev = torch.device("cuda:0")
+    sc, raw, pose, gt_image, gt_depth = fit_check.make_problem(N=6000, W=320, H=200, seed=11)
+    out = {}
+    for native in (False, True):
+        f = fit.FrameFitter({k: v.to(dev) for k, v in raw.items()}, sc.intr.to(dev), pose.to(dev), 320, 200)
+        cfg = fit.FitConfig(iterations=40, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, use_ssim=True, native=native,
+                            check_every=16)
+        res = f.train(gt_image.to(dev), gt_depth.to(dev), cfg)
+        out[native] = res
+        assert len(res.losses) == 40 and all(v == v for v in res.losses)
+    a, b = out[False].losses, out[True].losses
+    assert abs(a[0] - b[0]) <= 1e-3 * abs(a[0]), (a[0], b[0])
+    assert b[-1] < 0.9 * b[0], "native loop reduces the loss"
+    assert abs(a[-1] - b[-1]) <= 0.05 * abs(a[-1]), (a[-1], b[-1])
+
+
+def main():
+    results = {}
+    cases = fit_check.case_list()
+    from gflow_b200.fit import NativeFitLoop
+
+    for name, cfg, kwargs in cases:
+        try:
+            loop, fitter, raw0, pose0 = fit_check.run_and_check(NativeFitLoop, "cuda:0", cfg, **kwargs)
+            fit_check.post_checks(name, loop, fitter, raw0, pose0, kwargs)
+            torch.cuda.synchronize()
+            results[name] = "ok"
+        except Exception:  # noqa: BLE001
+            results[name] = traceback.format_exc()[-1500:]
+    try:
+        native_vs_operator_path()
+        torch.cuda.synchronize()
+        results["native_vs_operator_path"] = "ok"
+    except Exception:  # noqa: BLE001
+        results["native_vs_operator_path"] = traceback.format_exc()[-1500:]
+    print("RESULT " + json.dumps(results), flush=True)
+
+
+if __name__ == "__main__":
+    main()

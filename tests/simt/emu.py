@@ -152,71 +152,25 @@ def fused_pipeline(sc, Gimg, feature=None, capacity=None):
                            extr=d_cam[:12].reshape(3, 4).clone(), intr=d_cam[12:].clone()))
 
 
-class NativeFit:
-    """Drives gfb_fit_init / gfb_fit_iterate of the emulated library on host tensors (what
-    gflow_b200/fit.py does with device tensors)."""
 
-    def __init__(self, raw, pose, intr, gt_image, gt_depth, W, H, cfg, capacity, pixel_mask=None, still_mask=None,
-                 debug=True):
-        from gflow_b200.capi import FitLayout, FitProblem
+def fit_loop_class():
+    """gflow_b200.fit.NativeFitLoop (the product's host driver of csrc/fit.cu) re-pointed at the emulated
+    kernel library and host tensors, so its chunking / overflow / workspace logic runs in the CPU suite."""
+    import contextlib
 
-        self.L = load()
-        N = raw["xyz"].shape[0]
-        self.N, self.W, self.H, self.cap, self.iters = N, W, H, int(capacity), int(cfg["iterations"])
-        self.raw = {k: v.detach().clone().contiguous() for k, v in raw.items()}
-        self.pose = pose.detach().clone().contiguous()
-        self.depth_ab = torch.tensor([1.0, 0.0])
-        self.intr = intr.contiguous()
-        self.gt_image = gt_image.contiguous()
-        self.gt_depth = None if gt_depth is None else gt_depth.contiguous()
-        self.pixel_mask = None if pixel_mask is None else pixel_mask.to(torch.uint8).contiguous()
-        self.still_mask = None if still_mask is None else still_mask.to(torch.uint8).contiguous()
-        self.dbg_grads = f32(N, 14) if debug else None
-        self.dbg_act = f32(N, 14) if debug else None
-        lay = FitLayout()
-        ok(self.L.gfb_fit_get_layout(N, W, H, self.cap, self.iters, ctypes.addressof(lay)), "layout")
-        self.lay = lay
-        self.ws = torch.full((lay.total,), 0x77, dtype=torch.uint8)
-        pr = FitProblem()
-        for k in ("xyz", "scale", "rotate", "opacity", "rgb"):
-            setattr(pr, k, p(self.raw[k]))
-        pr.pose, pr.depth_ab, pr.intr = p(self.pose), p(self.depth_ab), p(self.intr)
-        pr.gt_image, pr.gt_depth = p(self.gt_image), p(self.gt_depth)
-        pr.pixel_mask, pr.still_mask = p(self.pixel_mask), p(self.still_mask)
-        pr.dbg_grads, pr.dbg_act = p(self.dbg_grads), p(self.dbg_act)
-        pr.N, pr.W, pr.H = N, W, H
-        pr.n_still = 0 if self.still_mask is None else self.still_mask.numel()
-        pr.total_iters = self.iters
-        pr.camera_only, pr.freeze_rgb = int(cfg.get("camera_only", False)), int(cfg.get("freeze_rgb", False))
-        pr.use_ssim = int(cfg.get("use_ssim", False))
-        pr.bg, pr.nearest, pr.extent = float(cfg.get("background", 0.0)), 0.2, 1.3
-        pr.lr, pr.lr_camera = float(cfg["lr"]), float(cfg.get("lr_camera", 0.0))
-        pr.lambda_rgb, pr.lambda_depth = float(cfg.get("lambda_rgb", 1.0)), float(cfg.get("lambda_depth", 0.0))
-        pr.lambda_var, pr.lambda_scale = float(cfg.get("lambda_var", 0.0)), float(cfg.get("lambda_scale", 0.0))
-        pr.beta1, pr.beta2, pr.eps = 0.9, 0.999, 1e-8
-        pr.depth_den_min = float(cfg.get("depth_den_min", 1e-6))
-        self.pr = pr
-        ok(self.L.gfb_fit_init(ctypes.addressof(pr), p(self.ws), self.cap, self.iters, None), "fit init")
-        self.done = 0
+    from gflow_b200.fit import NativeFitLoop
 
-    def iterate(self, n=1):
-        ok(self.L.gfb_fit_iterate(ctypes.addressof(self.pr), p(self.ws), self.cap, self.iters, self.done, n, None),
-           "fit iterate")
-        self.done += n
+    class EmulatedFitLoop(NativeFitLoop):
+        def _require_device(self, dev):
+            assert dev.type == "cpu", "the emulated loop runs on host tensors"
 
-    def view(self, off, count, dtype=torch.float32):
-        return self.ws[off:off + count * 4].view(dtype)
+        def _library(self):
+            return load()
 
-    @property
-    def status(self):
-        return self.view(self.lay.status, 16, torch.int32)
+        def _stream(self):
+            return 0
 
-    @property
-    def d_pose(self):
-        return self.view(self.lay.status + 32, 7)
+        def _device_guard(self):
+            return contextlib.nullcontext()
 
-    def loss_hist(self):
-        return self.view(self.lay.loss_hist, self.iters * 8).reshape(self.iters, 8)
-
-    def cam(self):
-        return self.view(self.lay.cam, 16)
+    return EmulatedFitLoop

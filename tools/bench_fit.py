@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 3 / 4: the 300-iteration per-frame Adam loop, single GPU or frame-sharded.
 
-  python tools/bench_fit.py [--iters 300] [--frames 1] [--fused]
+  python tools/bench_fit.py [--iters 300] [--frames 1] [--fused | --native] [--ssim]
   torchrun --nproc-per-node N tools/bench_fit.py --frames 48      (config 4, frame-sharded)
 
 Prints one JSON line: frames x iterations per second (max wall time over ranks, including the
@@ -27,6 +27,8 @@ ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--points", type=int, default=60000)
 ap.add_argument("--fused", action="store_true")
 ap.add_argument("--no-depth", action="store_true")
+ap.add_argument("--native", action="store_true", help="whole iteration in csrc/fit.cu (no autograd / torch.optim)")
+ap.add_argument("--ssim", action="store_true", help="loss_rgb = mse + (1 - SSIM) as in gflow/trainer.py:459-462")
 args = ap.parse_args()
 world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
 torch.cuda.set_device(local)
@@ -63,11 +65,12 @@ class Targets:
 
 
 cfg = fit.FitConfig(iterations=args.iters, lr=4e-3, lr_camera=1e-3, lambda_depth=0.0 if args.no_depth else 0.1,
-                    fused=args.fused)
+                    fused=args.fused, native=args.native, use_ssim=args.ssim)
 targets = Targets()
 # warm-up (allocator, K hints, NCCL)
 fit.FrameFitter({k: v.to(dev) for k, v in raw.items()}, sc.intr.to(dev), fit.extr_to_pose(sc.extr).to(dev), W, H).train(
-    *[t for t in targets(0)[:2]], fit.FitConfig(iterations=5, lambda_depth=cfg.lambda_depth, fused=args.fused))
+    *[t for t in targets(0)[:2]], fit.FitConfig(iterations=5, lambda_depth=cfg.lambda_depth, fused=args.fused, native=args.native,
+                                        use_ssim=args.ssim))
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
@@ -83,7 +86,7 @@ if rank == 0:
     first = results[min(results)]
     print(json.dumps({"metric": "per-frame Adam loop, frames x iterations / s", "value": args.frames * args.iters / dt,
                       "unit": "iters/s", "n_gpus": world, "frames": args.frames, "iterations": args.iters,
-                      "points": args.points, "resolution": [W, H], "seconds": dt, "fused": args.fused,
+                      "points": args.points, "resolution": [W, H], "seconds": dt, "fused": args.fused, "native": args.native, "ssim": args.ssim,
                       "depth_loss": not args.no_depth, "loss_first": first.losses[0], "loss_last": first.losses[-1],
                       "frames_per_rank": [len(frames.shard_frames(args.frames, world, r)) for r in range(world)]}))
 if world > 1:
