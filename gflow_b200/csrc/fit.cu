@@ -42,7 +42,8 @@ using namespace gfbm;
 
 enum { ST_ITER = 0, ST_K_LAST = 1, ST_K_MAX = 2, ST_WORDS = 16 };
 // loss accumulators (sums; fit_finish turns them into means)
-enum { LA_SQ = 0, LA_DEPTH = 1, LA_DA = 2, LA_DB = 3, LA_SSIM = 4, LA_VAR = 5, LA_SCALE = 6, LA_NSCALE = 7, LA_WORDS = 8 };
+enum { LA_SQ = 0, LA_DEPTH = 1, LA_DA = 2, LA_DB = 3, LA_SSIM = 4, LA_VAR = 5, LA_SCALE = 6, LA_NSCALE = 7, LA_STILL = 8,
+       LA_FLOW = 9, LA_WORDS = 12 };
 enum { HIST_WORDS = 8 };
 
 // per-launch Adam constants, computed on the host in double: step = lr * LinearLR factor / (1 - beta1^t)
@@ -95,6 +96,22 @@ __device__ __forceinline__ void extr_grad_to_pose(const float* pose, const float
     dp[6] = d[11];
 }
 
+// per-Gaussian terms of trainer.py:490-530 that do not go through the image
+struct FitRegs {
+    float lambda_var, lambda_scale;
+    const float* still_ref;     // loss_still = mean_sel |xyz - still_ref|
+    const uint8_t* still_sel;
+    int n_still_ref;
+    float w_still;              // lambda_still / still_count
+    const float* flow_target;   // loss_flow = mean_sel,2 (uv - flow_target)^2
+    const uint8_t* flow_sel;
+    int n_flow;
+    float w_flow;               // lambda_flow / (2 flow_count)
+    __device__ __forceinline__ bool any() const {
+        return lambda_var != 0.0f || lambda_scale != 0.0f || w_still != 0.0f || w_flow != 0.0f;
+    }
+};
+
 // ------------------------------------------------------------------ init
 __global__ void fit_init_kernel(const float* __restrict__ pose, const float* __restrict__ intr, float* __restrict__ cam,
                                 int32_t* __restrict__ status, float* __restrict__ loss_acc) {
@@ -113,8 +130,8 @@ fit_preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ s
                       float nearest, float extent, int C, float2* __restrict__ uv, float* __restrict__ depth,
                       float* __restrict__ conic, int32_t* __restrict__ radius, ushort4* __restrict__ rect,
                       float* __restrict__ op_act, float* __restrict__ feat, int32_t* __restrict__ counts,
-                      int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R, float lambda_var,
-                      float lambda_scale, float* __restrict__ loss_acc, float* __restrict__ dbg_act) {
+                      int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R, FitRegs rg,
+                      float* __restrict__ loss_acc, float* __restrict__ dbg_act) {
     __shared__ float s_cam[16];
     __shared__ int s_scan[34];
     __shared__ int s_buf[kScanSmemInts];
@@ -124,7 +141,9 @@ fit_preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ s
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
     const int i = blockIdx.x * kThreads + threadIdx.x;
     ushort4 rc = make_ushort4(0, 0, 0, 0);
-    float reg[3] = {0.0f, 0.0f, 0.0f};  // sum of std(scale), sum of |scale| / depth, count of the latter
+    const float lambda_var = rg.lambda_var, lambda_scale = rg.lambda_scale;
+    // sums of: std(scale), |scale| / depth, count of the latter, |xyz - still_ref|, (uv - flow_target)^2
+    float reg[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     if (i < N) {
         const float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
         const float s[3] = {fabsf(scale_raw[3 * i]), fabsf(scale_raw[3 * i + 1]), fabsf(scale_raw[3 * i + 2])};
@@ -174,13 +193,23 @@ fit_preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ s
             reg[1] = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) / zc;  // trainer.py:495-501
             reg[2] = 1.0f;
         }
+        if (rg.w_still != 0.0f && i < rg.n_still_ref && rg.still_sel[i]) {  // trainer.py:504-508
+            const float d0 = p[0] - rg.still_ref[3 * i], d1 = p[1] - rg.still_ref[3 * i + 1], d2 = p[2] - rg.still_ref[3 * i + 2];
+            reg[3] = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+        }
+        if (rg.w_flow != 0.0f && i < rg.n_flow && rg.flow_sel[i]) {  // trainer.py:510-530 (uv of a culled point is 0)
+            const float d0 = (ok ? u : 0.0f) - rg.flow_target[2 * i], d1 = (ok ? v : 0.0f) - rg.flow_target[2 * i + 1];
+            reg[4] = d0 * d0 + d1 * d1;
+        }
         if (dbg_act) {
             float* a = dbg_act + (size_t)i * 14;
             a[0] = p[0]; a[1] = p[1]; a[2] = p[2]; a[3] = s[0]; a[4] = s[1]; a[5] = s[2];
             a[6] = q.x; a[7] = q.y; a[8] = q.z; a[9] = q.w; a[10] = o; a[11] = cr; a[12] = cg; a[13] = cb;
         }
     }
-    if (lambda_var != 0.0f || lambda_scale != 0.0f) block_reduce_atomic<3>(reg, loss_acc + LA_VAR);
+    static_assert(LA_SCALE == LA_VAR + 1 && LA_NSCALE == LA_VAR + 2 && LA_STILL == LA_VAR + 3 && LA_FLOW == LA_VAR + 4,
+                  "the five per-Gaussian sums are reduced as one block");
+    if (rg.any()) block_reduce_atomic<5>(reg, loss_acc + LA_VAR);
     {   // per-tile counting, 32 (Gaussian, tile) pairs per warp round (as in pipeline.cu preprocess)
         const WarpTileWalk walk(rc.x, rc.y, rc.z - rc.x, rc.w - rc.y, gx, threadIdx.x & 31);
         for (int base = 0; base < walk.total; base += 32) {
@@ -387,7 +416,7 @@ __global__ void __launch_bounds__(kThreads)
 fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_raw, float4* __restrict__ rot_raw,
                              float* __restrict__ op_raw, float* __restrict__ rgb_raw, const float* __restrict__ cam,
                              int N, int W, int H, float nearest, float extent, int C,
-                             const float4* __restrict__ grad_pack, FitMasks mk, float lambda_var, float lambda_scale,
+                             const float4* __restrict__ grad_pack, FitMasks mk, FitRegs rg,
                              const float* __restrict__ loss_acc, float* __restrict__ adam_m,
                              float* __restrict__ adam_v, AdamStep a, float* __restrict__ d_cam,
                              float* __restrict__ dbg_grads) {
@@ -397,6 +426,7 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
     const float* in = s_cam + 12;
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
     const int i = blockIdx.x * kThreads + threadIdx.x;
+    const float lambda_var = rg.lambda_var, lambda_scale = rg.lambda_scale;
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
@@ -437,7 +467,21 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
 #pragma unroll
                 for (int k = 0; k < 3; ++k) ds[k] += ds2[k];
             }
-            project_bwd_one(in, e, p[0], p[1], p[2], xc, yc, zc, g0.x, g0.y, gd, dp, acc);
+            float gu = g0.x, gv = g0.y;
+            if (rg.w_flow != 0.0f && i < rg.n_flow && rg.flow_sel[i]) {  // d/duv of w_flow |uv - target|^2
+                gu += 2.0f * rg.w_flow * (u - rg.flow_target[2 * i]);
+                gv += 2.0f * rg.w_flow * (v - rg.flow_target[2 * i + 1]);
+            }
+            project_bwd_one(in, e, p[0], p[1], p[2], xc, yc, zc, gu, gv, gd, dp, acc);
+        }
+        if (rg.w_still != 0.0f && i < rg.n_still_ref && rg.still_sel[i]) {
+            const float d0 = p[0] - rg.still_ref[3 * i], d1 = p[1] - rg.still_ref[3 * i + 1], d2 = p[2] - rg.still_ref[3 * i + 2];
+            const float nrm = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+            if (nrm > 0.0f) {  // torch.norm's backward is 0 at 0
+                dp[0] += rg.w_still * d0 / nrm;
+                dp[1] += rg.w_still * d1 / nrm;
+                dp[2] += rg.w_still * d2 / nrm;
+            }
         }
         if (lambda_var != 0.0f) {
             const float mu = (s[0] + s[1] + s[2]) / 3.0f;
@@ -526,7 +570,8 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
 // ------------------------------------------------------------------ end of iteration (one warp)
 struct FitFinish {
     int iter, use_depth, use_ssim, N, P;
-    float lambda_rgb, lambda_depth, lambda_var, lambda_scale;
+    float lambda_rgb, lambda_depth, lambda_var, lambda_scale, lambda_still, lambda_flow;
+    float inv_still_count, inv_flow_count2;  // 1 / still_count, 1 / (2 flow_count); 0 when the term is off
 };
 
 __global__ void fit_finish_kernel(float* __restrict__ pose, float* __restrict__ depth_ab, const float* __restrict__ intr,
@@ -541,9 +586,10 @@ __global__ void fit_finish_kernel(float* __restrict__ pose, float* __restrict__ 
     const float lv = f.lambda_var != 0.0f ? loss_acc[LA_VAR] / (float)f.N : 0.0f;
     const float ls = (f.lambda_scale != 0.0f && loss_acc[LA_NSCALE] > 0.0f) ? loss_acc[LA_SCALE] / loss_acc[LA_NSCALE] : 0.0f;
     float* h = loss_hist + (size_t)f.iter * HIST_WORDS;
+    const float lst = loss_acc[LA_STILL] * f.inv_still_count, lfl = loss_acc[LA_FLOW] * f.inv_flow_count2;
     h[0] = f.lambda_rgb * (mse + (f.use_ssim ? 1.0f - ssim : 0.0f)) + f.lambda_depth * ld + f.lambda_var * lv +
-           f.lambda_scale * ls;
-    h[1] = mse; h[2] = ssim; h[3] = ld; h[4] = lv; h[5] = ls; h[6] = 0.0f; h[7] = 0.0f;
+           f.lambda_scale * ls + f.lambda_still * lst + f.lambda_flow * lfl;
+    h[1] = mse; h[2] = ssim; h[3] = ld; h[4] = lv; h[5] = ls; h[6] = lst; h[7] = lfl;
     float dp[7];
     extr_grad_to_pose(pose, d_cam, dp);
     float* diag = reinterpret_cast<float*>(status + 8);  // status[8..14]: dL/d(pose) of this iteration (float bits)
@@ -616,7 +662,8 @@ bool make_layout(int N, int W, int H, int64_t capacity, int max_iters, Layout& L
 bool problem_ok(const gfb_fit_problem* p) {
     return p && p->xyz && p->scale && p->rotate && p->opacity && p->rgb && p->pose && p->depth_ab && p->intr &&
            p->gt_image && p->N > 0 && p->W > 0 && p->H > 0 && p->total_iters > 0 && p->n_still >= 0 &&
-           (p->n_still == 0 || p->still_mask) && p->n_still <= p->N;
+           (p->n_still == 0 || p->still_mask) && p->n_still <= p->N && p->n_still_ref >= 0 && p->n_still_ref <= p->N &&
+           p->n_flow >= 0 && p->n_flow <= p->N && p->still_count >= 0 && p->flow_count >= 0;
 }
 
 AdamStep adam_step(const gfb_fit_problem* p, double lr, int iter) {
@@ -702,6 +749,13 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
     float* ssim_grad = (float*)(ws + L.ssim_grad);
     const float w_rgb = p->lambda_rgb / (3.0f * (float)P), w_depth = p->lambda_depth / (float)P;
     const FitMasks mk{p->still_mask, p->n_still, p->camera_only, p->freeze_rgb};
+    const bool use_still = p->lambda_still != 0.0f && p->still_ref && p->still_sel && p->still_count > 0;
+    const bool use_flow = p->lambda_flow != 0.0f && p->flow_target && p->flow_sel && p->flow_count > 0;
+    const float inv_still = use_still ? 1.0f / (float)p->still_count : 0.0f;
+    const float inv_flow2 = use_flow ? 1.0f / (2.0f * (float)p->flow_count) : 0.0f;
+    const FitRegs rg{p->lambda_var,  p->lambda_scale, p->still_ref,   p->still_sel, use_still ? p->n_still_ref : 0,
+                     p->lambda_still * inv_still, p->flow_target, p->flow_sel,  use_flow ? p->n_flow : 0,
+                     p->lambda_flow * inv_flow2};
     const int nblk = gfb_div_up(N, kThreads);
     int rc;
     for (int it = first_iter; it < first_iter + n_iters; ++it) {
@@ -709,7 +763,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
         fit_preprocess_kernel<<<nblk, kThreads, 0, st>>>(
             p->xyz, p->scale, reinterpret_cast<const float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest,
             p->extent, C, reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect), op_act,
-            feat, counts, offsets, ctrl, T, R, p->lambda_var, p->lambda_scale, loss_acc, p->dbg_act);
+            feat, counts, offsets, ctrl, T, R, rg, loss_acc, p->dbg_act);
         GFB_CHECK_LAUNCH();
         rc = gfb_internal_scatter_sort_pack(rect, depth, N, W, H, counts, capacity, keys, tile_range, uv, conic, op_act,
                                             feat, C, ids, geom, fstream, stream, false);
@@ -734,11 +788,12 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
         if (rc) return rc;
         fit_geometry_bwd_adam_kernel<<<nblk, kThreads, 0, st>>>(
             p->xyz, p->scale, reinterpret_cast<float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest, p->extent,
-            C, reinterpret_cast<const float4*>(grad_ws), mk, p->lambda_var, p->lambda_scale, loss_acc, adam_m, adam_v,
+            C, reinterpret_cast<const float4*>(grad_ws), mk, rg, loss_acc, adam_m, adam_v,
             adam_step(p, p->lr, it), d_cam, p->dbg_grads);
         GFB_CHECK_LAUNCH();
         const FitFinish ff{it, use_depth ? 1 : 0, p->use_ssim, N, P, p->lambda_rgb, p->lambda_depth, p->lambda_var,
-                           p->lambda_scale};
+                           p->lambda_scale, use_still ? p->lambda_still : 0.0f, use_flow ? p->lambda_flow : 0.0f,
+                           inv_still, inv_flow2};
         fit_finish_kernel<<<1, 32, 0, st>>>(p->pose, p->depth_ab, p->intr, cam, d_cam, loss_acc, loss_hist, status, ctrl,
                                             adam_m + 14 * (size_t)N, adam_v + 14 * (size_t)N,
                                             adam_step(p, p->lr_camera, it), adam_step(p, p->lr, it), ff);

@@ -104,6 +104,8 @@ class FitConfig:
     use_ssim: bool = False  # loss_rgb = mse + (1 - SSIM) as in trainer.py:459-462 (False: mse only)
     lambda_var: float = 0.0  # trainer.py:490-492
     lambda_scale: float = 0.0  # trainer.py:495-501
+    lambda_still: float = 0.0  # trainer.py:504-508 (needs `prev`)
+    lambda_flow: float = 0.0  # trainer.py:510-530 (needs `prev`)
     freeze_rgb: bool = False  # frames >= 1: rgb gradient zeroed (trainer.py:537-540)
     check_every: int = 50  # native path: iterations enqueued between two looks at the intersection count
 
@@ -127,6 +129,33 @@ def ssim(img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
     s1, s2, s12 = conv(img1 * img1) - mu1_sq, conv(img2 * img2) - mu2_sq, conv(img1 * img2) - mu1_mu2
     C1, C2 = 0.01 ** 2, 0.03 ** 2
     return (((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean()
+
+
+@dataclass
+class PrevFrame:
+    """What GFlow carries from the previous frame into the still / flow terms (trainer.py:619-625) plus this
+    frame's flow prior: last_xyz (n,3), last_still_mask (n,) bool, last_uv (n,2), gt_flow (H,W,2)."""
+    last_xyz: Optional[torch.Tensor] = None
+    last_still_mask: Optional[torch.Tensor] = None
+    last_uv: Optional[torch.Tensor] = None
+    gt_flow: Optional[torch.Tensor] = None
+
+    def flow_and_mask(self, W: int, H: int, still_mask: Optional[torch.Tensor], camera_only: bool) -> torch.Tensor:
+        """trainer.py:511-517."""
+        uv = self.last_uv
+        m = (uv[:, 0] > 0) & (uv[:, 0] < W - 1) & (uv[:, 1] > 0) & (uv[:, 1] < H - 1)
+        if still_mask is not None:
+            n = still_mask.shape[0]
+            m[:n] = (still_mask if camera_only else ~still_mask) & m[:n]
+        return m
+
+    def flow_target(self, and_mask: torch.Tensor) -> torch.Tensor:
+        """(n,2): where each selected Gaussian's centre should land, last_uv + gt_flow[last_uv] (rows outside
+        and_mask are unused)."""
+        uv = self.last_uv
+        x = uv[:, 0].long().clamp(0, self.gt_flow.shape[1] - 1)
+        y = uv[:, 1].long().clamp(0, self.gt_flow.shape[0] - 1)
+        return (uv + self.gt_flow[y, x]).contiguous()
 
 
 @dataclass
@@ -176,12 +205,18 @@ class FrameFitter:
         return img, dmap, uv
 
     def train(self, gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor], cfg: FitConfig,
-              pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None) -> FitResult:
+              pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None,
+              prev: Optional[PrevFrame] = None) -> FitResult:
         """gt_image (H,W,3) in [0,1]; gt_depth (H,W,1) or None; pixel_mask (H,W) bool (True = pixel counts,
-        trainer.py:452-455); still_mask (n,) bool (True = xyz frozen, trainer.py:542-546).
-        Returns per-iteration losses and the final render."""
+        trainer.py:452-455); still_mask (n,) bool (True = xyz frozen, trainer.py:542-546); prev: previous-frame
+        state for the still / flow terms.  Returns per-iteration losses and the final render."""
         if cfg.native:
-            return self._train_native(gt_image, gt_depth, cfg, pixel_mask, still_mask)
+            return self._train_native(gt_image, gt_depth, cfg, pixel_mask, still_mask, prev)
+        use_still = bool(cfg.lambda_still) and prev is not None and prev.last_still_mask is not None
+        use_flow = bool(cfg.lambda_flow) and prev is not None and prev.gt_flow is not None
+        if use_flow:
+            and_mask = prev.flow_and_mask(self.W, self.H, still_mask, cfg.camera_only)
+            flow_target = prev.flow_target(and_mask)
         groups = [{"params": list(self.attrs.values()), "lr": cfg.lr},
                   {"params": [self.pose], "lr": cfg.lr_camera},
                   {"params": [self.depth_a, self.depth_b], "lr": cfg.lr}]
@@ -194,7 +229,7 @@ class FrameFitter:
         gt = gt_image if pm is None else gt_image * pm[..., None]
         for _ in range(cfg.iterations):
             uv = depth = None
-            if cfg.fused and not use_depth and not cfg.lambda_scale:
+            if cfg.fused and not use_depth and not cfg.lambda_scale and not use_flow:
                 img = ops.rasterization(self.get_attribute("xyz"), self.get_attribute("scale"),
                                         self.get_attribute("rotate"), self.get_attribute("opacity"),
                                         self.get_attribute("rgb"), self.intr, self.get_extr(), self.W, self.H,
@@ -222,6 +257,14 @@ class FrameFitter:
                 within = (uv[:, 0] > 0) & (uv[:, 0] < self.W - 1) & (uv[:, 1] > 0) & (uv[:, 1] < self.H - 1)
                 ls = torch.norm(self.get_attribute("scale")[within], dim=1) * (1.0 / depth[within]).squeeze(-1)
                 loss = loss + cfg.lambda_scale * ls.mean()
+            if use_still:
+                m = prev.last_still_mask
+                n = m.shape[0]
+                loss = loss + cfg.lambda_still * torch.norm(self.get_attribute("xyz")[:n][m] - prev.last_xyz[:n][m],
+                                                            dim=1).mean()
+            if use_flow:
+                n = flow_target.shape[0]
+                loss = loss + cfg.lambda_flow * torch.mean((uv[:n][and_mask] - flow_target[and_mask]) ** 2)
             opt.zero_grad(set_to_none=True)
             loss.backward()
             if cfg.freeze_rgb and self.attrs["rgb"].grad is not None:  # trainer.py:537-540
@@ -241,8 +284,8 @@ class FrameFitter:
             res.pose = self.pose.detach().clone()
         return res
 
-    def _train_native(self, gt_image, gt_depth, cfg: FitConfig, pixel_mask, still_mask) -> FitResult:
-        loop = NativeFitLoop(self, gt_image, gt_depth, cfg, pixel_mask=pixel_mask, still_mask=still_mask)
+    def _train_native(self, gt_image, gt_depth, cfg: FitConfig, pixel_mask, still_mask, prev=None) -> FitResult:
+        loop = NativeFitLoop(self, gt_image, gt_depth, cfg, pixel_mask=pixel_mask, still_mask=still_mask, prev=prev)
         loop.run(cfg.iterations)
         res = FitResult()
         res.losses = [float(v) for v in loop.loss_history()[:, 0].cpu()]
@@ -261,7 +304,7 @@ class NativeFitLoop:
 
     def __init__(self, fitter: "FrameFitter", gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor], cfg: FitConfig,
                  pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None,
-                 capacity: Optional[int] = None, debug: bool = False):
+                 capacity: Optional[int] = None, debug: bool = False, prev: Optional[PrevFrame] = None):
         dev = fitter.attrs["xyz"].device
         self._require_device(dev)
         self.lib = self._library()
@@ -285,6 +328,20 @@ class NativeFitLoop:
         self.still_mask = None if still_mask is None else still_mask.to(dev).to(torch.uint8).contiguous()
         if self.still_mask is not None and self.still_mask.numel() > self.N:
             raise RuntimeError("gflow_b200: still_mask is longer than the number of Gaussians")
+        # still / flow terms: everything that is constant over the call is folded on the host once
+        self.still_ref = self.still_sel = self.flow_target = self.flow_sel = None
+        self.still_count = self.flow_count = 0
+        if cfg.lambda_still and prev is not None and prev.last_still_mask is not None:
+            self.still_ref = prev.last_xyz.detach().to(**f32).contiguous()
+            self.still_sel = prev.last_still_mask.to(dev).to(torch.uint8).contiguous()
+            self.still_count = int(self.still_sel.sum())
+        if cfg.lambda_flow and prev is not None and prev.gt_flow is not None:
+            pv = PrevFrame(last_uv=prev.last_uv.detach().to(**f32), gt_flow=prev.gt_flow.detach().to(**f32))
+            and_mask = pv.flow_and_mask(self.W, self.H, None if still_mask is None else still_mask.to(dev).bool(),
+                                        cfg.camera_only)
+            self.flow_target = pv.flow_target(and_mask)
+            self.flow_sel = and_mask.to(torch.uint8).contiguous()
+            self.flow_count = int(self.flow_sel.sum())
         # depth_a / depth_b live in one 2-float tensor on the device side; copied back after every run()
         self.depth_ab = torch.cat([fitter.depth_a.data.reshape(1), fitter.depth_b.data.reshape(1)]).contiguous()
         self.dbg_grads = torch.zeros(self.N, 14, **f32) if debug else None
@@ -330,8 +387,14 @@ class NativeFitLoop:
         pr.gt_image, pr.gt_depth = self.gt_image.data_ptr(), ops._ptr(self.gt_depth)
         pr.pixel_mask, pr.still_mask = ops._ptr(self.pixel_mask), ops._ptr(self.still_mask)
         pr.dbg_grads, pr.dbg_act = ops._ptr(self.dbg_grads), ops._ptr(self.dbg_act)
+        pr.still_ref, pr.still_sel = ops._ptr(self.still_ref), ops._ptr(self.still_sel)
+        pr.flow_target, pr.flow_sel = ops._ptr(self.flow_target), ops._ptr(self.flow_sel)
         pr.N, pr.W, pr.H = self.N, self.W, self.H
         pr.n_still = 0 if self.still_mask is None else self.still_mask.numel()
+        pr.n_still_ref = 0 if self.still_sel is None else min(self.N, self.still_sel.numel())
+        pr.n_flow = 0 if self.flow_sel is None else min(self.N, self.flow_sel.numel())
+        pr.still_count, pr.flow_count = self.still_count, self.flow_count
+        pr.lambda_still, pr.lambda_flow = float(c.lambda_still), float(c.lambda_flow)
         pr.total_iters = self.iters
         pr.camera_only, pr.freeze_rgb, pr.use_ssim = int(c.camera_only), int(c.freeze_rgb), int(c.use_ssim)
         pr.bg, pr.nearest, pr.extent = float(c.background), 0.2, 1.3
@@ -381,7 +444,7 @@ class NativeFitLoop:
         self.fitter.depth_b.data.copy_(self.depth_ab[1:2])
 
     def loss_history(self) -> torch.Tensor:
-        """(iterations done, 8): total, mse, ssim, depth, var, scale, -, - per iteration."""
+        """(iterations done, 8): total, mse, ssim, depth, var, scale, still, flow per iteration."""
         return self._view(self.lay.loss_hist, self.iters * 8).reshape(self.iters, 8)[: self.done]
 
     def status(self) -> torch.Tensor:

@@ -183,15 +183,21 @@ typedef struct gfb_fit_problem {
     const float *gt_depth;       /* (H,W,1) or NULL (no depth term) */
     const uint8_t *pixel_mask;   /* (H,W) 1 = pixel takes part in the losses, or NULL (trainer.py:452-455,484) */
     const uint8_t *still_mask;   /* (n_still) 1 = xyz gradient zeroed (trainer.py:542-546), or NULL */
+    const float *still_ref;      /* (n_still_ref,3) last frame's xyz, or NULL: loss_still (trainer.py:504-508) */
+    const uint8_t *still_sel;    /* (n_still_ref) 1 = Gaussian takes part in loss_still (last_still_mask) */
+    const float *flow_target;    /* (n_flow,2) last_uv + gt_flow[last_uv], or NULL: loss_flow (trainer.py:510-530) */
+    const uint8_t *flow_sel;     /* (n_flow) 1 = Gaussian takes part in loss_flow (and_mask) */
     float *dbg_grads;            /* NULL, or (N,14) raw-attribute gradients of the last iteration before masking */
     float *dbg_act;              /* NULL, or (N,14) activated attributes of the last iteration */
     int32_t N, W, H, n_still;
+    int32_t n_still_ref, still_count; /* still_count = number of 1s in still_sel (the mean's denominator) */
+    int32_t n_flow, flow_count;       /* flow_count = number of 1s in flow_sel */
     int32_t total_iters;         /* LinearLR horizon (`iterations` of trainer.train) */
     int32_t camera_only;         /* attribute gradients zeroed, pose still optimised (trainer.py:548-551) */
     int32_t freeze_rgb;          /* rgb gradient zeroed (frames >= 1, trainer.py:537-540) */
     int32_t use_ssim;            /* loss_rgb = mse + (1 - SSIM) as in trainer.py:459-462; 0 = mse only */
     float bg, nearest, extent;
-    float lr, lr_camera, lambda_rgb, lambda_depth, lambda_var, lambda_scale;
+    float lr, lr_camera, lambda_rgb, lambda_depth, lambda_var, lambda_scale, lambda_still, lambda_flow;
     float beta1, beta2, eps;     /* Adam; torch defaults 0.9, 0.999, 1e-8 */
     float depth_den_min;         /* lower clamp of the depth-loss denominator (0 = reference behaviour) */
 } gfb_fit_problem;
@@ -200,7 +206,7 @@ typedef struct gfb_fit_problem {
 typedef struct gfb_fit_layout {
     size_t status;      /* int32[16]: [0] iterations done, [1] K of the last iteration, [2] max K seen,
                            [8..14] float bits of dL/d(pose) of the last iteration (diagnostics) */
-    size_t loss_hist;   /* float[max_iters][8]: total, mse, ssim, depth, var, scale, -, - per iteration */
+    size_t loss_hist;   /* float[max_iters][8]: total, mse, ssim, depth, var, scale, still, flow per iteration */
     size_t cam;         /* float[16]: extr (3x4) + intr used by the NEXT iteration */
     size_t adam_m;      /* float[14 N + 12]: xyz | scale | rotate | opacity | rgb | pose(7) | depth_ab(2) */
     size_t adam_v;

@@ -16,6 +16,7 @@ and is followed line by line:
                          zero padding 5, C1 = 0.01^2, C2 = 0.03^2, mean over all elements)
   loss_depth             /root/reference/gflow/trainer.py:476-488: ((a D + b) - D_gt)^2 / ((a D + b) + D_gt), mean
   loss_var / loss_scale  /root/reference/gflow/trainer.py:490-503
+  loss_still / loss_flow /root/reference/gflow/trainer.py:504-530
   gradient masks         /root/reference/gflow/trainer.py:535-551
   Adam + LinearLR        /root/reference/gflow/trainer.py:123-153,383-384,554-555 (torch.optim.Adam defaults,
                          LinearLR 1.0 -> 0.1 over `iterations`, stepped after the optimiser)
@@ -92,6 +93,8 @@ class FitRefConfig:
     lambda_depth: float = 0.1
     lambda_var: float = 0.0
     lambda_scale: float = 0.0
+    lambda_still: float = 0.0
+    lambda_flow: float = 0.0
     camera_only: bool = False
     freeze_rgb: bool = False         # frames >= 1: rgb gradient zeroed (trainer.py:537-540)
     background: float = 0.0
@@ -112,8 +115,21 @@ def render(raw: Dict[str, torch.Tensor], pose, intr, W, H, bg, want_depth=True):
     return img, dmap, uv, depth
 
 
-def iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg: FitRefConfig):
-    """One forward of the iteration; returns (loss, dict of parts)."""
+def flow_and_mask(last_uv, W, H, still_mask=None, camera_only=False):
+    """trainer.py:511-517: Gaussians whose previous-frame centre lies inside the image, restricted to the
+    still (camera-only stage) or moving (full stage) set."""
+    m = (last_uv[:, 0] > 0) & (last_uv[:, 0] < W - 1) & (last_uv[:, 1] > 0) & (last_uv[:, 1] < H - 1)
+    if still_mask is not None:
+        n = still_mask.shape[0]
+        m[:n] = (still_mask if camera_only else ~still_mask) & m[:n]
+    return m.detach()
+
+
+def iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg: FitRefConfig, prev=None):
+    """One forward of the iteration; returns (loss, dict of parts).
+
+    prev (optional, frames >= 1): dict(last_xyz (n,3), last_still_mask (n,), last_uv (n,2), gt_flow (H,W,2),
+    and_mask (n,)) -- the state trainer.py:619-625 saves after the previous frame, and flow_and_mask()."""
     use_depth = gt_depth is not None and cfg.lambda_depth > 0
     img, dmap, uv, depth = render(raw, pose, intr, W, H, cfg.background, want_depth=use_depth)
     parts = {}
@@ -147,13 +163,26 @@ def iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W,
         ls = ls.mean()
         parts["scale"] = ls.detach()
         loss = loss + cfg.lambda_scale * ls
+    if cfg.lambda_still and prev is not None and "last_still_mask" in prev:  # trainer.py:504-508
+        m = prev["last_still_mask"]
+        n = m.shape[0]
+        lst = torch.norm(raw["xyz"][:n][m] - prev["last_xyz"][:n][m], dim=1).mean()
+        parts["still"] = lst.detach()
+        loss = loss + cfg.lambda_still * lst
+    if cfg.lambda_flow and prev is not None and "gt_flow" in prev:  # trainer.py:510-530
+        am, last_uv = prev["and_mask"], prev["last_uv"]
+        pred = uv[: last_uv.shape[0]][am] - last_uv[am]
+        gtf = prev["gt_flow"][last_uv[am][:, 1].long(), last_uv[am][:, 0].long()]
+        lfl = F.mse_loss(pred, gtf)
+        parts["flow"] = lfl.detach()
+        loss = loss + cfg.lambda_flow * lfl
     parts["total"] = loss.detach()
     return loss, parts
 
 
 def fit_loop(raw0: Dict[str, torch.Tensor], pose0, intr, gt_image, gt_depth, W, H, cfg: FitRefConfig,
              pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None, n_iters=None,
-             record=None):
+             record=None, prev=None):
     """Runs `n_iters` (default cfg.iterations) iterations; returns (raw, pose, depth_ab, history).
 
     history[i] = dict(parts of iteration i, grads = raw gradients BEFORE masking, params after the step).
@@ -167,7 +196,7 @@ def fit_loop(raw0: Dict[str, torch.Tensor], pose0, intr, gt_image, gt_depth, W, 
     sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.1, total_iters=cfg.iterations)
     history = []
     for it in range(cfg.iterations if n_iters is None else n_iters):
-        loss, parts = iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg)
+        loss, parts = iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg, prev)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in raw.items()}

@@ -46,21 +46,42 @@ def make_problem(N=350, W=64, H=48, seed=0):
 def ref_config(cfg: fit.FitConfig) -> FR.FitRefConfig:
     return FR.FitRefConfig(iterations=cfg.iterations, lr=cfg.lr, lr_camera=cfg.lr_camera, lambda_rgb=cfg.lambda_rgb,
                            use_ssim=cfg.use_ssim, lambda_depth=cfg.lambda_depth, lambda_var=cfg.lambda_var,
-                           lambda_scale=cfg.lambda_scale, camera_only=cfg.camera_only, freeze_rgb=cfg.freeze_rgb,
-                           background=cfg.background)
+                           lambda_scale=cfg.lambda_scale, lambda_still=cfg.lambda_still, lambda_flow=cfg.lambda_flow,
+                           camera_only=cfg.camera_only, freeze_rgb=cfg.freeze_rgb, background=cfg.background)
+
+
+def make_prev(sc, raw, pose, W, H, seed):
+    """Previous-frame state for the still / flow terms: the same Gaussians slightly displaced, their projected
+    centres, a random still mask and a smooth random flow field."""
+    g = torch.Generator().manual_seed(seed + 77)
+    N = raw["xyz"].shape[0]
+    n = N - 30  # the previous frame had fewer Gaussians (densification appends)
+    last_xyz = raw["xyz"][:n] + 0.01 * torch.randn(n, 3, generator=g)
+    with torch.no_grad():
+        _, _, uv, _ = FR.render(dict(raw, xyz=torch.cat([last_xyz, raw["xyz"][n:]])), pose, sc.intr, W, H, 0.0, want_depth=False)
+    gt_flow = 2.0 * torch.randn(H, W, 2, generator=g)
+    return dict(last_xyz=last_xyz, last_still_mask=torch.rand(n, generator=g) > 0.4, last_uv=uv[:n].contiguous(),
+                gt_flow=gt_flow)
 
 
 def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=48, seed=0, pixel_mask=None,
-                  still_mask=None, capacity=None):
+                  still_mask=None, capacity=None, with_prev=False):
     """Returns (loop, fitter, raw0, pose0) after `n_iters` checked iterations."""
     sc, raw, pose, gt_image, gt_depth = make_problem(N, W, H, seed)
+    prev_ref = prev_dev = None
+    if with_prev:
+        prev_ref = make_prev(sc, raw, pose, W, H, seed)
+        prev_ref["and_mask"] = FR.flow_and_mask(prev_ref["last_uv"], W, H, still_mask, cfg.camera_only)
+        assert int(prev_ref["and_mask"].sum()) > 20 and int(prev_ref["last_still_mask"].sum()) > 20
+        prev_dev = fit.PrevFrame(**{k: prev_ref[k].to(device) for k in ("last_xyz", "last_still_mask", "last_uv", "gt_flow")})
     use_depth = cfg.lambda_depth > 0
     rcfg = ref_config(cfg)
     dev = torch.device(device)
     fitter = fit.FrameFitter({k: v.to(dev) for k, v in raw.items()}, sc.intr.to(dev), pose.to(dev), W, H)
     loop = loop_cls(fitter, gt_image.to(dev), gt_depth.to(dev) if use_depth else None, cfg,
                     pixel_mask=None if pixel_mask is None else pixel_mask.to(dev),
-                    still_mask=None if still_mask is None else still_mask.to(dev), capacity=capacity or 40 * N, debug=True)
+                    still_mask=None if still_mask is None else still_mask.to(dev), capacity=capacity or 40 * N, debug=True,
+                    prev=prev_dev)
     # shadow optimiser: torch.optim.Adam fed with the KERNEL's gradients
     shadow = {k: raw[k].clone().requires_grad_(True) for k in ATTRS}
     sh_pose = pose.clone().requires_grad_(True)
@@ -74,7 +95,7 @@ def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=
         cur_pose = fitter.pose.data.cpu().clone().requires_grad_(True)
         cur_ab = torch.cat([fitter.depth_a.data.cpu(), fitter.depth_b.data.cpu()]).clone().requires_grad_(True)
         loss, parts = FR.iteration_loss(cur, cur_pose, cur_ab, sc.intr, gt_image, gt_depth if use_depth else None,
-                                        pixel_mask, W, H, rcfg)
+                                        pixel_mask, W, H, rcfg, prev_ref)
         loss.backward()
         assert torch.allclose(loop.camera().cpu()[:12].reshape(3, 4), FR.pose_to_extr(cur_pose.detach()), atol=2e-6)
         loop.run(1)
@@ -89,6 +110,10 @@ def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=
             assert abs(float(h[4]) - float(parts["var"])) <= 1e-5 * float(parts["var"]) + 1e-9
         if rcfg.lambda_scale:
             assert abs(float(h[5]) - float(parts["scale"])) <= 1e-5 * float(parts["scale"]) + 1e-9
+        if rcfg.lambda_still and with_prev:
+            assert abs(float(h[6]) - float(parts["still"])) <= 1e-5 * float(parts["still"]) + 1e-9
+        if rcfg.lambda_flow and with_prev:
+            assert abs(float(h[7]) - float(parts["flow"])) <= 1e-4 * float(parts["flow"]) + 1e-9
         st = loop.status().cpu()
         assert int(st[0]) == it + 1 and 0 < int(st[1]) <= loop.capacity
         # gradients
@@ -138,6 +163,8 @@ def case_list():
          dict(n_iters=2, W=70, H=37, seed=3)),
         ("regularisers", C(iterations=5, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, lambda_var=0.7, lambda_scale=0.4,
                            native=True), dict(n_iters=2, seed=4)),
+        ("still_flow", C(iterations=5, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, lambda_still=0.5, lambda_flow=0.02,
+                         native=True), dict(n_iters=2, seed=7, with_prev=True, still_mask=torch.rand(300, generator=g) > 0.5)),
         ("camera_only", C(iterations=6, lr=4e-3, lr_camera=2e-3, lambda_depth=0.1, camera_only=True, native=True),
          dict(n_iters=3, seed=5)),
         ("masks", C(iterations=6, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, freeze_rgb=True, use_ssim=True, native=True),
