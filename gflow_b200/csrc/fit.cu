@@ -24,6 +24,8 @@
 // All of it is HBM / latency bound per-Gaussian and per-pixel streaming around the two blend kernels;
 // nothing here is GEMM shaped.  Compiled with -fmad=false like geometry.cu / pipeline.cu so the
 // per-Gaussian geometry is bit-identical to the operator path for the same activated inputs.
+#include <cstdlib>
+
 #include "sort_network.cuh"
 #include "splat_math.cuh"
 
@@ -137,6 +139,7 @@ fit_preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ s
     __shared__ int s_buf[kScanSmemInts];
     static_assert(kThreads == kScanThreads, "the last CTA of fit_preprocess runs the scan");
     __shared__ bool s_last;
+    gfb_pdl_launch_dependents();  // with GFB_FIT_PDL=1 scatter may take SM slots while the counting tail drains
     load_camera(s_cam, cam + 12, cam);
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
     const int i = blockIdx.x * kThreads + threadIdx.x;
@@ -421,7 +424,8 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
                              float* __restrict__ adam_v, AdamStep a, float* __restrict__ d_cam,
                              float* __restrict__ dbg_grads) {
     __shared__ float s_cam[16];
-    load_camera(s_cam, cam + 12, cam);
+    load_camera(s_cam, cam + 12, cam);  // written by the previous iteration's fit_finish: long complete
+    gfb_pdl_wait();                     // grad_pack comes from blend_bwd (no-op without the PDL attribute)
     const float* e = s_cam;
     const float* in = s_cam + 12;
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
@@ -680,6 +684,16 @@ AdamStep adam_step(const gfb_fit_problem* p, double lr, int iter) {
     return a;
 }
 
+// Programmatic dependent launch between the iteration's kernels, the way pipeline.cu chains its own
+// (preprocess -> scatter -> sort -> blend, blend_bwd -> geometry_bwd).  Off until measured on hardware.
+bool fit_pdl() {
+    static const bool on = [] {
+        const char* e = getenv("GFB_FIT_PDL");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+
 }  // namespace
 
 extern "C" {
@@ -757,6 +771,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                      p->lambda_still * inv_still, p->flow_target, p->flow_sel,  use_flow ? p->n_flow : 0,
                      p->lambda_flow * inv_flow2};
     const int nblk = gfb_div_up(N, kThreads);
+    const bool pdl = fit_pdl();
     int rc;
     for (int it = first_iter; it < first_iter + n_iters; ++it) {
         GFB_TRY(cudaMemsetAsync(counts, 0, ((size_t)T * R + GFB_CTRL_WORDS) * sizeof(int32_t), st));
@@ -766,10 +781,10 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
             feat, counts, offsets, ctrl, T, R, rg, loss_acc, p->dbg_act);
         GFB_CHECK_LAUNCH();
         rc = gfb_internal_scatter_sort_pack(rect, depth, N, W, H, counts, capacity, keys, tile_range, uv, conic, op_act,
-                                            feat, C, ids, geom, fstream, stream, false);
+                                            feat, C, ids, geom, fstream, stream, pdl);
         if (rc) return rc;
         rc = gfb_internal_blend_fwd(geom, fstream, capacity, tile_range, C, 0, C, p->bg, W, H, out, final_T, n_contrib,
-                                    stream, false);
+                                    stream, pdl);
         if (rc) return rc;
         if (p->use_ssim) {
             ssim_stats_kernel<<<dim3(gx, gy, 3), 256, 0, st>>>(out, p->gt_image, p->pixel_mask, W, H, ssim_maps, loss_acc);
@@ -786,10 +801,10 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
         rc = gfb_alpha_blending_bwd(geom, fstream, capacity, ids, tile_range, C, 0, C, p->bg, W, H, final_T, n_contrib,
                                     g_out, grad_ws, stream);
         if (rc) return rc;
-        fit_geometry_bwd_adam_kernel<<<nblk, kThreads, 0, st>>>(
-            p->xyz, p->scale, reinterpret_cast<float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest, p->extent,
-            C, reinterpret_cast<const float4*>(grad_ws), mk, rg, loss_acc, adam_m, adam_v,
-            adam_step(p, p->lr, it), d_cam, p->dbg_grads);
+        GFB_TRY(gfb_launch_pdl(fit_geometry_bwd_adam_kernel, dim3(nblk), dim3(kThreads), st, pdl, p->xyz, p->scale,
+                               reinterpret_cast<float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest, p->extent,
+                               C, reinterpret_cast<const float4*>(grad_ws), mk, rg, loss_acc, adam_m, adam_v,
+                               adam_step(p, p->lr, it), d_cam, p->dbg_grads));
         GFB_CHECK_LAUNCH();
         const FitFinish ff{it, use_depth ? 1 : 0, p->use_ssim, N, P, p->lambda_rgb, p->lambda_depth, p->lambda_var,
                            p->lambda_scale, use_still ? p->lambda_still : 0.0f, use_flow ? p->lambda_flow : 0.0f,
