@@ -77,3 +77,23 @@ def gather_frames(image: torch.Tensor, pose: torch.Tensor, dst: int = 0) -> Opti
         return None
     n_img = image.numel()
     return [(b[:n_img].reshape(image.shape), b[n_img:].reshape(pose.shape)) for b in bufs]
+
+
+def broadcast_frame_state(state, src: int = 0, device=None):
+    """Broadcast a whole checkpoint.FrameState (attributes + camera + still mask + last_uv) from `src` as ONE
+    packed float32 buffer (checkpoint.to_wire); other ranks pass None.  Two messages: length, then payload."""
+    from . import checkpoint as _ckpt
+
+    rank = dist.get_rank()
+    if device is None:
+        device = state.attributes["xyz"].device if state is not None else torch.device("cpu")
+    n = torch.zeros(1, dtype=torch.int64, device=device)
+    buf = None
+    if rank == src:
+        buf = _ckpt.to_wire(state).to(device)
+        n[0] = buf.numel()
+    dist.broadcast(n, src=src)
+    if rank != src:
+        buf = torch.empty(int(n.item()), dtype=torch.float32, device=device)
+    dist.broadcast(buf, src=src)
+    return _ckpt.from_wire(buf)

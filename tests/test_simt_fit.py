@@ -67,3 +67,23 @@ def test_bad_arguments():
     assert L.gfb_fit_get_layout(10, 64, 48, 100, 10, None) == -1
     assert L.gfb_fit_get_layout(10, 64, 48, 100, 10, ctypes.addressof(lay)) == 0 and lay.total > 0
     assert L.gfb_fit_iterate(None, None, 100, 10, 0, 1, None) == -1
+
+
+def test_train_native_with_every_term_through_the_emulated_loop(monkeypatch):
+    """FrameFitter.train(native=True) end to end on the host side (what tools/fit_small.py does on the GPU):
+    every loss term on, masks, previous-frame state, chunked run with a workspace that has to grow."""
+    monkeypatch.setattr(fit, "NativeFitLoop", emu.fit_loop_class())
+    monkeypatch.setattr(fit.FrameFitter, "render", lambda self, bg=0.0, want_depth=True, with_depth=False: (None, None, None))
+    N, W, H = 351, 64, 48  # odd N
+    sc, raw, pose, gt_image, gt_depth = fit_check.make_problem(N, W, H, seed=8)
+    g = torch.Generator().manual_seed(1)
+    prev_ref = fit_check.make_prev(sc, raw, pose, W, H, 8)
+    prev = fit.PrevFrame(**prev_ref)
+    f = fit.FrameFitter(raw, sc.intr, pose, W, H)
+    cfg = fit.FitConfig(iterations=5, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, use_ssim=True, lambda_var=0.1,
+                        lambda_scale=0.1, lambda_still=0.1, lambda_flow=0.01, native=True, check_every=2)
+    res = f.train(gt_image, gt_depth, cfg, pixel_mask=torch.rand(H, W, generator=g) > 0.1,
+                  still_mask=torch.rand(N - 30, generator=g) > 0.5, prev=prev)
+    assert len(res.losses) == 5 and all(v == v and v > 0 for v in res.losses)
+    assert res.losses[-1] < res.losses[0]
+    assert not torch.equal(f.depth_a.data, torch.ones(1)), "depth_a is copied back from the device-side pair"
