@@ -22,8 +22,8 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC]
 # geometry.cu must not fuse multiply-adds: its float32 results are bit-compared with the oracle
 PER_FILE_FLAGS = {"geometry.cu": ["-fmad=false"], "binning.cu": ["-fmad=false"], "pipeline.cu": ["-fmad=false"],
-                  "fit.cu": ["-fmad=false"]}
-SOURCES = ["capi.cu", "geometry.cu", "binning.cu", "blend.cu", "pipeline.cu", "fit.cu"]
+                  "fit.cu": ["-fmad=false"], "densify.cu": ["-fmad=false"]}
+SOURCES = ["capi.cu", "geometry.cu", "binning.cu", "blend.cu", "pipeline.cu", "fit.cu", "densify.cu"]
 
 
 def _nvcc() -> str:

@@ -48,6 +48,10 @@ SIGNATURES = {
     "gfb_fit_get_layout": (I, [I, I, I, L, I, P]),
     "gfb_fit_init": (I, [P, P, L, I, P]),
     "gfb_fit_iterate": (I, [P, P, L, I, I, I, P]),
+    "gfb_rgb_error_map": (I, [P, P, P, I, I, P, P]),
+    "gfb_densify_workspace_bytes": (c_size_t, [I, I]),
+    "gfb_densify_prepare": (I, [P, P, I, I, F, P, P]),
+    "gfb_densify_sample": (I, [P, P, P, P, P, I, I, I, I, ctypes.c_uint64, P, P, P, P, P, P, P]),
 }
 
 
@@ -57,7 +61,8 @@ class FitProblem(ctypes.Structure):
                                  "gt_depth", "pixel_mask", "still_mask", "still_ref", "still_sel", "flow_target",
                                  "flow_sel", "dbg_grads", "dbg_act")] + \
                [(n, ctypes.c_int32) for n in ("N", "W", "H", "n_still", "n_still_ref", "still_count", "n_flow",
-                                              "flow_count", "total_iters", "camera_only", "freeze_rgb", "use_ssim")] + \
+                                              "flow_count", "total_iters", "camera_only", "freeze_rgb", "use_ssim", "adam_t0",
+                                              "constant_lr", "freeze_camera")] + \
                [(n, F) for n in ("bg", "nearest", "extent", "lr", "lr_camera", "lambda_rgb", "lambda_depth",
                                  "lambda_var", "lambda_scale", "lambda_still", "lambda_flow", "beta1", "beta2", "eps",
                                  "depth_den_min")]

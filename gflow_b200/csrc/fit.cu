@@ -573,7 +573,7 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
 
 // ------------------------------------------------------------------ end of iteration (one warp)
 struct FitFinish {
-    int iter, use_depth, use_ssim, N, P;
+    int iter, use_depth, use_ssim, N, P, freeze_camera;
     float lambda_rgb, lambda_depth, lambda_var, lambda_scale, lambda_still, lambda_flow;
     float inv_still_count, inv_flow_count2;  // 1 / still_count, 1 / (2 flow_count); 0 when the term is off
 };
@@ -599,9 +599,11 @@ __global__ void fit_finish_kernel(float* __restrict__ pose, float* __restrict__ 
     float* diag = reinterpret_cast<float*>(status + 8);  // status[8..14]: dL/d(pose) of this iteration (float bits)
 #pragma unroll
     for (int k = 0; k < 7; ++k) diag[k] = dp[k];
+    if (!f.freeze_camera) {
 #pragma unroll
-    for (int k = 0; k < 7; ++k) adam_update(pose[k], m_tail[k], v_tail[k], dp[k], a_pose);
-    if (f.use_depth) {
+        for (int k = 0; k < 7; ++k) adam_update(pose[k], m_tail[k], v_tail[k], dp[k], a_pose);
+    }
+    if (f.use_depth && !f.freeze_camera) {
         adam_update(depth_ab[0], m_tail[7], v_tail[7], loss_acc[LA_DA], a_ab);
         adam_update(depth_ab[1], m_tail[8], v_tail[8], loss_acc[LA_DB], a_ab);
     }
@@ -667,13 +669,14 @@ bool problem_ok(const gfb_fit_problem* p) {
     return p && p->xyz && p->scale && p->rotate && p->opacity && p->rgb && p->pose && p->depth_ab && p->intr &&
            p->gt_image && p->N > 0 && p->W > 0 && p->H > 0 && p->total_iters > 0 && p->n_still >= 0 &&
            (p->n_still == 0 || p->still_mask) && p->n_still <= p->N && p->n_still_ref >= 0 && p->n_still_ref <= p->N &&
-           p->n_flow >= 0 && p->n_flow <= p->N && p->still_count >= 0 && p->flow_count >= 0;
+           p->n_flow >= 0 && p->n_flow <= p->N && p->still_count >= 0 && p->flow_count >= 0 && p->adam_t0 >= 0;
 }
 
 AdamStep adam_step(const gfb_fit_problem* p, double lr, int iter) {
     const int total = p->total_iters;
-    const double factor = 1.0 + (0.1 - 1.0) * (double)(iter < total ? iter : total) / (double)total;  // LinearLR 1 -> 0.1
-    const double t = (double)iter + 1.0;
+    const double factor =  // LinearLR 1 -> 0.1; constant after a densification re-created the optimiser
+        p->constant_lr ? 1.0 : 1.0 + (0.1 - 1.0) * (double)(iter < total ? iter : total) / (double)total;
+    const double t = (double)(iter - p->adam_t0) + 1.0;
     const double bc1 = 1.0 - pow((double)p->beta1, t), bc2 = 1.0 - pow((double)p->beta2, t);
     AdamStep a;
     a.step = (float)(lr * factor / bc1);
@@ -723,7 +726,8 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                     int n_iters, void* stream) {
     Layout L;
     if (!problem_ok(p) || !workspace || !make_layout(p->N, p->W, p->H, capacity, max_iters, L)) return GFB_E_BADARG;
-    if (first_iter < 0 || n_iters < 0 || first_iter + n_iters > max_iters || capacity <= 0) return GFB_E_BADARG;
+    if (first_iter < 0 || n_iters < 0 || first_iter + n_iters > max_iters || capacity <= 0 || first_iter < p->adam_t0)
+        return GFB_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     const int N = p->N, W = p->W, H = p->H;
@@ -806,7 +810,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                                C, reinterpret_cast<const float4*>(grad_ws), mk, rg, loss_acc, adam_m, adam_v,
                                adam_step(p, p->lr, it), d_cam, p->dbg_grads));
         GFB_CHECK_LAUNCH();
-        const FitFinish ff{it, use_depth ? 1 : 0, p->use_ssim, N, P, p->lambda_rgb, p->lambda_depth, p->lambda_var,
+        const FitFinish ff{it, use_depth ? 1 : 0, p->use_ssim, N, P, p->freeze_camera, p->lambda_rgb, p->lambda_depth, p->lambda_var,
                            p->lambda_scale, use_still ? p->lambda_still : 0.0f, use_flow ? p->lambda_flow : 0.0f,
                            inv_still, inv_flow2};
         fit_finish_kernel<<<1, 32, 0, st>>>(p->pose, p->depth_ab, p->intr, cam, d_cam, loss_acc, loss_hist, status, ctrl,

@@ -30,6 +30,7 @@ import math
 import torch
 
 from . import capi
+from . import densify as _densify
 from . import frames as _frames
 from . import ops
 
@@ -108,6 +109,13 @@ class FitConfig:
     lambda_flow: float = 0.0  # trainer.py:510-530 (needs `prev`)
     freeze_rgb: bool = False  # frames >= 1: rgb gradient zeroed (trainer.py:537-540)
     check_every: int = 50  # native path: iterations enqueued between two looks at the intersection count
+    # error-driven densification, trainer.py:566-571 ((iteration + 1) % interval == 0, at most `times` times)
+    densify_interval: int = 0
+    densify_times: int = 0
+    densify_err_thre: float = 1e-3
+    densify_err_percent: float = 0.1
+    num_points: Optional[int] = None  # the reference's self.num_points (configured count); default: initial N
+    densify_seed: int = 0
 
 
 _SSIM_WINDOW = None
@@ -227,7 +235,8 @@ class FrameFitter:
         loss_hist = []
         pm = None if pixel_mask is None else pixel_mask.to(gt_image.dtype)
         gt = gt_image if pm is None else gt_image * pm[..., None]
-        for _ in range(cfg.iterations):
+        self._num_points0 = cfg.num_points or int(self.attrs["xyz"].shape[0])
+        for it in range(cfg.iterations):
             uv = depth = None
             if cfg.fused and not use_depth and not cfg.lambda_scale and not use_flow:
                 img = ops.rasterization(self.get_attribute("xyz"), self.get_attribute("scale"),
@@ -278,15 +287,47 @@ class FrameFitter:
             opt.step()
             sched.step()
             loss_hist.append(loss.detach())
+            if self._densify_due(cfg, it):
+                # trainer.py:566-571 + 941-951: append Gaussians drawn from the error map, then a NEW Adam over
+                # the attributes only (initial lr, no scheduler; pose / depth_a / depth_b drop out)
+                if self._densify_operator_path(img.detach(), gt, gt_image, gt_depth, cfg, it):
+                    opt = torch.optim.Adam(list(self.attrs.values()), lr=cfg.lr)
         res.losses = [float(v) for v in torch.stack(loss_hist).cpu()] if loss_hist else []
         with torch.no_grad():
             res.image, _, res.uv = self.render(cfg.background, want_depth=False)
             res.pose = self.pose.detach().clone()
         return res
 
+    @staticmethod
+    def _densify_due(cfg: FitConfig, it: int) -> bool:
+        k = cfg.densify_interval
+        return bool(k) and not cfg.camera_only and (it + 1) % k == 0 and (it + 1) // k <= cfg.densify_times
+
+    def _densify_operator_path(self, img, gt_masked, gt_image, gt_depth, cfg: FitConfig, it: int) -> bool:
+        if gt_depth is None:
+            raise RuntimeError("gflow_b200: densification back-projects with the depth prior; gt_depth is required")
+        dens = _densify.Densifier(self.W, self.H, self.attrs["xyz"].device)
+        err = dens.rgb_error_map(img.contiguous(), gt_masked.contiguous())
+        new = dens.sample(err, gt_image, gt_depth, self.intr, self.get_extr().detach(), self._num_points0,
+                          cfg.densify_err_thre, cfg.densify_err_percent, seed=cfg.densify_seed + it)
+        if new is None:
+            return False
+        for k in ATTRS:
+            self.attrs[k] = torch.nn.Parameter(torch.cat([self.attrs[k].data, new[k]], dim=0))
+        return True
+
     def _train_native(self, gt_image, gt_depth, cfg: FitConfig, pixel_mask, still_mask, prev=None) -> FitResult:
         loop = NativeFitLoop(self, gt_image, gt_depth, cfg, pixel_mask=pixel_mask, still_mask=still_mask, prev=prev)
-        loop.run(cfg.iterations)
+        if cfg.densify_interval and not cfg.camera_only:
+            k, done = cfg.densify_interval, 0
+            while done < cfg.iterations:
+                nxt = min(cfg.iterations, (done // k + 1) * k)
+                loop.run(nxt - done)
+                done = nxt
+                if self._densify_due(cfg, done - 1):
+                    loop.densify(cfg.densify_err_thre, cfg.densify_err_percent, seed=cfg.densify_seed + done - 1)
+        else:
+            loop.run(cfg.iterations)
         res = FitResult()
         res.losses = [float(v) for v in loop.loss_history()[:, 0].cpu()]
         with torch.no_grad():
@@ -348,6 +389,9 @@ class NativeFitLoop:
         self.dbg_act = torch.zeros(self.N, 14, **f32) if debug else None
         self.iters = int(cfg.iterations)
         self.done = 0
+        self.num_points0 = int(cfg.num_points or self.N)
+        self.adam_t0, self.constant_lr, self.freeze_camera = 0, 0, 0  # change when a densification re-creates Adam
+        self._densifier = None
         self.capacity = int(capacity) if capacity is not None else 6 * self.N + 65536
         self.ws = None
         self._alloc(self.capacity)
@@ -397,6 +441,7 @@ class NativeFitLoop:
         pr.lambda_still, pr.lambda_flow = float(c.lambda_still), float(c.lambda_flow)
         pr.total_iters = self.iters
         pr.camera_only, pr.freeze_rgb, pr.use_ssim = int(c.camera_only), int(c.freeze_rgb), int(c.use_ssim)
+        pr.adam_t0, pr.constant_lr, pr.freeze_camera = self.adam_t0, self.constant_lr, self.freeze_camera
         pr.bg, pr.nearest, pr.extent = float(c.background), 0.2, 1.3
         pr.lr, pr.lr_camera = float(c.lr), float(c.lr_camera)
         pr.lambda_rgb, pr.lambda_depth = float(c.lambda_rgb), float(c.lambda_depth if self.use_depth else 0.0)
@@ -442,6 +487,49 @@ class NativeFitLoop:
                     self._alloc(int(1.5 * k_max) + 65536)
         self.fitter.depth_a.data.copy_(self.depth_ab[0:1])
         self.fitter.depth_b.data.copy_(self.depth_ab[1:2])
+
+    def _make_densifier(self):
+        return _densify.Densifier(self.W, self.H, self.dev)
+
+    def densify(self, error_threshold: float = 1e-3, percent: float = 0.1, mask: Optional[torch.Tensor] = None,
+                uniform_error: bool = False, seed: int = 0) -> int:
+        """densify_by_pixels (trainer.py:878-951) between two iterations, entirely on the device: error map of
+        the last iteration's render (or ones, with a mask: the occlusion densification of trainer.py:562-564) ->
+        weighted draw -> new Gaussians appended -> optimiser re-created the way the reference does it (Adam state
+        zeroed, constant lr, pose / depth_a / depth_b no longer updated).  Returns the number added."""
+        if self.gt_depth is None:
+            raise RuntimeError("gflow_b200: densification back-projects with the depth prior; gt_depth is required")
+        if self.done == 0 and not uniform_error:
+            raise RuntimeError("gflow_b200: no iteration has run yet, there is no error map to densify from")
+        if self._densifier is None:
+            self._densifier = self._make_densifier()
+        d, f = self._densifier, self.fitter
+        with self._device_guard():
+            if uniform_error:
+                err = torch.ones(self.H, self.W, dtype=torch.float32, device=self.dev)
+            else:
+                err = d.rgb_error_map(self.rendered(), self.gt_image, self.pixel_mask)
+            extr = self.camera()[:12].reshape(3, 4)  # camera after the last update = get_extr() at this point
+            new = d.sample(err, self.gt_image, self.gt_depth, f.intr, extr, self.num_points0, error_threshold, percent, mask=mask,
+                           seed=seed)
+            if new is None:
+                return 0
+            count = int(new["xyz"].shape[0])
+            self._last_densify_pixels = new["pixels"]
+            for k in ATTRS:
+                f.attrs[k] = torch.nn.Parameter(torch.cat([f.attrs[k].data, new[k]], dim=0))
+            head = self.ws[: self.lay.adam_m].clone()  # status | loss sums | camera | loss history: N independent
+            self.N += count
+            if self.dbg_grads is not None:  # per-Gaussian debug outputs grow with N
+                self.dbg_grads = torch.zeros(self.N, 14, dtype=torch.float32, device=self.dev)
+                self.dbg_act = torch.zeros(self.N, 14, dtype=torch.float32, device=self.dev)
+            self.adam_t0, self.constant_lr, self.freeze_camera = self.done, 1, 1
+            self.ws = None
+            self._alloc(self.capacity)
+            capi.check(self.lib.gfb_fit_init(ctypes.addressof(self.problem), self.ws.data_ptr(), self.capacity, self.iters,
+                                             self._stream()), "fit init after densify")
+            self.ws[: self.lay.adam_m].copy_(head)
+        return count
 
     def loss_history(self) -> torch.Tensor:
         """(iterations done, 8): total, mse, ssim, depth, var, scale, still, flow per iteration."""

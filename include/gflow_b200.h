@@ -196,6 +196,12 @@ typedef struct gfb_fit_problem {
     int32_t camera_only;         /* attribute gradients zeroed, pose still optimised (trainer.py:548-551) */
     int32_t freeze_rgb;          /* rgb gradient zeroed (frames >= 1, trainer.py:537-540) */
     int32_t use_ssim;            /* loss_rgb = mse + (1 - SSIM) as in trainer.py:459-462; 0 = mse only */
+    /* state of the optimiser after a densification: the reference re-creates Adam over the attributes only,
+     * with the initial lr and no scheduler (trainer.py:941-951), so from then on the Adam step count restarts
+     * at adam_t0, the lr stays constant and pose / depth_a / depth_b are no longer updated */
+    int32_t adam_t0;             /* iteration index at which the Adam state was last zeroed (0 initially) */
+    int32_t constant_lr;         /* 1 = LinearLR factor fixed at 1 */
+    int32_t freeze_camera;       /* 1 = pose and depth_a / depth_b not updated */
     float bg, nearest, extent;
     float lr, lr_camera, lambda_rgb, lambda_depth, lambda_var, lambda_scale, lambda_still, lambda_flow;
     float beta1, beta2, eps;     /* Adam; torch defaults 0.9, 0.999, 1e-8 */
@@ -229,6 +235,28 @@ int gfb_fit_init(const gfb_fit_problem *problem, void *workspace, int64_t capaci
  * iterations since the last check rendered truncated tiles and must be redone with a larger workspace. */
 int gfb_fit_iterate(const gfb_fit_problem *problem, void *workspace, int64_t capacity, int max_iters, int first_iter,
                     int n_iters, void *stream);
+
+/* ------------------------------------------------------------------ error-driven densification
+ * SimpleGaussian.densify_by_pixels, /root/reference/gflow/trainer.py:878-939, without the host round trip.
+ *   gfb_rgb_error_map   : loss_rgb_pixel of trainer.py:457 from the rendered (3,H,W) image and the target
+ *   gfb_densify_prepare : weights = (error + min positive error) * mask (mask given, or weights > threshold),
+ *                         block sums + their scan.  The workspace starts with int32 stats[8]:
+ *                         [1] = number of mask pixels (the caller derives densify_num = int(num_points *
+ *                         mask_ratio * percent) from it), [3] = float bits of the total weight.
+ *   gfb_densify_sample  : draws `count` pixels with replacement, proportional to the weights (counter-based
+ *                         generator, `seed`), and writes the new RAW attributes of trainer.py:908-933 for
+ *                         them: xyz = pix2world(pixel, gt_depth) (geometry.py:104-116), scale =
+ *                         gt_depth / (min sampled depth * num_points), rotate = (1,0,0,0),
+ *                         opacity = logit(0.99)/10, rgb = logit(target colour); sampled_pixels (count) int32. */
+int gfb_rgb_error_map(const float *rendered, const float *gt_image, const uint8_t *pixel_mask, int W, int H,
+                      float *error_map, void *stream);
+size_t gfb_densify_workspace_bytes(int W, int H);
+int gfb_densify_prepare(const float *error_map, const uint8_t *mask, int W, int H, float error_threshold,
+                        void *workspace, void *stream);
+int gfb_densify_sample(const void *workspace, const float *gt_image, const float *gt_depth, const float *intr,
+                       const float *extr, int W, int H, int count, int num_points, uint64_t seed, float *new_xyz,
+                       float *new_scale, float *new_rotate, float *new_opacity, float *new_rgb,
+                       int32_t *sampled_pixels, void *stream);
 
 #ifdef __cplusplus
 }

@@ -219,3 +219,46 @@ def fit_loop(raw0: Dict[str, torch.Tensor], pose0, intr, gt_image, gt_depth, W, 
         else:
             history.append(rec)
     return {k: v.detach() for k, v in raw.items()}, pose.detach(), depth_ab.detach(), history
+
+
+# --------------------------------------------------------------------------- densification
+def densify_weights(error_map, error_threshold=1e-3, mask=None):
+    """trainer.py:880-895 on numpy: returns (weights (H,W), mask (H,W) bool, mask_ratio)."""
+    import numpy as np
+
+    e = np.asarray(error_map, dtype=np.float32)
+    pos = e[e > 0]
+    e = e + (np.nanmin(pos) if pos.size else np.float32(0))
+    if mask is None:
+        m = (e > error_threshold).squeeze()
+    else:
+        m = np.asarray(mask).squeeze()
+    m = m > 0
+    w = e * m
+    return w, m, float(np.sum(m)) / m.size
+
+
+def densify_count(num_points, mask_ratio, percent):
+    """trainer.py:900."""
+    return int(num_points * mask_ratio * percent)
+
+
+def densify_attributes(sampled_pixels, gt_image, gt_depth, intr, extr, num_points, W):
+    """trainer.py:904-933 for an already drawn set of flat pixel indices: new raw attributes."""
+    idx = torch.as_tensor(sampled_pixels, dtype=torch.long)
+    ys, xs = idx // W, idx % W
+    xys = torch.stack([xs, ys], dim=1).float()
+    depths = gt_depth[ys, xs].reshape(-1, 1).float()
+    scales = torch.ones(idx.numel()) * (1.0 / num_points) * (depths / depths.min()).squeeze(-1)
+    rgbs = gt_image[ys, xs]
+    # geometry.py:104-116
+    rel = torch.cat((depths * (xys - intr[2:]) / intr[0], depths), dim=-1)
+    extr_h = torch.cat((extr, torch.tensor([[0.0, 0.0, 0.0, 1.0]])), dim=0)
+    c2w = torch.linalg.inv(extr_h)
+    xyz = rel @ c2w[:3, :3].T + c2w[:3, 3]
+    new_scale = torch.abs(scales.unsqueeze(1).repeat(1, 3))
+    rgbs = torch.clamp(rgbs.contiguous(), min=1e-15, max=1 - 1e-15)
+    new_rgb = torch.logit(rgbs)
+    new_rot = torch.tensor([1.0, 0.0, 0.0, 0.0]).repeat(idx.numel(), 1)
+    new_op = torch.logit(0.99 * torch.ones(idx.numel(), 1)) / 10.0
+    return dict(xyz=xyz, scale=new_scale, rotate=new_rot, opacity=new_op, rgb=new_rgb)

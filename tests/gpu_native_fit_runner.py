@@ -38,6 +38,22 @@ def native_vs_operator_path():
     assert abs(a[-1] - b[-1]) <= 0.05 * abs(a[-1]), (a[-1], b[-1])
 
 
+def densification_both_paths():
+    """trainer.py:566-571: (iteration + 1) % interval == 0 appends Gaussians drawn from the error map; both
+    execution modes grow the attribute tensors and keep optimising with finite losses."""
+    dev = torch.device("cuda:0")
+    sc, raw, pose, gt_image, gt_depth = fit_check.make_problem(N=3000, W=160, H=120, seed=21)
+    for native in (False, True):
+        f = fit.FrameFitter({k: v.to(dev) for k, v in raw.items()}, sc.intr.to(dev), pose.to(dev), 160, 120)
+        cfg = fit.FitConfig(iterations=13, lr=4e-3, lambda_depth=0.1, native=native, densify_interval=4, densify_times=2,
+                            densify_err_thre=1e-5, densify_err_percent=0.3, check_every=3)
+        res = f.train(gt_image.to(dev), gt_depth.to(dev), cfg)
+        n = f.attrs["xyz"].shape[0]
+        assert n > 3000 and all(f.attrs[k].shape[0] == n for k in fit.ATTRS), (native, n)
+        assert len(res.losses) == 13 and all(v == v for v in res.losses), (native, res.losses)
+        assert res.image.shape == (3, 120, 160)
+
+
 def main():
     results = {}
     cases = fit_check.case_list()
@@ -57,6 +73,12 @@ def main():
         results["native_vs_operator_path"] = "ok"
     except Exception:  # noqa: BLE001
         results["native_vs_operator_path"] = traceback.format_exc()[-1500:]
+    try:
+        densification_both_paths()
+        torch.cuda.synchronize()
+        results["densification_both_paths"] = "ok"
+    except Exception:  # noqa: BLE001
+        results["densification_both_paths"] = traceback.format_exc()[-1500:]
     print("RESULT " + json.dumps(results), flush=True)
 
 

@@ -173,4 +173,24 @@ def fit_loop_class():
         def _device_guard(self):
             return contextlib.nullcontext()
 
+        def _make_densifier(self):
+            return densifier_class()(self.W, self.H, self.dev)
+
     return EmulatedFitLoop
+
+
+def densifier_class():
+    """gflow_b200.densify.Densifier re-pointed at the emulated library and host tensors."""
+    from gflow_b200.densify import Densifier
+
+    class EmulatedDensifier(Densifier):
+        def _require_device(self, dev):
+            assert dev.type == "cpu"
+
+        def _library(self):
+            return load()
+
+        def _stream(self):
+            return 0
+
+    return EmulatedDensifier

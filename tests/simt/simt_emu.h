@@ -108,6 +108,8 @@ static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; retu
 static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 static inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 
 // ------------------------------------------------------------------ scheduler interface
 namespace gfb_emu {

@@ -87,3 +87,68 @@ def test_train_native_with_every_term_through_the_emulated_loop(monkeypatch):
     assert len(res.losses) == 5 and all(v == v and v > 0 for v in res.losses)
     assert res.losses[-1] < res.losses[0]
     assert not torch.equal(f.depth_a.data, torch.ones(1)), "depth_a is copied back from the device-side pair"
+
+
+def test_densify_between_iterations_recreates_the_optimiser_like_the_reference():
+    """trainer.py:566-571,941-951: new Gaussians are appended, Adam restarts over the attributes only with the
+    initial lr; pose and depth_a / depth_b stop moving.  Checked against torch.optim.Adam fed with the
+    kernel's gradients, as in fit_check."""
+    from oracle import fit_ref as FR
+
+    N, W, H = 350, 64, 48
+    sc, raw, pose, gt_image, gt_depth = fit_check.make_problem(N, W, H, seed=12)
+    cfg = fit.FitConfig(iterations=8, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, native=True, check_every=1, num_points=N)
+    f = fit.FrameFitter(raw, sc.intr, pose, W, H)
+    loop = emu.fit_loop_class()(f, gt_image, gt_depth, cfg, capacity=40 * N, debug=True)
+    loop.run(2)
+    pose_before, ab_before = f.pose.data.clone(), loop.depth_ab.clone()
+    hist_before = loop.loss_history().clone()
+    old = {k: f.attrs[k].data.clone() for k in fit.ATTRS}
+    added = loop.densify(error_threshold=1e-5, percent=0.5, seed=3)
+    assert added > 10 and loop.N == N + added
+    for k in fit.ATTRS:
+        assert f.attrs[k].shape[0] == N + added and torch.equal(f.attrs[k].data[:N], old[k])
+    assert torch.equal(loop.loss_history(), hist_before) and int(loop.status()[0]) == 2
+    # the appended Gaussians project onto the pixels they were drawn from, at the prior's depth
+    with torch.no_grad():
+        _, _, uv, depth = FR.render({k: f.attrs[k].data for k in fit.ATTRS}, f.pose.data, sc.intr, W, H, 0.0, want_depth=False)
+    new_uv = uv[N:]
+    seen = depth[N:, 0] != 0
+    assert bool(seen.float().mean() > 0.9)
+    # geometry.py:115 back-projects with fx on BOTH axes (GFlow's cameras have fx = fy; this one has 32 / 24), so
+    # u lands on the drawn pixel column and v on cy + (row - cy) fy / fx
+    pix = loop._last_densify_pixels.long()[seen]
+    col, row = (pix % W).float(), (pix // W).float()
+    fx, fy, cx, cy = (float(v) for v in sc.intr)
+    assert torch.allclose(new_uv[seen, 0], col, atol=2e-3)
+    assert torch.allclose(new_uv[seen, 1], cy + (row - cy) * fy / fx, atol=2e-3)
+    assert torch.allclose(depth[N:][seen, 0], gt_depth.reshape(-1)[pix], rtol=1e-4)
+    # next iterations: fresh Adam (t restarts at 1), constant lr, camera frozen
+    shadow = {k: f.attrs[k].data.clone().requires_grad_(True) for k in fit.ATTRS}
+    opt = torch.optim.Adam(list(shadow.values()), lr=cfg.lr)
+    for it in range(2):
+        loop.run(1)
+        kg, col = loop.dbg_grads.clone(), 0
+        for k in fit.ATTRS:
+            w = shadow[k].shape[1]
+            shadow[k].grad = kg[:, col:col + w].clone()
+            col += w
+        opt.step()
+        for k in fit.ATTRS:
+            assert torch.allclose(f.attrs[k].data, shadow[k].detach(), rtol=1e-5, atol=2e-6), (it, k)
+        assert torch.equal(f.pose.data, pose_before) and torch.equal(loop.depth_ab, ab_before)
+    assert loop.done == 4 and int(loop.status()[0]) == 4
+
+
+def test_train_native_with_densification_schedule(monkeypatch):
+    monkeypatch.setattr(fit, "NativeFitLoop", emu.fit_loop_class())
+    monkeypatch.setattr(fit.FrameFitter, "render", lambda self, bg=0.0, want_depth=True, with_depth=False: (None, None, None))
+    N, W, H = 300, 64, 48
+    sc, raw, pose, gt_image, gt_depth = fit_check.make_problem(N, W, H, seed=13)
+    f = fit.FrameFitter(raw, sc.intr, pose, W, H)
+    cfg = fit.FitConfig(iterations=7, lr=4e-3, lambda_depth=0.1, native=True, densify_interval=2, densify_times=2,
+                        densify_err_thre=1e-5, densify_err_percent=0.3)
+    res = f.train(gt_image, gt_depth, cfg)
+    assert len(res.losses) == 7 and all(v == v for v in res.losses)
+    n_final = f.attrs["xyz"].shape[0]
+    assert n_final > N and all(f.attrs[k].shape[0] == n_final for k in fit.ATTRS)
