@@ -58,7 +58,7 @@ SIGNATURES = {
 class FitProblem(ctypes.Structure):
     """struct gfb_fit_problem of include/gflow_b200.h, field by field."""
     _fields_ = [(n, P) for n in ("xyz", "scale", "rotate", "opacity", "rgb", "pose", "depth_ab", "intr", "gt_image",
-                                 "gt_depth", "pixel_mask", "still_mask", "still_ref", "still_sel", "flow_target",
+                                 "gt_depth", "pixel_mask", "still_mask", "scale_sel", "still_ref", "still_sel", "flow_target",
                                  "flow_sel", "dbg_grads", "dbg_act")] + \
                [(n, ctypes.c_int32) for n in ("N", "W", "H", "n_still", "n_still_ref", "still_count", "n_flow",
                                               "flow_count", "total_iters", "camera_only", "freeze_rgb", "use_ssim", "adam_t0",

@@ -101,6 +101,7 @@ __device__ __forceinline__ void extr_grad_to_pose(const float* pose, const float
 // per-Gaussian terms of trainer.py:490-530 that do not go through the image
 struct FitRegs {
     float lambda_var, lambda_scale;
+    const uint8_t* scale_sel;   // loss_scale only over these (NULL = every in-image Gaussian)
     const float* still_ref;     // loss_still = mean_sel |xyz - still_ref|
     const uint8_t* still_sel;
     int n_still_ref;
@@ -192,7 +193,8 @@ fit_preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ s
             const float d0 = s[0] - mu, d1 = s[1] - mu, d2 = s[2] - mu;
             reg[0] = sqrtf((d0 * d0 + d1 * d1 + d2 * d2) * 0.5f);
         }
-        if (lambda_scale != 0.0f && ok && u > 0.0f && u < (float)(W - 1) && v > 0.0f && v < (float)(H - 1)) {
+        if (lambda_scale != 0.0f && ok && u > 0.0f && u < (float)(W - 1) && v > 0.0f && v < (float)(H - 1) &&
+            (!rg.scale_sel || rg.scale_sel[i])) {
             reg[1] = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) / zc;  // trainer.py:495-501
             reg[2] = 1.0f;
         }
@@ -449,7 +451,8 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
         float gd = (C > 3) ? g2.y : 0.0f;  // dL/d(depth_i): the depth map's feature gradient
         float u, v, xc, yc, zc;
         if (project_one(in, e, W, H, nearest, extent, p[0], p[1], p[2], u, v, xc, yc, zc)) {
-            if (lambda_scale != 0.0f && u > 0.0f && u < (float)(W - 1) && v > 0.0f && v < (float)(H - 1)) {
+            if (lambda_scale != 0.0f && u > 0.0f && u < (float)(W - 1) && v > 0.0f && v < (float)(H - 1) &&
+                (!rg.scale_sel || rg.scale_sel[i])) {
                 const float nrm = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
                 const float wgt = lambda_scale / loss_acc[LA_NSCALE];
                 if (nrm > 0.0f) {
@@ -771,7 +774,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
     const bool use_flow = p->lambda_flow != 0.0f && p->flow_target && p->flow_sel && p->flow_count > 0;
     const float inv_still = use_still ? 1.0f / (float)p->still_count : 0.0f;
     const float inv_flow2 = use_flow ? 1.0f / (2.0f * (float)p->flow_count) : 0.0f;
-    const FitRegs rg{p->lambda_var,  p->lambda_scale, p->still_ref,   p->still_sel, use_still ? p->n_still_ref : 0,
+    const FitRegs rg{p->lambda_var,  p->lambda_scale, p->scale_sel, p->still_ref,   p->still_sel, use_still ? p->n_still_ref : 0,
                      p->lambda_still * inv_still, p->flow_target, p->flow_sel,  use_flow ? p->n_flow : 0,
                      p->lambda_flow * inv_flow2};
     const int nblk = gfb_div_up(N, kThreads);

@@ -264,6 +264,9 @@ class FrameFitter:
                 loss = loss + cfg.lambda_var * torch.mean(torch.std(self.get_attribute("scale"), dim=1))
             if cfg.lambda_scale:
                 within = (uv[:, 0] > 0) & (uv[:, 0] < self.W - 1) & (uv[:, 1] > 0) & (uv[:, 1] < self.H - 1)
+                if still_mask is not None:  # trainer.py:467-471,495-501 (in-place narrowing seen through an alias)
+                    n = still_mask.shape[0]
+                    within[:n] = (still_mask if cfg.camera_only else ~still_mask) & within[:n]
                 ls = torch.norm(self.get_attribute("scale")[within], dim=1) * (1.0 / depth[within]).squeeze(-1)
                 loss = loss + cfg.lambda_scale * ls.mean()
             if use_still:
@@ -369,6 +372,13 @@ class NativeFitLoop:
         self.still_mask = None if still_mask is None else still_mask.to(dev).to(torch.uint8).contiguous()
         if self.still_mask is not None and self.still_mask.numel() > self.N:
             raise RuntimeError("gflow_b200: still_mask is longer than the number of Gaussians")
+        # loss_scale runs over the still (camera-only) / moving (full stage) Gaussians once a still mask exists
+        self.scale_sel = None
+        if cfg.lambda_scale and self.still_mask is not None:
+            sel = torch.ones(self.N, dtype=torch.uint8, device=dev)
+            n = self.still_mask.numel()
+            sel[:n] = self.still_mask if cfg.camera_only else (1 - self.still_mask)
+            self.scale_sel = sel
         # still / flow terms: everything that is constant over the call is folded on the host once
         self.still_ref = self.still_sel = self.flow_target = self.flow_sel = None
         self.still_count = self.flow_count = 0
@@ -431,6 +441,7 @@ class NativeFitLoop:
         pr.gt_image, pr.gt_depth = self.gt_image.data_ptr(), ops._ptr(self.gt_depth)
         pr.pixel_mask, pr.still_mask = ops._ptr(self.pixel_mask), ops._ptr(self.still_mask)
         pr.dbg_grads, pr.dbg_act = ops._ptr(self.dbg_grads), ops._ptr(self.dbg_act)
+        pr.scale_sel = ops._ptr(self.scale_sel)
         pr.still_ref, pr.still_sel = ops._ptr(self.still_ref), ops._ptr(self.still_sel)
         pr.flow_target, pr.flow_sel = ops._ptr(self.flow_target), ops._ptr(self.flow_sel)
         pr.N, pr.W, pr.H = self.N, self.W, self.H
@@ -520,6 +531,8 @@ class NativeFitLoop:
                 f.attrs[k] = torch.nn.Parameter(torch.cat([f.attrs[k].data, new[k]], dim=0))
             head = self.ws[: self.lay.adam_m].clone()  # status | loss sums | camera | loss history: N independent
             self.N += count
+            if self.scale_sel is not None:
+                self.scale_sel = torch.cat([self.scale_sel, torch.ones(count, dtype=torch.uint8, device=self.dev)])
             if self.dbg_grads is not None:  # per-Gaussian debug outputs grow with N
                 self.dbg_grads = torch.zeros(self.N, 14, dtype=torch.float32, device=self.dev)
                 self.dbg_act = torch.zeros(self.N, 14, dtype=torch.float32, device=self.dev)

@@ -183,6 +183,9 @@ typedef struct gfb_fit_problem {
     const float *gt_depth;       /* (H,W,1) or NULL (no depth term) */
     const uint8_t *pixel_mask;   /* (H,W) 1 = pixel takes part in the losses, or NULL (trainer.py:452-455,484) */
     const uint8_t *still_mask;   /* (n_still) 1 = xyz gradient zeroed (trainer.py:542-546), or NULL */
+    const uint8_t *scale_sel;    /* (N) 1 = Gaussian takes part in loss_scale, or NULL = all: trainer.py:467-471 narrows
+                                    the in-image index to the still (camera-only) / moving (full stage) set in place, and
+                                    trainer.py:495-501 reads it through the alias self.within_index */
     const float *still_ref;      /* (n_still_ref,3) last frame's xyz, or NULL: loss_still (trainer.py:504-508) */
     const uint8_t *still_sel;    /* (n_still_ref) 1 = Gaussian takes part in loss_still (last_still_mask) */
     const float *flow_target;    /* (n_flow,2) last_uv + gt_flow[last_uv], or NULL: loss_flow (trainer.py:510-530) */

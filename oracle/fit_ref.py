@@ -125,7 +125,8 @@ def flow_and_mask(last_uv, W, H, still_mask=None, camera_only=False):
     return m.detach()
 
 
-def iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg: FitRefConfig, prev=None):
+def iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg: FitRefConfig, prev=None,
+                   still_mask=None):
     """One forward of the iteration; returns (loss, dict of parts).
 
     prev (optional, frames >= 1): dict(last_xyz (n,3), last_still_mask (n,), last_uv (n,2), gt_flow (H,W,2),
@@ -159,6 +160,9 @@ def iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W,
         loss = loss + cfg.lambda_var * lv
     if cfg.lambda_scale:
         within = (uv[:, 0] > 0) & (uv[:, 0] < W - 1) & (uv[:, 1] > 0) & (uv[:, 1] < H - 1)
+        if still_mask is not None:  # trainer.py:467-471 narrows the index in place; 495-501 reads it via self.within_index
+            n = still_mask.shape[0]
+            within[:n] = (still_mask if cfg.camera_only else ~still_mask) & within[:n]
         ls = torch.norm(activate("scale", raw["scale"])[within], dim=1) * (1.0 / depth[within]).squeeze(-1)
         ls = ls.mean()
         parts["scale"] = ls.detach()
@@ -196,7 +200,7 @@ def fit_loop(raw0: Dict[str, torch.Tensor], pose0, intr, gt_image, gt_depth, W, 
     sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.1, total_iters=cfg.iterations)
     history = []
     for it in range(cfg.iterations if n_iters is None else n_iters):
-        loss, parts = iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg, prev)
+        loss, parts = iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg, prev, still_mask)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v)) for k, v in raw.items()}

@@ -95,7 +95,7 @@ def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=
         cur_pose = fitter.pose.data.cpu().clone().requires_grad_(True)
         cur_ab = torch.cat([fitter.depth_a.data.cpu(), fitter.depth_b.data.cpu()]).clone().requires_grad_(True)
         loss, parts = FR.iteration_loss(cur, cur_pose, cur_ab, sc.intr, gt_image, gt_depth if use_depth else None,
-                                        pixel_mask, W, H, rcfg, prev_ref)
+                                        pixel_mask, W, H, rcfg, prev_ref, still_mask)
         loss.backward()
         assert torch.allclose(loop.camera().cpu()[:12].reshape(3, 4), FR.pose_to_extr(cur_pose.detach()), atol=2e-6)
         loop.run(1)
@@ -167,7 +167,8 @@ def case_list():
                          native=True), dict(n_iters=2, seed=7, with_prev=True, still_mask=torch.rand(300, generator=g) > 0.5)),
         ("camera_only", C(iterations=6, lr=4e-3, lr_camera=2e-3, lambda_depth=0.1, camera_only=True, native=True),
          dict(n_iters=3, seed=5)),
-        ("masks", C(iterations=6, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, freeze_rgb=True, use_ssim=True, native=True),
+        ("masks", C(iterations=6, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, freeze_rgb=True, use_ssim=True, lambda_scale=0.3,
+                    native=True),
          dict(n_iters=2, N=N, W=W, H=H, seed=6, pixel_mask=pixel_mask, still_mask=still)),
     ]
 
