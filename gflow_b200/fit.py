@@ -166,6 +166,30 @@ class PrevFrame:
         return (uv + self.gt_flow[y, x]).contiguous()
 
 
+def warp_moving_by_flow(xyz: torch.Tensor, prev: "PrevFrame", gt_depth: torch.Tensor, intr: torch.Tensor,
+                        extr: torch.Tensor, W: int, H: int) -> torch.Tensor:
+    """The pre-update step of a full (not camera-only) stage on frames >= 1, trainer.py:348-376: every MOVING
+    Gaussian of the previous frame whose centre was inside the image is moved to where the flow prior sends its
+    centre, back-projected with the new depth prior (geometry.py:104-116, focal = fx on both axes).  Returns the
+    new raw xyz; runs once per frame, plain tensor ops on whatever device the inputs live on."""
+    m = prev.last_still_mask
+    n = m.shape[0]
+    uv_move = prev.last_uv[:n][~m]
+    inside = (uv_move[:, 0] > 0) & (uv_move[:, 0] < W - 1) & (uv_move[:, 1] > 0) & (uv_move[:, 1] < H - 1)
+    uv_in = uv_move[inside]
+    uv_new = uv_in + prev.gt_flow[uv_in[:, 1].long(), uv_in[:, 0].long()]
+    yc = uv_new[:, 1].long().clamp(0, H - 1)
+    xc = uv_new[:, 0].long().clamp(0, W - 1)
+    depth = gt_depth[yc, xc].reshape(-1, 1)
+    cam = torch.cat((depth * (uv_new - intr[2:]) / intr[0], depth), dim=-1)
+    R, t = extr[:, :3], extr[:, 3]
+    world = (cam - t) @ R  # R^T (p_cam - t) for the rigid world->camera [R|t]
+    out = xyz.detach().clone()
+    idx = torch.nonzero(~m, as_tuple=False).squeeze(-1)[inside]
+    out[idx] = world.to(out.dtype)
+    return out
+
+
 @dataclass
 class FitResult:
     losses: List[float] = field(default_factory=list)

@@ -154,3 +154,89 @@ def test_first_frame_stage_runs_unmodified_and_matches_the_fit_oracle(reference_
     assert torch.allclose(t.pose.detach(), pose, rtol=1e-4, atol=1e-6)
     assert torch.allclose(torch.cat([t.depth_a.detach(), t.depth_b.detach()]), ab, rtol=1e-4, atol=1e-6)
     assert float(_Bar.posted[-1]["total"]) < float(_Bar.posted[0]["total"])
+
+
+def _first_frame(ref_trainer, tmp_path, W=48, H=32, N=300):
+    img, depth = _scene(W, H)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    t = ref_trainer.SimpleGaussian(gt_image=img, gt_depth=depth, num_points=N, sequence_path=str(tmp_path / "seq"))
+    t.load_camera(focal=0.6 * W, pp=[W / 2.0, H / 2.0], show=False)
+    t.init_gaussians_from_image(gt_image=img, gt_depth=depth, num_points=N)
+    move_mask = torch.zeros(H, W, dtype=torch.bool)
+    move_mask[10:20, 5:25] = True
+    import utils as ref_utils
+
+    class _Hull:
+        def __init__(self, pts, *a, **k):
+            pass
+
+        def mask(self, w, h):
+            return np.zeros((h, w), dtype=np.float32)
+
+    ref_utils.FastConcaveHull2D = _Hull
+    t.train(iterations=2, lr=4e-3, lr_camera=1e-3, lambda_rgb=1.0, lambda_depth=0.1, move_mask=move_mask, densify_interval=500,
+            densify_times=0)
+    return t, img, depth, move_mask
+
+
+def test_later_frame_full_stage_matches_the_fit_oracle(reference_trainer, tmp_path, monkeypatch):
+    """Frame >= 1, full stage (fit_video.py:288-315): moving Gaussians warped by the flow prior, rgb frozen, xyz of the
+    still set frozen, still / flow / scale terms over the right subsets."""
+    from gflow_b200 import fit
+
+    ref_trainer, calls = reference_trainer
+    W, H = 48, 32
+    t, img0, depth0, move_mask = _first_frame(ref_trainer, tmp_path, W, H)
+    assert 5 < int((~t.still_mask).sum()) < t.still_mask.numel() - 5, "frame 0 left both still and moving Gaussians"
+    g = torch.Generator().manual_seed(3)
+    img1 = torch.roll(img0, shifts=1, dims=1).contiguous()
+    depth1 = (depth0 * 1.02).contiguous()
+    gt_flow = torch.zeros(H, W, 2)
+    gt_flow[..., 0] = 1.0 + 0.2 * torch.rand(H, W, generator=g)
+    gt_flow[..., 1] = 0.3 * torch.randn(H, W, generator=g)
+    t.set_gt_image(img1)
+    t.set_gt_depth(depth1)
+    t.set_gt_flow(gt_flow)
+    state = dict(still_mask=t.still_mask.clone(), last_still_mask=t.last_still_mask.clone(), last_uv=t.last_uv.clone(),
+                 last_xyz=t.last_xyz.clone())
+    xyz_before = t._attributes["xyz"].detach().clone()
+    snap = {}
+    orig_add = ref_trainer.SimpleGaussian.add_optimizer
+
+    def add_optimizer(self, *a, **k):  # called right after the pre-update warp (trainer.py:383)
+        snap.update({k2: v.detach().clone() for k2, v in self._attributes.items()})
+        snap["pose"] = self.pose.detach().clone()
+        return orig_add(self, *a, **k)
+
+    monkeypatch.setattr(ref_trainer.SimpleGaussian, "add_optimizer", add_optimizer)
+    _Bar.posted = []
+    iters = 3
+    lam = dict(lambda_rgb=1.0, lambda_depth=0.1, lambda_var=0.2, lambda_scale=0.05, lambda_still=0.3, lambda_flow=0.01)
+    t.train(iterations=iters, lr=2e-3, lr_camera=0.0, mask=torch.zeros(H, W, 1), move_mask=move_mask, densify_interval=500,
+            densify_times=0, **lam)
+    # --- our host-side warp == the reference's pre-update processing
+    prev = fit.PrevFrame(last_xyz=state["last_xyz"], last_still_mask=state["last_still_mask"], last_uv=state["last_uv"],
+                         gt_flow=gt_flow)
+    extr0 = FR.pose_to_extr(snap["pose"])
+    warped = fit.warp_moving_by_flow(xyz_before, prev, depth1, t.intr, extr0, W, H)
+    assert not torch.equal(snap["xyz"], xyz_before), "the reference moved the moving Gaussians"
+    assert torch.allclose(warped, snap["xyz"], rtol=1e-4, atol=1e-5)
+    # --- the loop itself
+    start = {k: snap[k] for k in FR.ATTRS}
+    cfg = FR.FitRefConfig(iterations=iters, lr=2e-3, lr_camera=0.0, use_ssim=True, depth_den_min=0.0, freeze_rgb=True, **lam)
+    pr = dict(last_xyz=state["last_xyz"], last_still_mask=state["last_still_mask"], last_uv=state["last_uv"], gt_flow=gt_flow,
+              and_mask=FR.flow_and_mask(state["last_uv"], W, H, state["still_mask"], False))
+    assert int(pr["and_mask"].sum()) > 3
+    raw, pose, ab, hist = FR.fit_loop(start, snap["pose"], t.intr, img1, depth1, W, H, cfg, still_mask=state["still_mask"], prev=pr)
+    for i in range(iters):
+        p, h = _Bar.posted[i], hist[i]
+        assert abs(float(p["total"]) - float(h["total"])) <= 1e-4 * abs(float(h["total"])), (i, p, h["total"])
+        for key in ("still", "flow", "scale", "var", "depth"):  # posted as "%.6f" strings (trainer.py:464-530)
+            assert abs(float(p[key]) - float(h[key])) <= 1.5e-6 + 1e-4 * abs(float(h[key])), (i, key, p[key], h[key])
+    for k in FR.ATTRS:
+        assert torch.allclose(t._attributes[k].detach(), raw[k], rtol=1e-4, atol=1e-5), k
+    assert torch.equal(t._attributes["rgb"].detach(), start["rgb"]), "rgb is frozen on frames >= 1"
+    n = state["still_mask"].shape[0]
+    assert torch.equal(t._attributes["xyz"].detach()[:n][state["still_mask"]], start["xyz"][:n][state["still_mask"]])
+    assert torch.allclose(t.pose.detach(), pose, atol=1e-6)
