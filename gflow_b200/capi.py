@@ -46,6 +46,7 @@ SIGNATURES = {
     "gfb_alpha_blending_bwd": (I, [P, P, L, P, P, I, I, I, F, I, I, P, P, P, P, P]),
     "gfb_blend_unpack_grads": (I, [P, I, I, I, I, P, P, P, P, I, P]),
     "gfb_fit_get_layout": (I, [I, I, I, L, I, P]),
+    "gfb_fit_sub_workspace_bytes": (c_size_t, [I, I, I, L]),
     "gfb_fit_init": (I, [P, P, L, I, P]),
     "gfb_fit_iterate": (I, [P, P, L, I, I, I, P]),
     "gfb_rgb_error_map": (I, [P, P, P, I, I, P, P]),
@@ -59,9 +60,10 @@ class FitProblem(ctypes.Structure):
     """struct gfb_fit_problem of include/gflow_b200.h, field by field."""
     _fields_ = [(n, P) for n in ("xyz", "scale", "rotate", "opacity", "rgb", "pose", "depth_ab", "intr", "gt_image",
                                  "gt_depth", "pixel_mask", "still_mask", "scale_sel", "still_ref", "still_sel", "flow_target",
-                                 "flow_sel", "dbg_grads", "dbg_act")] + \
+                                 "flow_sel", "sub_xyz", "sub_scale", "sub_rotate", "sub_opacity", "sub_rgb",
+                                 "dyn_mask", "sub_workspace", "dbg_grads", "dbg_act")] + \
                [(n, ctypes.c_int32) for n in ("N", "W", "H", "n_still", "n_still_ref", "still_count", "n_flow",
-                                              "flow_count", "total_iters", "camera_only", "freeze_rgb", "use_ssim", "adam_t0",
+                                              "flow_count", "sub_N", "sub_capacity", "total_iters", "camera_only", "freeze_rgb", "use_ssim", "adam_t0",
                                               "constant_lr", "freeze_camera")] + \
                [(n, F) for n in ("bg", "nearest", "extent", "lr", "lr_camera", "lambda_rgb", "lambda_depth",
                                  "lambda_var", "lambda_scale", "lambda_still", "lambda_flow", "beta1", "beta2", "eps",

@@ -42,7 +42,7 @@ namespace {
 
 using namespace gfbm;
 
-enum { ST_ITER = 0, ST_K_LAST = 1, ST_K_MAX = 2, ST_WORDS = 16 };
+enum { ST_ITER = 0, ST_K_LAST = 1, ST_K_MAX = 2, ST_SUB_K_MAX = 3, ST_WORDS = 16 };
 // loss accumulators (sums; fit_finish turns them into means)
 enum { LA_SQ = 0, LA_DEPTH = 1, LA_DA = 2, LA_DB = 3, LA_SSIM = 4, LA_VAR = 5, LA_SCALE = 6, LA_NSCALE = 7, LA_STILL = 8,
        LA_FLOW = 9, LA_WORDS = 12 };
@@ -367,6 +367,19 @@ ssim_grad_kernel(const float* __restrict__ out, const float* __restrict__ gt_ima
     ssim_grad[ch * P + pix] = -w_ssim * (c0 + 2.0f * x * c1 + y * c2);
 }
 
+// ------------------------------------------------------------------ camera-only stage: moving-subset mask
+// trainer.py:446-451: grey = 0.299 r + 0.587 g + 0.114 b of the moving Gaussians' render; grey > 0 removes the
+// pixel from the losses from now on (move_mask = move_gs_mask | move_mask).  Also tracks the subset's max K.
+__global__ void __launch_bounds__(256)
+fit_move_mask_kernel(const float* __restrict__ sub_out, int P, uint8_t* __restrict__ dyn_mask,
+                     const int32_t* __restrict__ sub_ctrl, int32_t* __restrict__ status) {
+    const int pix = blockIdx.x * 256 + threadIdx.x;
+    if (pix == 0) status[ST_SUB_K_MAX] = max(status[ST_SUB_K_MAX], sub_ctrl[GFB_CTRL_K]);
+    if (pix >= P) return;
+    const float grey = 0.299f * sub_out[pix] + 0.587f * sub_out[(size_t)P + pix] + 0.114f * sub_out[2 * (size_t)P + pix];
+    if (grey > 0.0f) dyn_mask[pix] = 0;
+}
+
 // ------------------------------------------------------------------ pixel losses -> dL/d(out)
 // trainer.py:452-464 (mse over (H,W,3)) and trainer.py:476-488 ((aD+b - Dgt)^2 / (aD+b + Dgt), mean);
 // w_rgb = lambda_rgb / (3 H W), w_depth = lambda_depth / (H W).  ssim_grad (3,H,W) is added when present.
@@ -668,11 +681,50 @@ bool make_layout(int N, int W, int H, int64_t capacity, int max_iters, Layout& L
     return true;
 }
 
+struct SubLayout {
+    size_t uv, depth, conic, radius, rect, op_act, feat, control, tile_range, keys, ids, geom, fstream, out, final_T,
+        n_contrib, total;
+};
+
+bool make_sub_layout(int n_, int W, int H, int64_t capacity, SubLayout& L) {
+    if (n_ <= 0 || W <= 0 || H <= 0 || capacity <= 0) return false;
+    const size_t P = (size_t)W * H, n = (size_t)n_, cap = (size_t)capacity;
+    const size_t T = (size_t)((W + GFB_TILE - 1) / GFB_TILE) * ((H + GFB_TILE - 1) / GFB_TILE);
+    const size_t R = (size_t)gfb_tile_replicas((int)T);
+    size_t off = 0;
+    auto take = [&off](size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    L.uv = take(n * 8);
+    L.depth = take(n * 4);
+    L.conic = take(n * 12);
+    L.radius = take(n * 4);
+    L.rect = take(n * 8);
+    L.op_act = take(n * 4);
+    L.feat = take(n * 12);
+    L.control = take((2 * T * R + 1 + GFB_CTRL_WORDS) * 4);
+    L.tile_range = take(T * 8);
+    L.keys = take(cap * 8);
+    L.ids = take(cap * 4);
+    L.geom = take(cap * 32);
+    L.fstream = take(cap * 16);
+    L.out = take(3 * P * 4);
+    L.final_T = take(P * 4);
+    L.n_contrib = take(P * 4);
+    L.total = off;
+    return true;
+}
+
 bool problem_ok(const gfb_fit_problem* p) {
     return p && p->xyz && p->scale && p->rotate && p->opacity && p->rgb && p->pose && p->depth_ab && p->intr &&
            p->gt_image && p->N > 0 && p->W > 0 && p->H > 0 && p->total_iters > 0 && p->n_still >= 0 &&
            (p->n_still == 0 || p->still_mask) && p->n_still <= p->N && p->n_still_ref >= 0 && p->n_still_ref <= p->N &&
-           p->n_flow >= 0 && p->n_flow <= p->N && p->still_count >= 0 && p->flow_count >= 0 && p->adam_t0 >= 0;
+           p->n_flow >= 0 && p->n_flow <= p->N && p->still_count >= 0 && p->flow_count >= 0 && p->adam_t0 >= 0 &&
+           p->sub_N >= 0 &&
+           (p->sub_N == 0 || (p->sub_xyz && p->sub_scale && p->sub_rotate && p->sub_opacity && p->sub_rgb && p->dyn_mask &&
+                              p->sub_workspace && p->sub_capacity > 0));
 }
 
 AdamStep adam_step(const gfb_fit_problem* p, double lr, int iter) {
@@ -709,6 +761,11 @@ int gfb_fit_get_layout(int N, int W, int H, int64_t capacity, int max_iters, gfb
     if (!layout || !make_layout(N, W, H, capacity, max_iters, L)) return GFB_E_BADARG;
     *layout = L.pub;
     return 0;
+}
+
+size_t gfb_fit_sub_workspace_bytes(int sub_N, int W, int H, int64_t sub_capacity) {
+    SubLayout L;
+    return make_sub_layout(sub_N, W, H, sub_capacity, L) ? L.total : 0;
 }
 
 int gfb_fit_init(const gfb_fit_problem* p, void* workspace, int64_t capacity, int max_iters, void* stream) {
@@ -779,6 +836,13 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                      p->lambda_flow * inv_flow2};
     const int nblk = gfb_div_up(N, kThreads);
     const bool pdl = fit_pdl();
+    // camera-only stage: the moving subset is rendered every iteration and its footprint leaves the losses
+    const bool use_sub = p->sub_N > 0 && p->camera_only;
+    SubLayout S;
+    if (use_sub && !make_sub_layout(p->sub_N, W, H, p->sub_capacity, S)) return GFB_E_BADARG;
+    char* sw = (char*)p->sub_workspace;
+    const uint8_t* loss_mask = use_sub ? p->dyn_mask : p->pixel_mask;
+    const FitRegs no_regs{0.0f, 0.0f, nullptr, nullptr, nullptr, 0, 0.0f, nullptr, nullptr, 0, 0.0f};
     int rc;
     for (int it = first_iter; it < first_iter + n_iters; ++it) {
         GFB_TRY(cudaMemsetAsync(counts, 0, ((size_t)T * R + GFB_CTRL_WORDS) * sizeof(int32_t), st));
@@ -793,14 +857,37 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
         rc = gfb_internal_blend_fwd(geom, fstream, capacity, tile_range, C, 0, C, p->bg, W, H, out, final_T, n_contrib,
                                     stream, pdl);
         if (rc) return rc;
-        if (p->use_ssim) {
-            ssim_stats_kernel<<<dim3(gx, gy, 3), 256, 0, st>>>(out, p->gt_image, p->pixel_mask, W, H, ssim_maps, loss_acc);
+        if (use_sub) {
+            int32_t* s_counts = (int32_t*)(sw + S.control);
+            int32_t* s_ctrl = s_counts + (size_t)T * R;
+            GFB_TRY(cudaMemsetAsync(s_counts, 0, ((size_t)T * R + GFB_CTRL_WORDS) * sizeof(int32_t), st));
+            fit_preprocess_kernel<<<gfb_div_up(p->sub_N, kThreads), kThreads, 0, st>>>(
+                p->sub_xyz, p->sub_scale, reinterpret_cast<const float4*>(p->sub_rotate), p->sub_opacity, p->sub_rgb, cam,
+                p->sub_N, W, H, p->nearest, p->extent, 3, reinterpret_cast<float2*>(sw + S.uv), (float*)(sw + S.depth),
+                (float*)(sw + S.conic), (int32_t*)(sw + S.radius), reinterpret_cast<ushort4*>(sw + S.rect),
+                (float*)(sw + S.op_act), (float*)(sw + S.feat), s_counts, s_ctrl + GFB_CTRL_WORDS, s_ctrl, T, R, no_regs,
+                loss_acc, nullptr);
             GFB_CHECK_LAUNCH();
-            ssim_grad_kernel<<<dim3(gx, gy, 3), 256, 0, st>>>(out, p->gt_image, p->pixel_mask, W, H, ssim_maps, w_rgb,
+            rc = gfb_internal_scatter_sort_pack(sw + S.rect, (float*)(sw + S.depth), p->sub_N, W, H, s_counts, p->sub_capacity,
+                                                sw + S.keys, (int32_t*)(sw + S.tile_range), (float*)(sw + S.uv),
+                                                (float*)(sw + S.conic), (float*)(sw + S.op_act), (float*)(sw + S.feat), 3,
+                                                (int32_t*)(sw + S.ids), sw + S.geom, sw + S.fstream, stream, pdl);
+            if (rc) return rc;
+            rc = gfb_internal_blend_fwd(sw + S.geom, sw + S.fstream, p->sub_capacity, (int32_t*)(sw + S.tile_range), 3, 0, 3,
+                                        p->bg, W, H, (float*)(sw + S.out), (float*)(sw + S.final_T),
+                                        (int32_t*)(sw + S.n_contrib), stream, pdl);
+            if (rc) return rc;
+            fit_move_mask_kernel<<<gfb_div_up(P, 256), 256, 0, st>>>((float*)(sw + S.out), P, p->dyn_mask, s_ctrl, status);
+            GFB_CHECK_LAUNCH();
+        }
+        if (p->use_ssim) {
+            ssim_stats_kernel<<<dim3(gx, gy, 3), 256, 0, st>>>(out, p->gt_image, loss_mask, W, H, ssim_maps, loss_acc);
+            GFB_CHECK_LAUNCH();
+            ssim_grad_kernel<<<dim3(gx, gy, 3), 256, 0, st>>>(out, p->gt_image, loss_mask, W, H, ssim_maps, w_rgb,
                                                                ssim_grad);
             GFB_CHECK_LAUNCH();
         }
-        fit_loss_kernel<<<gfb_div_up(P, kThreads), kThreads, 0, st>>>(out, C, p->gt_image, p->gt_depth, p->pixel_mask,
+        fit_loss_kernel<<<gfb_div_up(P, kThreads), kThreads, 0, st>>>(out, C, p->gt_image, p->gt_depth, loss_mask,
                                                                      p->depth_ab, W, H, w_rgb, w_depth, p->depth_den_min,
                                                                      p->use_ssim ? ssim_grad : nullptr, g_out, loss_acc);
         GFB_CHECK_LAUNCH();

@@ -114,6 +114,7 @@ class FitConfig:
     densify_times: int = 0
     densify_err_thre: float = 1e-3
     densify_err_percent: float = 0.1
+    densify_occ_percent: float = 0.1  # trainer.py:562-564: after iteration 0 of a later frame, inside the occlusion mask
     num_points: Optional[int] = None  # the reference's self.num_points (configured count); default: initial N
     densify_seed: int = 0
 
@@ -238,12 +239,22 @@ class FrameFitter:
 
     def train(self, gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor], cfg: FitConfig,
               pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None,
-              prev: Optional[PrevFrame] = None) -> FitResult:
+              prev: Optional[PrevFrame] = None, tentative_still: Optional[torch.Tensor] = None,
+              occlusion_mask: Optional[torch.Tensor] = None) -> FitResult:
         """gt_image (H,W,3) in [0,1]; gt_depth (H,W,1) or None; pixel_mask (H,W) bool (True = pixel counts,
         trainer.py:452-455); still_mask (n,) bool (True = xyz frozen, trainer.py:542-546); prev: previous-frame
-        state for the still / flow terms.  Returns per-iteration losses and the final render."""
+        state for the still / flow terms; tentative_still (n,) bool: in a camera-only stage the Gaussians that are
+        NOT tentatively still are re-rendered every iteration and their footprint leaves the losses, cumulatively
+        (trainer.py:427-451); occlusion_mask (H,W): on frames >= 1 (prev given), new Gaussians are drawn uniformly
+        inside it right after iteration 0 (trainer.py:562-564).  Returns per-iteration losses and the final render."""
+        occ = None
+        if occlusion_mask is not None and prev is not None and not cfg.camera_only and bool((occlusion_mask > 0).any()):
+            occ = (occlusion_mask > 0).reshape(self.H, self.W)
         if cfg.native:
-            return self._train_native(gt_image, gt_depth, cfg, pixel_mask, still_mask, prev)
+            return self._train_native(gt_image, gt_depth, cfg, pixel_mask, still_mask, prev, tentative_still, occ)
+        dynamic = cfg.camera_only and tentative_still is not None
+        if dynamic:
+            keep = torch.ones(self.H, self.W, dtype=torch.bool, device=gt_image.device) if pixel_mask is None else pixel_mask.bool()
         use_still = bool(cfg.lambda_still) and prev is not None and prev.last_still_mask is not None
         use_flow = bool(cfg.lambda_flow) and prev is not None and prev.gt_flow is not None
         if use_flow:
@@ -262,6 +273,10 @@ class FrameFitter:
         self._num_points0 = cfg.num_points or int(self.attrs["xyz"].shape[0])
         for it in range(cfg.iterations):
             uv = depth = None
+            if dynamic:
+                keep = keep & ~self._moving_footprint(tentative_still, cfg.background)
+                pm = keep.to(gt_image.dtype)
+                gt = gt_image * pm[..., None]
             if cfg.fused and not use_depth and not cfg.lambda_scale and not use_flow:
                 img = ops.rasterization(self.get_attribute("xyz"), self.get_attribute("scale"),
                                         self.get_attribute("rotate"), self.get_attribute("opacity"),
@@ -314,6 +329,9 @@ class FrameFitter:
             opt.step()
             sched.step()
             loss_hist.append(loss.detach())
+            if it == 0 and occ is not None:
+                if self._densify_operator_path(img.detach(), gt, gt_image, gt_depth, cfg, it, occ):
+                    opt = torch.optim.Adam(list(self.attrs.values()), lr=cfg.lr)
             if self._densify_due(cfg, it):
                 # trainer.py:566-571 + 941-951: append Gaussians drawn from the error map, then a NEW Adam over
                 # the attributes only (initial lr, no scheduler; pose / depth_a / depth_b drop out)
@@ -325,28 +343,46 @@ class FrameFitter:
             res.pose = self.pose.detach().clone()
         return res
 
+    def _moving_footprint(self, tentative_still: torch.Tensor, bg: float) -> torch.Tensor:
+        """(H,W) bool: pixels the not-tentatively-still Gaussians touch under the current pose (trainer.py:427-451)."""
+        n = tentative_still.shape[0]
+        sel = ~tentative_still
+        with torch.no_grad():
+            a = {k: self.get_attribute(k).detach()[:n][sel] for k in ATTRS}
+            img = ops.rasterization(a["xyz"], a["scale"], a["rotate"], a["opacity"], a["rgb"], self.intr, self.get_extr().detach(),
+                                    self.W, self.H, bg)
+        return (0.299 * img[0] + 0.587 * img[1] + 0.114 * img[2]) > 0.0
+
     @staticmethod
     def _densify_due(cfg: FitConfig, it: int) -> bool:
         k = cfg.densify_interval
         return bool(k) and not cfg.camera_only and (it + 1) % k == 0 and (it + 1) // k <= cfg.densify_times
 
-    def _densify_operator_path(self, img, gt_masked, gt_image, gt_depth, cfg: FitConfig, it: int) -> bool:
+    def _densify_operator_path(self, img, gt_masked, gt_image, gt_depth, cfg: FitConfig, it: int, occ=None) -> bool:
         if gt_depth is None:
             raise RuntimeError("gflow_b200: densification back-projects with the depth prior; gt_depth is required")
         dens = _densify.Densifier(self.W, self.H, self.attrs["xyz"].device)
-        err = dens.rgb_error_map(img.contiguous(), gt_masked.contiguous())
-        new = dens.sample(err, gt_image, gt_depth, self.intr, self.get_extr().detach(), self._num_points0,
-                          cfg.densify_err_thre, cfg.densify_err_percent, seed=cfg.densify_seed + it)
+        if occ is not None:  # uniform draw inside the occlusion mask
+            err, thre, pct = torch.ones(self.H, self.W, device=img.device), 0.0, cfg.densify_occ_percent
+        else:
+            err, thre, pct = dens.rgb_error_map(img.contiguous(), gt_masked.contiguous()), cfg.densify_err_thre, cfg.densify_err_percent
+        new = dens.sample(err, gt_image, gt_depth, self.intr, self.get_extr().detach(), self._num_points0, thre, pct, mask=occ,
+                          seed=cfg.densify_seed + it)
         if new is None:
             return False
         for k in ATTRS:
             self.attrs[k] = torch.nn.Parameter(torch.cat([self.attrs[k].data, new[k]], dim=0))
         return True
 
-    def _train_native(self, gt_image, gt_depth, cfg: FitConfig, pixel_mask, still_mask, prev=None) -> FitResult:
-        loop = NativeFitLoop(self, gt_image, gt_depth, cfg, pixel_mask=pixel_mask, still_mask=still_mask, prev=prev)
+    def _train_native(self, gt_image, gt_depth, cfg: FitConfig, pixel_mask, still_mask, prev=None,
+                      tentative_still=None, occ=None) -> FitResult:
+        loop = NativeFitLoop(self, gt_image, gt_depth, cfg, pixel_mask=pixel_mask, still_mask=still_mask, prev=prev,
+                             tentative_still=tentative_still)
+        if occ is not None and cfg.iterations > 0:
+            loop.run(1)
+            loop.densify(0.0, cfg.densify_occ_percent, mask=occ, uniform_error=True, seed=cfg.densify_seed)
         if cfg.densify_interval and not cfg.camera_only:
-            k, done = cfg.densify_interval, 0
+            k, done = cfg.densify_interval, loop.done
             while done < cfg.iterations:
                 nxt = min(cfg.iterations, (done // k + 1) * k)
                 loop.run(nxt - done)
@@ -354,7 +390,7 @@ class FrameFitter:
                 if self._densify_due(cfg, done - 1):
                     loop.densify(cfg.densify_err_thre, cfg.densify_err_percent, seed=cfg.densify_seed + done - 1)
         else:
-            loop.run(cfg.iterations)
+            loop.run(cfg.iterations - loop.done)
         res = FitResult()
         res.losses = [float(v) for v in loop.loss_history()[:, 0].cpu()]
         with torch.no_grad():
@@ -372,7 +408,8 @@ class NativeFitLoop:
 
     def __init__(self, fitter: "FrameFitter", gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor], cfg: FitConfig,
                  pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None,
-                 capacity: Optional[int] = None, debug: bool = False, prev: Optional[PrevFrame] = None):
+                 capacity: Optional[int] = None, debug: bool = False, prev: Optional[PrevFrame] = None,
+                 tentative_still: Optional[torch.Tensor] = None, sub_capacity: Optional[int] = None):
         dev = fitter.attrs["xyz"].device
         self._require_device(dev)
         self.lib = self._library()
@@ -396,6 +433,19 @@ class NativeFitLoop:
         self.still_mask = None if still_mask is None else still_mask.to(dev).to(torch.uint8).contiguous()
         if self.still_mask is not None and self.still_mask.numel() > self.N:
             raise RuntimeError("gflow_b200: still_mask is longer than the number of Gaussians")
+        # camera-only stage: compact raw copy of the moving subset (attributes are frozen in this stage), the
+        # cumulative pixel mask it carves, and a workspace for its per-iteration render
+        self.sub = self.dyn_mask = self.sub_ws = None
+        self.sub_N = self.sub_capacity = 0
+        if cfg.camera_only and tentative_still is not None:
+            n = tentative_still.shape[0]
+            sel = ~tentative_still.to(dev).bool()
+            if int(sel.sum()) > 0:
+                self.sub = {k: fitter.attrs[k].data[:n][sel].contiguous() for k in ATTRS}
+                self.sub_N = int(self.sub["xyz"].shape[0])
+                self.sub_capacity = int(sub_capacity) if sub_capacity is not None else 8 * self.sub_N + 16384
+                self.dyn_mask = (torch.ones(self.H, self.W, dtype=torch.uint8, device=dev) if self.pixel_mask is None
+                                 else self.pixel_mask.clone())
         # loss_scale runs over the still (camera-only) / moving (full stage) Gaussians once a still mask exists
         self.scale_sel = None
         if cfg.lambda_scale and self.still_mask is not None:
@@ -466,6 +516,14 @@ class NativeFitLoop:
         pr.pixel_mask, pr.still_mask = ops._ptr(self.pixel_mask), ops._ptr(self.still_mask)
         pr.dbg_grads, pr.dbg_act = ops._ptr(self.dbg_grads), ops._ptr(self.dbg_act)
         pr.scale_sel = ops._ptr(self.scale_sel)
+        pr.sub_N, pr.sub_capacity = self.sub_N, self.sub_capacity
+        if self.sub_N > 0:
+            need = self.lib.gfb_fit_sub_workspace_bytes(self.sub_N, self.W, self.H, self.sub_capacity)
+            if self.sub_ws is None or self.sub_ws.numel() != need:
+                self.sub_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+            pr.sub_xyz, pr.sub_scale, pr.sub_rotate = (self.sub[k].data_ptr() for k in ("xyz", "scale", "rotate"))
+            pr.sub_opacity, pr.sub_rgb = self.sub["opacity"].data_ptr(), self.sub["rgb"].data_ptr()
+            pr.dyn_mask, pr.sub_workspace = self.dyn_mask.data_ptr(), self.sub_ws.data_ptr()
         pr.still_ref, pr.still_sel = ops._ptr(self.still_ref), ops._ptr(self.still_sel)
         pr.flow_target, pr.flow_sel = ops._ptr(self.flow_target), ops._ptr(self.flow_sel)
         pr.N, pr.W, pr.H = self.N, self.W, self.H
@@ -491,10 +549,12 @@ class NativeFitLoop:
     def _snapshot(self):
         f = self.fitter
         return ([f.attrs[k].data.clone() for k in ATTRS], f.pose.data.clone(), self.depth_ab.clone(),
-                self.ws[: self.lay.uv].clone(), self.done)
+                self.ws[: self.lay.uv].clone(), self.done, None if self.dyn_mask is None else self.dyn_mask.clone())
 
     def _restore(self, snap) -> None:
-        attrs, pose, ab, head, done = snap
+        attrs, pose, ab, head, done, dyn = snap
+        if dyn is not None:
+            self.dyn_mask.copy_(dyn)
         for k, t in zip(ATTRS, attrs):
             self.fitter.attrs[k].data.copy_(t)
         self.fitter.pose.data.copy_(pose)
@@ -515,11 +575,13 @@ class NativeFitLoop:
                 capi.check(self.lib.gfb_fit_iterate(ctypes.addressof(self.problem), self.ws.data_ptr(), self.capacity,
                                                     self.iters, self.done, n, self._stream()), "fit iterate")
                 self.done += n
-                k_max = int(self._view(self.lay.status, 16, torch.int32)[2])  # synchronises: one read per chunk
-                if k_max > self.capacity:
+                st = self._view(self.lay.status, 16, torch.int32)[:4].tolist()  # synchronises: one read per chunk
+                k_max, sub_k_max = st[2], st[3]
+                if k_max > self.capacity or sub_k_max > self.sub_capacity:
                     self._restore(snap)
-                    self._view(self.lay.status, 16, torch.int32)[2] = 0
-                    self._alloc(int(1.5 * k_max) + 65536)
+                    if sub_k_max > self.sub_capacity:
+                        self.sub_capacity = int(1.5 * sub_k_max) + 16384
+                    self._alloc(int(1.5 * k_max) + 65536 if k_max > self.capacity else self.capacity)
         self.fitter.depth_a.data.copy_(self.depth_ab[0:1])
         self.fitter.depth_b.data.copy_(self.depth_ab[1:2])
 
@@ -567,6 +629,11 @@ class NativeFitLoop:
                                              self._stream()), "fit init after densify")
             self.ws[: self.lay.adam_m].copy_(head)
         return count
+
+    def pixel_keep_mask(self) -> Optional[torch.Tensor]:
+        """(H,W) bool: pixels that still take part in the losses (static mask, or the one the moving subset carved)."""
+        m = self.dyn_mask if self.dyn_mask is not None else self.pixel_mask
+        return None if m is None else m.bool()
 
     def loss_history(self) -> torch.Tensor:
         """(iterations done, 8): total, mse, ssim, depth, var, scale, still, flow per iteration."""

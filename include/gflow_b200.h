@@ -190,11 +190,18 @@ typedef struct gfb_fit_problem {
     const uint8_t *still_sel;    /* (n_still_ref) 1 = Gaussian takes part in loss_still (last_still_mask) */
     const float *flow_target;    /* (n_flow,2) last_uv + gt_flow[last_uv], or NULL: loss_flow (trainer.py:510-530) */
     const uint8_t *flow_sel;     /* (n_flow) 1 = Gaussian takes part in loss_flow (and_mask) */
+    /* camera-only stage on frames >= 1 (trainer.py:427-451): every iteration the MOVING Gaussians (attributes are
+     * frozen in this stage, so the caller passes a compact raw copy) are rendered under the current pose and every
+     * pixel they touch (grey > 0) is removed from the losses, cumulatively.  sub_N = 0 switches this off. */
+    const float *sub_xyz, *sub_scale, *sub_rotate, *sub_opacity, *sub_rgb; /* (sub_N, 3|3|4|1|3) raw */
+    uint8_t *dyn_mask;           /* (H,W) 1 = pixel still counts; read and updated by the kernels; replaces pixel_mask */
+    void *sub_workspace;         /* gfb_fit_sub_workspace_bytes(sub_N, W, H, sub_capacity) */
     float *dbg_grads;            /* NULL, or (N,14) raw-attribute gradients of the last iteration before masking */
     float *dbg_act;              /* NULL, or (N,14) activated attributes of the last iteration */
     int32_t N, W, H, n_still;
     int32_t n_still_ref, still_count; /* still_count = number of 1s in still_sel (the mean's denominator) */
     int32_t n_flow, flow_count;       /* flow_count = number of 1s in flow_sel */
+    int32_t sub_N, sub_capacity;      /* moving subset: Gaussians, intersection capacity of sub_workspace */
     int32_t total_iters;         /* LinearLR horizon (`iterations` of trainer.train) */
     int32_t camera_only;         /* attribute gradients zeroed, pose still optimised (trainer.py:548-551) */
     int32_t freeze_rgb;          /* rgb gradient zeroed (frames >= 1, trainer.py:537-540) */
@@ -214,6 +221,7 @@ typedef struct gfb_fit_problem {
 /* byte offsets of the pieces of the fit workspace a caller may want to read back */
 typedef struct gfb_fit_layout {
     size_t status;      /* int32[16]: [0] iterations done, [1] K of the last iteration, [2] max K seen,
+                           [3] max K of the moving-subset render seen,
                            [8..14] float bits of dL/d(pose) of the last iteration (diagnostics) */
     size_t loss_hist;   /* float[max_iters][8]: total, mse, ssim, depth, var, scale, still, flow per iteration */
     size_t cam;         /* float[16]: extr (3x4) + intr used by the NEXT iteration */
@@ -231,6 +239,7 @@ typedef struct gfb_fit_layout {
 } gfb_fit_layout;
 
 int gfb_fit_get_layout(int N, int W, int H, int64_t capacity, int max_iters, gfb_fit_layout *layout);
+size_t gfb_fit_sub_workspace_bytes(int sub_N, int W, int H, int64_t sub_capacity);
 /* zeroes the Adam state / status / loss history and derives the camera of iteration 0 from the pose */
 int gfb_fit_init(const gfb_fit_problem *problem, void *workspace, int64_t capacity, int max_iters, void *stream);
 /* enqueues iterations [first_iter, first_iter + n_iters) and returns without synchronising.  K is not

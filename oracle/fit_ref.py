@@ -184,9 +184,19 @@ def iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W,
     return loss, parts
 
 
+def moving_footprint(raw, pose, intr, W, H, bg, tentative_still):
+    """trainer.py:427-451: the Gaussians that are NOT tentatively still, rendered (detached) under the current
+    pose; a pixel belongs to the moving footprint when its grey value is > 0."""
+    n = tentative_still.shape[0]
+    sub = {k: raw[k].detach()[:n][~tentative_still] for k in ATTRS}
+    with torch.no_grad():
+        img, _, _, _ = render(sub, pose.detach(), intr, W, H, bg, want_depth=False)
+    return (0.299 * img[0] + 0.587 * img[1] + 0.114 * img[2]) > 0.0
+
+
 def fit_loop(raw0: Dict[str, torch.Tensor], pose0, intr, gt_image, gt_depth, W, H, cfg: FitRefConfig,
              pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None, n_iters=None,
-             record=None, prev=None):
+             record=None, prev=None, tentative_still: Optional[torch.Tensor] = None):
     """Runs `n_iters` (default cfg.iterations) iterations; returns (raw, pose, depth_ab, history).
 
     history[i] = dict(parts of iteration i, grads = raw gradients BEFORE masking, params after the step).
@@ -200,6 +210,9 @@ def fit_loop(raw0: Dict[str, torch.Tensor], pose0, intr, gt_image, gt_depth, W, 
     sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.1, total_iters=cfg.iterations)
     history = []
     for it in range(cfg.iterations if n_iters is None else n_iters):
+        if cfg.camera_only and tentative_still is not None:  # move_mask = move_gs_mask | move_mask, cumulative
+            keep = torch.ones(H, W, dtype=torch.bool) if pixel_mask is None else pixel_mask.bool()
+            pixel_mask = keep & ~moving_footprint(raw, pose, intr, W, H, cfg.background, tentative_still)
         loss, parts = iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W, H, cfg, prev, still_mask)
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -216,7 +229,7 @@ def fit_loop(raw0: Dict[str, torch.Tensor], pose0, intr, gt_image, gt_depth, W, 
                     p.grad.zero_()
         opt.step()
         sched.step()
-        rec = dict(parts, grads=grads, params={k: v.detach().clone() for k, v in raw.items()},
+        rec = dict(parts, grads=grads, pixel_mask=None if pixel_mask is None else pixel_mask.clone(), params={k: v.detach().clone() for k, v in raw.items()},
                    pose=pose.detach().clone(), depth_ab=depth_ab.detach().clone())
         if record is not None:
             record(it, rec)

@@ -65,7 +65,7 @@ def make_prev(sc, raw, pose, W, H, seed):
 
 
 def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=48, seed=0, pixel_mask=None,
-                  still_mask=None, capacity=None, with_prev=False):
+                  still_mask=None, capacity=None, with_prev=False, tentative_still=None):
     """Returns (loop, fitter, raw0, pose0) after `n_iters` checked iterations."""
     sc, raw, pose, gt_image, gt_depth = make_problem(N, W, H, seed)
     prev_ref = prev_dev = None
@@ -81,7 +81,11 @@ def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=
     loop = loop_cls(fitter, gt_image.to(dev), gt_depth.to(dev) if use_depth else None, cfg,
                     pixel_mask=None if pixel_mask is None else pixel_mask.to(dev),
                     still_mask=None if still_mask is None else still_mask.to(dev), capacity=capacity or 40 * N, debug=True,
-                    prev=prev_dev)
+                    prev=prev_dev, tentative_still=None if tentative_still is None else tentative_still.to(dev))
+    dynamic = cfg.camera_only and tentative_still is not None
+    keep = None
+    if dynamic:
+        keep = torch.ones(H, W, dtype=torch.bool) if pixel_mask is None else pixel_mask.clone()
     # shadow optimiser: torch.optim.Adam fed with the KERNEL's gradients
     shadow = {k: raw[k].clone().requires_grad_(True) for k in ATTRS}
     sh_pose = pose.clone().requires_grad_(True)
@@ -94,6 +98,12 @@ def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=
         cur = {k: fitter.attrs[k].data.cpu().clone().requires_grad_(True) for k in ATTRS}
         cur_pose = fitter.pose.data.cpu().clone().requires_grad_(True)
         cur_ab = torch.cat([fitter.depth_a.data.cpu(), fitter.depth_b.data.cpu()]).clone().requires_grad_(True)
+        if dynamic:  # the moving subset's footprint under the current pose leaves the losses, cumulatively
+            foot = FR.moving_footprint({k: v.detach() for k, v in cur.items()}, cur_pose, sc.intr, W, H, cfg.background,
+                                       tentative_still)
+            assert 0 < int(foot.sum()) < H * W
+            keep = keep & ~foot
+            pixel_mask = keep
         loss, parts = FR.iteration_loss(cur, cur_pose, cur_ab, sc.intr, gt_image, gt_depth if use_depth else None,
                                         pixel_mask, W, H, rcfg, prev_ref, still_mask)
         loss.backward()
@@ -114,6 +124,9 @@ def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=
             assert abs(float(h[6]) - float(parts["still"])) <= 1e-5 * float(parts["still"]) + 1e-9
         if rcfg.lambda_flow and with_prev:
             assert abs(float(h[7]) - float(parts["flow"])) <= 1e-4 * float(parts["flow"]) + 1e-9
+        if dynamic:
+            got = loop.pixel_keep_mask().cpu()
+            assert int((got != keep).sum()) <= 2, "pixel mask carved by the moving subset (grey > 0 is a hard threshold)"
         st = loop.status().cpu()
         assert int(st[0]) == it + 1 and 0 < int(st[1]) <= loop.capacity
         # gradients
@@ -167,6 +180,9 @@ def case_list():
                          native=True), dict(n_iters=2, seed=7, with_prev=True, still_mask=torch.rand(300, generator=g) > 0.5)),
         ("camera_only", C(iterations=6, lr=4e-3, lr_camera=2e-3, lambda_depth=0.1, camera_only=True, native=True),
          dict(n_iters=3, seed=5)),
+        ("camera_only_moving_footprint", C(iterations=6, lr=4e-3, lr_camera=2e-3, lambda_depth=0.1, camera_only=True,
+                                           use_ssim=True, native=True),
+         dict(n_iters=3, seed=14, tentative_still=torch.rand(330, generator=g) > 0.15, pixel_mask=torch.rand(48, 64, generator=g) > 0.1)),
         ("masks", C(iterations=6, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, freeze_rgb=True, use_ssim=True, lambda_scale=0.3,
                     native=True),
          dict(n_iters=2, N=N, W=W, H=H, seed=6, pixel_mask=pixel_mask, still_mask=still)),

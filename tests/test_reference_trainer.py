@@ -240,3 +240,51 @@ def test_later_frame_full_stage_matches_the_fit_oracle(reference_trainer, tmp_pa
     n = state["still_mask"].shape[0]
     assert torch.equal(t._attributes["xyz"].detach()[:n][state["still_mask"]], start["xyz"][:n][state["still_mask"]])
     assert torch.allclose(t.pose.detach(), pose, atol=1e-6)
+
+
+def test_later_frame_camera_only_stage_matches_the_fit_oracle(reference_trainer, tmp_path, monkeypatch):
+    """Frame >= 1, camera-only stage (fit_video.py:256-278): attributes frozen, pose optimised, and every iteration the
+    tentatively-moving Gaussians are re-rendered and their footprint leaves the losses (trainer.py:427-455,484)."""
+    ref_trainer, calls = reference_trainer
+    W, H = 48, 32
+    t, img0, depth0, move_mask = _first_frame(ref_trainer, tmp_path, W, H)
+    g = torch.Generator().manual_seed(4)
+    img1 = torch.roll(img0, shifts=1, dims=1).contiguous()
+    depth1 = (depth0 * 1.02).contiguous()
+    gt_flow = torch.zeros(H, W, 2)
+    gt_flow[..., 0] = 1.0 + 0.2 * torch.rand(H, W, generator=g)
+    t.set_gt_image(img1)
+    t.set_gt_depth(depth1)
+    t.set_gt_flow(gt_flow)
+    state = dict(still_mask=t.still_mask.clone(), tentative=t.still_mask_tentative.clone(), last_still_mask=t.last_still_mask.clone(),
+                 last_uv=t.last_uv.clone(), last_xyz=t.last_xyz.clone())
+    start = {k: v.detach().clone() for k, v in t._attributes.items()}
+    pose0 = t.pose.detach().clone()
+    move_mask1 = torch.zeros(H, W, dtype=torch.bool)
+    move_mask1[2:6, 30:40] = True
+    _Bar.posted = []
+    calls.clear()
+    iters = 3
+    lam = dict(lambda_rgb=1.0, lambda_depth=0.1, lambda_flow=0.01)
+    t.train(iterations=iters, lr_camera=2e-3, camera_only=True, move_mask=move_mask1, lambda_var=0.0, lambda_still=0.0,
+            densify_interval=500, densify_times=0, **lam)
+    # two operator chains per iteration: the full set (4 blends) and the moving subset (1 blend)
+    chain = ["project_point", "compute_cov3d", "ewa_project", "sort_gaussian"]
+    assert calls[: 13 * iters] == (chain + ["alpha_blending"] * 4 + chain + ["alpha_blending"]) * iters
+    lr_default = inspect.signature(ref_trainer.SimpleGaussian.train).parameters["lr"].default
+    cfg = FR.FitRefConfig(iterations=iters, lr=lr_default, lr_camera=2e-3, use_ssim=True, depth_den_min=0.0, camera_only=True,
+                          freeze_rgb=True, lambda_var=0.0, lambda_still=0.0, **lam)
+    pr = dict(last_xyz=state["last_xyz"], last_still_mask=state["last_still_mask"], last_uv=state["last_uv"], gt_flow=gt_flow,
+              and_mask=FR.flow_and_mask(state["last_uv"], W, H, state["still_mask"], True))
+    raw, pose, ab, hist = FR.fit_loop(start, pose0, t.intr, img1, depth1, W, H, cfg, pixel_mask=~move_mask1,
+                                      still_mask=state["still_mask"], prev=pr, tentative_still=state["tentative"])
+    for i in range(iters):
+        p, h = _Bar.posted[i], hist[i]
+        assert abs(float(p["total"]) - float(h["total"])) <= 1e-4 * abs(float(h["total"])), (i, p, h["total"])
+        assert abs(float(p["depth"]) - float(h["depth"])) <= 1.5e-6 + 1e-4 * float(h["depth"])
+        assert abs(float(p["flow"]) - float(h["flow"])) <= 1.5e-6 + 1e-4 * float(h["flow"])
+        assert int((~h["pixel_mask"]).sum()) > int(move_mask1.sum()), "the moving footprint widened the mask"
+    assert all(torch.equal(t._attributes[k].detach(), start[k]) for k in FR.ATTRS), "attributes are frozen"
+    assert not torch.equal(t.pose.detach(), pose0)
+    assert torch.allclose(t.pose.detach(), pose, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(torch.cat([t.depth_a.detach(), t.depth_b.detach()]), ab, rtol=1e-4, atol=1e-6)

@@ -152,3 +152,27 @@ def test_train_native_with_densification_schedule(monkeypatch):
     assert len(res.losses) == 7 and all(v == v for v in res.losses)
     n_final = f.attrs["xyz"].shape[0]
     assert n_final > N and all(f.attrs[k].shape[0] == n_final for k in fit.ATTRS)
+
+
+def test_occlusion_densification_after_iteration_zero(monkeypatch):
+    """trainer.py:562-564: on a later frame, Gaussians are drawn uniformly inside the occlusion mask right after
+    iteration 0 and the optimiser is re-created."""
+    monkeypatch.setattr(fit, "NativeFitLoop", emu.fit_loop_class())
+    monkeypatch.setattr(fit.FrameFitter, "render", lambda self, bg=0.0, want_depth=True, with_depth=False: (None, None, None))
+    N, W, H = 300, 64, 48
+    sc, raw, pose, gt_image, gt_depth = fit_check.make_problem(N, W, H, seed=15)
+    prev = fit.PrevFrame(**fit_check.make_prev(sc, raw, pose, W, H, 15))
+    occ = torch.zeros(H, W, 1)
+    occ[10:30, 20:50] = 1.0
+    f = fit.FrameFitter(raw, sc.intr, pose, W, H)
+    cfg = fit.FitConfig(iterations=4, lr=4e-3, lambda_depth=0.1, lambda_flow=0.01, native=True, densify_occ_percent=0.5)
+    res = f.train(gt_image, gt_depth, cfg, prev=prev, occlusion_mask=occ, still_mask=torch.rand(270, generator=torch.Generator().manual_seed(0)) > 0.5)
+    added = f.attrs["xyz"].shape[0] - N
+    assert added == int(N * (600 / (W * H)) * 0.5) and len(res.losses) == 4
+    # the new Gaussians sit inside the mask: project them with the oracle
+    from oracle import fit_ref as FR
+
+    with torch.no_grad():
+        _, _, uv, depth = FR.render({k: f.attrs[k].data for k in fit.ATTRS}, f.pose.data, sc.intr, W, H, 0.0, want_depth=False)
+    u = uv[N:, 0]
+    assert bool(((u > 19.4) & (u < 49.6)).all())
