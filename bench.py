@@ -418,13 +418,15 @@ def run_ours(args):
 def fit_loop_section():
     """BASELINE config 3: 60k Gaussians, 854x480, per-frame Adam loop with rgb + depth loss, iterations/s.
     `operator_path` = msplat operators + autograd + torch.optim.Adam (how gflow/trainer.py drives them);
-    `native` = the same iteration as nine kernels (csrc/fit.cu)."""
+    `native` = the same iteration as nine kernels (csrc/fit.cu); `native_ssim` adds the 1 - SSIM term GFlow's
+    loss_rgb carries (trainer.py:459-462)."""
     import subprocess
 
     out = {"what": "BASELINE config 3: 60k Gaussians, 854x480, per-frame Adam loop (mse + depth loss), iterations/s",
            "unit": "iters/s"}
     tool = os.path.join(ROOT, "tools", "bench_fit.py")
-    for key, extra, iters in (("operator_path", [], 100), ("native", ["--native"], 300)):
+    for key, extra, iters in (("operator_path", [], 100), ("native", ["--native"], 300),
+                              ("native_ssim", ["--native", "--ssim"], 300)):
         try:
             res = subprocess.run([sys.executable, tool, "--iters", str(iters), *extra], capture_output=True, text=True,
                                  timeout=240)

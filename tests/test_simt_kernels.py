@@ -125,3 +125,27 @@ def test_empty_inputs():
     assert r["rc"] == 0 and r["K"] == 0
     assert torch.allclose(r["image"], torch.full_like(r["image"], 0.3))
     assert int(r["tile_range"].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("K", [1, 4, 9, 16])
+def test_compute_sh_matches_oracle(K):
+    """gfb_compute_sh_fwd / bwd (geometry.cu) for degrees 0..3 with a visibility mask and N not a multiple of the CTA."""
+    N, Cn = 517, 3
+    g = torch.Generator().manual_seed(K)
+    shs, dirs = torch.randn(N, Cn, K, generator=g), torch.randn(N, 3, generator=g)
+    vis = torch.rand(N, generator=g) > 0.2
+    g_out = torch.randn(N, Cn, generator=g)
+    L = emu.load()
+    for visible in (None, vis):
+        v8 = None if visible is None else visible.to(torch.uint8)
+        out = emu.f32(N, Cn)
+        emu.ok(L.gfb_compute_sh_fwd(emu.p(shs), emu.p(dirs), emu.p(v8), N, Cn, K, emu.p(out), None), "sh fwd")
+        ref = C.compute_sh(shs, dirs, visible)
+        assert_close(out, ref, 1e-6, "sh forward")
+        d_shs, d_dirs = emu.f32(N, Cn, K), emu.f32(N, 3)
+        emu.ok(L.gfb_compute_sh_bwd(emu.p(shs), emu.p(dirs), emu.p(v8), N, Cn, K, emu.p(g_out), emu.p(d_shs), emu.p(d_dirs), None),
+               "sh bwd")
+        r_shs, r_dirs = C.compute_sh_bwd(shs, dirs, visible, g_out)
+        assert_close(d_shs, r_shs, 1e-5, "d_shs")
+        assert_close(d_dirs, r_dirs, 1e-4, "d_dirs")
+    assert L.gfb_compute_sh_fwd(emu.p(shs), emu.p(dirs), None, N, Cn, 5, emu.p(out), None) == -1
