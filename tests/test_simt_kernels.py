@@ -149,3 +149,42 @@ def test_compute_sh_matches_oracle(K):
         assert_close(d_shs, r_shs, 1e-5, "d_shs")
         assert_close(d_dirs, r_dirs, 1e-4, "d_dirs")
     assert L.gfb_compute_sh_fwd(emu.p(shs), emu.p(dirs), None, N, Cn, 5, emu.p(out), None) == -1
+
+
+def test_randomised_edge_cases():
+    """A bounded slice of the fuzz campaign run during development (500 trials, none failing): tiny / odd image sizes
+    (down to 1x1), N = 1, splats covering the whole frame, opacities 0 / 1 / 0.003 / 0.999, flat Gaussians, mostly
+    culled scenes, 1-4 channels, all three thread schedules -- operator chain and fused pipeline against the oracle."""
+    import random
+
+    rnd = random.Random(1234)
+    for trial in range(24):
+        N = rnd.choice([1, 2, 7, 33, 100, 257, 600])
+        W, H = rnd.choice([1, 5, 16, 17, 31, 48, 64, 100]), rnd.choice([1, 3, 16, 20, 33, 47])
+        seed, bg = rnd.randrange(10000), rnd.choice([0.0, 0.5, 1.0])
+        sc = make_scene(N, W, H, seed=seed, profile=rnd.choice(["synthetic", "gflow"]), bg=bg,
+                        outside_frac=rnd.choice([0.0, 0.05, 0.5]))
+        mode = rnd.choice(["plain", "huge", "opaque", "transparent", "mixed", "flat"])
+        g = torch.Generator().manual_seed(seed)
+        if mode == "huge":
+            sc.scale = sc.scale * 30
+        elif mode == "opaque":
+            sc.opacity = torch.full_like(sc.opacity, 0.999)
+        elif mode == "transparent":
+            sc.opacity = torch.full_like(sc.opacity, 0.003)
+        elif mode == "mixed":
+            sc.opacity = torch.where(torch.rand(N, 1, generator=g) < 0.5, torch.zeros(N, 1), torch.ones(N, 1))
+            sc.scale = sc.scale * torch.where(torch.rand(N, 1, generator=g) < 0.3, 40.0, 1.0)
+        elif mode == "flat":
+            sc.scale[:, 2] = 1e-9
+        Cn = rnd.choice([1, 2, 3, 4])
+        feat = torch.rand(N, Cn, generator=g)
+        Gimg = make_grad_image(Cn, W, H, seed=seed + 1)
+        emu.set_schedule(rnd.choice([0, 1, 2]), seed)
+        try:
+            o = _oracle(sc, Gimg, feat)
+            what = f"trial {trial} N={N} {W}x{H} seed={seed} bg={bg} {mode} C={Cn}"
+            _check(emu.operator_chain(sc, Gimg, feature=feat), o, what + " chain")
+            _check(emu.fused_pipeline(sc, Gimg, feature=feat), o, what + " fused")
+        finally:
+            emu.set_schedule(0)
