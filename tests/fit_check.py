@@ -101,7 +101,6 @@ def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=
         if dynamic:  # the moving subset's footprint under the current pose leaves the losses, cumulatively
             foot = FR.moving_footprint({k: v.detach() for k, v in cur.items()}, cur_pose, sc.intr, W, H, cfg.background,
                                        tentative_still)
-            assert 0 < int(foot.sum()) < H * W
             keep = keep & ~foot
             pixel_mask = keep
         loss, parts = FR.iteration_loss(cur, cur_pose, cur_ab, sc.intr, gt_image, gt_depth if use_depth else None,
@@ -194,6 +193,9 @@ def post_checks(name, loop, fitter, raw0, pose0, kwargs):
     if name == "mse_depth":
         h = loop.loss_history().cpu()
         assert float(h[-1, 0]) < float(h[0, 0]), "the loss goes down"
+    if name == "camera_only_moving_footprint":
+        keep = loop.pixel_keep_mask().cpu()
+        assert 0 < int(keep.sum()) < int(kwargs["pixel_mask"].sum()), "the moving subset carved pixels out of the static mask"
     if name == "camera_only":
         assert all(torch.equal(cur[k], raw0[k]) for k in ATTRS)
         assert not torch.equal(fitter.pose.data.cpu(), pose0)
