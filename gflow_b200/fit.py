@@ -409,10 +409,12 @@ class NativeFitLoop:
     def __init__(self, fitter: "FrameFitter", gt_image: torch.Tensor, gt_depth: Optional[torch.Tensor], cfg: FitConfig,
                  pixel_mask: Optional[torch.Tensor] = None, still_mask: Optional[torch.Tensor] = None,
                  capacity: Optional[int] = None, debug: bool = False, prev: Optional[PrevFrame] = None,
-                 tentative_still: Optional[torch.Tensor] = None, sub_capacity: Optional[int] = None):
+                 tentative_still: Optional[torch.Tensor] = None, sub_capacity: Optional[int] = None, stream=None):
         dev = fitter.attrs["xyz"].device
         self._require_device(dev)
         self.lib = self._library()
+        self.stream = stream  # torch.cuda.Stream this loop enqueues on (None: the current stream at each call)
+        self._pending = None
         self.fitter, self.cfg, self.dev = fitter, cfg, dev
         self.N, self.W, self.H = int(fitter.attrs["xyz"].shape[0]), fitter.W, fitter.H
         if self.N <= 0:
@@ -478,8 +480,8 @@ class NativeFitLoop:
         self._densifier = None
         self.capacity = int(capacity) if capacity is not None else 6 * self.N + 65536
         self.ws = None
-        self._alloc(self.capacity)
-        with self._device_guard():
+        with self._device_guard(), self._stream_guard():
+            self._alloc(self.capacity)  # allocated under the loop's stream: the caching allocator keys blocks by stream
             capi.check(self.lib.gfb_fit_init(ctypes.addressof(self.problem), self.ws.data_ptr(), self.capacity, self.iters,
                                              self._stream()), "fit init")
 
@@ -494,10 +496,16 @@ class NativeFitLoop:
         return capi.load()
 
     def _stream(self) -> int:
-        return ops._stream()
+        return self.stream.cuda_stream if self.stream is not None else ops._stream()
 
     def _device_guard(self):
         return ops._on_device(self.dev)
+
+    def _stream_guard(self):
+        """torch-side copies (snapshots, roll-backs, status reads) must be ordered on the loop's stream too."""
+        import contextlib
+
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     def _alloc(self, capacity: int) -> None:
         lay = capi.FitLayout()
@@ -563,27 +571,58 @@ class NativeFitLoop:
         self.done = done
 
     # ------------------------------------------------------------------ public
+    def enqueue(self, n_iters: Optional[int] = None) -> int:
+        """Enqueues the next chunk (at most cfg.check_every iterations) on this loop's stream and returns without
+        waiting; check() must follow before the next enqueue.  Returns the number of iterations enqueued."""
+        if self._pending is not None:
+            raise RuntimeError("gflow_b200: check() the previous chunk before enqueueing the next one")
+        n = min(max(1, int(self.cfg.check_every)), self.iters - self.done)
+        if n_iters is not None:
+            n = min(n, int(n_iters))
+        if n <= 0:
+            return 0
+        with self._device_guard(), self._stream_guard():
+            snap = self._snapshot()
+            capi.check(self.lib.gfb_fit_iterate(ctypes.addressof(self.problem), self.ws.data_ptr(), self.capacity,
+                                                self.iters, self.done, n, self._stream()), "fit iterate")
+        self.done += n
+        self._pending = snap
+        return n
+
+    def check(self) -> bool:
+        """Waits for the enqueued chunk (one 16-byte read of the status block) and compares the largest
+        intersection counts seen with the workspace capacities.  True: the chunk stands.  False: its tiles were
+        truncated -- parameters, pose, Adam state and pixel mask are back at the chunk start, the workspace has
+        grown, and the chunk has to be enqueued again."""
+        if self._pending is None:
+            return True
+        snap, self._pending = self._pending, None
+        with self._device_guard(), self._stream_guard():
+            st = self._view(self.lay.status, 16, torch.int32)[:4].tolist()  # synchronises this stream
+            k_max, sub_k_max = st[2], st[3]
+            if k_max <= self.capacity and sub_k_max <= self.sub_capacity:
+                return True
+            self._restore(snap)
+            if sub_k_max > self.sub_capacity:
+                self.sub_capacity = int(1.5 * sub_k_max) + 16384
+            self._alloc(int(1.5 * k_max) + 65536 if k_max > self.capacity else self.capacity)
+        return False
+
+    def finish(self) -> None:
+        """Copies depth_a / depth_b back into the fitter's parameters (they live in one 2-float device tensor)."""
+        with self._device_guard(), self._stream_guard():
+            self.fitter.depth_a.data.copy_(self.depth_ab[0:1])
+            self.fitter.depth_b.data.copy_(self.depth_ab[1:2])
+
     def run(self, n_iters: int) -> None:
-        """Enqueues `n_iters` iterations in chunks of cfg.check_every.  After each chunk the largest
-        intersection count seen is compared with the workspace capacity; a chunk that overflowed is
-        rolled back and redone with a larger workspace (its tiles were truncated)."""
+        """Runs `n_iters` iterations in chunks of cfg.check_every.  After each chunk the largest intersection
+        count seen is compared with the workspace capacity; a chunk that overflowed is rolled back and redone with
+        a larger workspace (its tiles were truncated)."""
         end = min(self.iters, self.done + int(n_iters))
-        with self._device_guard():
-            while self.done < end:
-                n = min(max(1, int(self.cfg.check_every)), end - self.done)
-                snap = self._snapshot()
-                capi.check(self.lib.gfb_fit_iterate(ctypes.addressof(self.problem), self.ws.data_ptr(), self.capacity,
-                                                    self.iters, self.done, n, self._stream()), "fit iterate")
-                self.done += n
-                st = self._view(self.lay.status, 16, torch.int32)[:4].tolist()  # synchronises: one read per chunk
-                k_max, sub_k_max = st[2], st[3]
-                if k_max > self.capacity or sub_k_max > self.sub_capacity:
-                    self._restore(snap)
-                    if sub_k_max > self.sub_capacity:
-                        self.sub_capacity = int(1.5 * sub_k_max) + 16384
-                    self._alloc(int(1.5 * k_max) + 65536 if k_max > self.capacity else self.capacity)
-        self.fitter.depth_a.data.copy_(self.depth_ab[0:1])
-        self.fitter.depth_b.data.copy_(self.depth_ab[1:2])
+        while self.done < end:
+            self.enqueue(end - self.done)
+            self.check()  # False: rolled back, self.done is at the chunk start again and the loop re-enqueues it
+        self.finish()
 
     def _make_densifier(self):
         return _densify.Densifier(self.W, self.H, self.dev)
@@ -601,7 +640,9 @@ class NativeFitLoop:
         if self._densifier is None:
             self._densifier = self._make_densifier()
         d, f = self._densifier, self.fitter
-        with self._device_guard():
+        if self._pending is not None:
+            raise RuntimeError("gflow_b200: check() the enqueued chunk before densifying")
+        with self._device_guard(), self._stream_guard():
             if uniform_error:
                 err = torch.ones(self.H, self.W, dtype=torch.float32, device=self.dev)
             else:
@@ -654,8 +695,37 @@ class NativeFitLoop:
         return self._view(self.lay.out, C * self.H * self.W).reshape(C, self.H, self.W)
 
 
+def fit_frames_concurrently(fitters, targets, cfg: FitConfig, streams=None, loop_cls=None):
+    """Runs the native loop of several independent frames of ONE GPU side by side, each on its own CUDA stream.
+
+    A 60k-Gaussian / 480p iteration under-fills a B200 (1620 tiles against 148 SMs x several resident CTAs, and a
+    tail of small per-Gaussian kernels and one-warp kernels), so kernels of different frames are left to overlap:
+    chunks are enqueued round-robin without waiting, then checked in the same order (one status read each).
+    `fitters[i]` is trained against `targets[i] = (gt_image, gt_depth_or_None)`.  Returns the loops (loss
+    histories, final state).  No densification in this mode."""
+    loop_cls = loop_cls or NativeFitLoop
+    if streams is None:
+        streams = [torch.cuda.Stream(device=f.attrs["xyz"].device) for f in fitters]
+        cur = torch.cuda.current_stream(fitters[0].attrs["xyz"].device)
+        for s_ in streams:  # the fitters' tensors were produced on the current stream
+            s_.wait_stream(cur)
+    loops = [loop_cls(f, gi, gd, cfg, stream=s_) for f, (gi, gd), s_ in zip(fitters, targets, streams)]
+    while any(lp.done < lp.iters for lp in loops):
+        for lp in loops:
+            lp.enqueue()
+        for lp in loops:
+            lp.check()  # False = rolled back and grown; the next round re-enqueues that chunk
+    for lp in loops:
+        lp.finish()
+    if streams and streams[0] is not None:
+        cur = torch.cuda.current_stream(fitters[0].attrs["xyz"].device)
+        for s_ in streams:
+            cur.wait_stream(s_)
+    return loops
+
+
 def fit_sequence_sharded(state0: Optional[Dict[str, torch.Tensor]], intr: torch.Tensor, frame_targets, W: int, H: int,
-                         cfg: FitConfig, device: torch.device):
+                         cfg: FitConfig, device: torch.device, concurrent_frames: int = 1):
     """Frame-sharded sequence fit: every rank fits its own contiguous chunk of frames,
     each frame starting from the broadcast frame-0 state.
 
@@ -663,7 +733,8 @@ def fit_sequence_sharded(state0: Optional[Dict[str, torch.Tensor]], intr: torch.
     is the number of frames; rank 0 passes `state0` (activated attributes are NOT expected: raw
     parameters as in the checkpoint), other ranks pass None.  Collectives: one broadcast before the
     loop, one all_gather after it.  Returns (local results keyed by frame index, gathered final frames
-    on rank 0).
+    on rank 0).  With cfg.native and concurrent_frames > 1 a rank works on that many of its frames at a time,
+    one CUDA stream each (fit_frames_concurrently).
     """
     import torch.distributed as dist
 
@@ -672,11 +743,25 @@ def fit_sequence_sharded(state0: Optional[Dict[str, torch.Tensor]], intr: torch.
     mine = _frames.shard_frames(len(frame_targets), world, rank)
     results = {}
     last_img, last_pose = None, None
-    for i in mine:
-        gt_image, gt_depth, pose0 = frame_targets(i)
-        fitter = FrameFitter(state, intr.to(device), pose0.to(device), W, H)
-        results[i] = fitter.train(gt_image.to(device), None if gt_depth is None else gt_depth.to(device), cfg)
-        last_img, last_pose = results[i].image, pose_to_extr(results[i].pose)
+    mine = list(mine)
+    group = max(1, int(concurrent_frames)) if (cfg.native and not cfg.densify_interval) else 1
+    for g0 in range(0, len(mine), group):
+        idx = mine[g0:g0 + group]
+        if group == 1:
+            gt_image, gt_depth, pose0 = frame_targets(idx[0])
+            fitter = FrameFitter(state, intr.to(device), pose0.to(device), W, H)
+            results[idx[0]] = fitter.train(gt_image.to(device), None if gt_depth is None else gt_depth.to(device), cfg)
+        else:
+            tg = [frame_targets(i) for i in idx]
+            fitters = [FrameFitter(state, intr.to(device), t[2].to(device), W, H) for t in tg]
+            loops = fit_frames_concurrently(fitters, [(t[0].to(device), None if t[1] is None else t[1].to(device)) for t in tg], cfg)
+            for i, f, lp in zip(idx, fitters, loops):
+                r = FitResult(losses=[float(v) for v in lp.loss_history()[:, 0].cpu()])
+                with torch.no_grad():
+                    r.image, _, r.uv = f.render(cfg.background, want_depth=False)
+                    r.pose = f.pose.detach().clone()
+                results[i] = r
+        last_img, last_pose = results[idx[-1]].image, pose_to_extr(results[idx[-1]].pose)
     gathered = None
     if world > 1:
         if last_img is None:  # a rank without frames still takes part in the collective

@@ -54,6 +54,30 @@ def densification_both_paths():
         assert res.image.shape == (3, 120, 160)
 
 
+def concurrent_frames_on_streams():
+    """Two frames side by side on two CUDA streams follow the same loss curves as one after the other (float
+    atomics reorder sums, so the comparison is a tolerance, not bit equality)."""
+    dev = torch.device("cuda:0")
+    probs = [fit_check.make_problem(N=4000, W=256, H=160, seed=40 + i) for i in range(2)]
+    cfg = fit.FitConfig(iterations=30, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, use_ssim=True, native=True, check_every=8)
+
+    def fitters():
+        return [fit.FrameFitter({k: v.to(dev) for k, v in raw.items()}, sc.intr.to(dev), pose.to(dev), 256, 160)
+                for sc, raw, pose, _, _ in probs]
+
+    alone = []
+    for f, (_, _, _, gi, gd) in zip(fitters(), probs):
+        lp = fit.NativeFitLoop(f, gi.to(dev), gd.to(dev), cfg)
+        lp.run(30)
+        alone.append(lp.loss_history()[:, 0].cpu())
+    loops = fit.fit_frames_concurrently(fitters(), [(p[3].to(dev), p[4].to(dev)) for p in probs], cfg)
+    torch.cuda.synchronize()
+    for a, lp in zip(alone, loops):
+        b = lp.loss_history()[:, 0].cpu()
+        assert torch.allclose(a, b, rtol=2e-2), (a, b)
+        assert abs(float(a[0]) - float(b[0])) <= 1e-4 * float(a[0])
+
+
 def main():
     results = {}
     cases = fit_check.case_list()
@@ -79,6 +103,11 @@ def main():
         results["densification_both_paths"] = "ok"
     except Exception:  # noqa: BLE001
         results["densification_both_paths"] = traceback.format_exc()[-1500:]
+    try:
+        concurrent_frames_on_streams()
+        results["concurrent_frames_on_streams"] = "ok"
+    except Exception:  # noqa: BLE001
+        results["concurrent_frames_on_streams"] = traceback.format_exc()[-1500:]
     print("RESULT " + json.dumps(results), flush=True)
 
 

@@ -176,3 +176,30 @@ def test_occlusion_densification_after_iteration_zero(monkeypatch):
         _, _, uv, depth = FR.render({k: f.attrs[k].data for k in fit.ATTRS}, f.pose.data, sc.intr, W, H, 0.0, want_depth=False)
     u = uv[N:, 0]
     assert bool(((u > 19.4) & (u < 49.6)).all())
+
+
+def test_frames_side_by_side_equal_frames_one_after_the_other():
+    """fit_frames_concurrently: round-robin enqueue / check over several loops (streams are a no-op in the emulation);
+    each frame's result is bit-identical to running it alone, including a roll-back in one of them."""
+    Loop = emu.fit_loop_class()
+    cfg = fit.FitConfig(iterations=5, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, native=True, check_every=2)
+    probs = [fit_check.make_problem(N=200 + 31 * i, W=64, H=48, seed=30 + i) for i in range(3)]
+
+    def fitters():
+        return [fit.FrameFitter(raw, sc.intr, pose, 64, 48) for sc, raw, pose, _, _ in probs]
+
+    alone = fitters()
+    for f, (_, _, _, gi, gd) in zip(alone, probs):
+        Loop(f, gi, gd, cfg, capacity=40 * 300).run(5)
+    together = fitters()
+
+    class SmallFirst(Loop):  # the first workspace is too small: that loop rolls back while the others go on
+        def __init__(self, fitter, gi, gd, cfg, stream=None):
+            super().__init__(fitter, gi, gd, cfg, capacity=150 if fitter is together[1] else 40 * 300, stream=stream)
+
+    loops = fit.fit_frames_concurrently(together, [(p[3], p[4]) for p in probs], cfg, streams=[None, None, None], loop_cls=SmallFirst)
+    assert loops[1].capacity > 150 and all(lp.done == 5 for lp in loops)
+    for a, b in zip(alone, together):
+        for k in fit.ATTRS:
+            assert torch.equal(a.attrs[k].data, b.attrs[k].data)
+        assert torch.equal(a.pose.data, b.pose.data) and torch.equal(a.depth_a.data, b.depth_a.data)

@@ -28,6 +28,7 @@ ap.add_argument("--points", type=int, default=60000)
 ap.add_argument("--fused", action="store_true")
 ap.add_argument("--no-depth", action="store_true")
 ap.add_argument("--native", action="store_true", help="whole iteration in csrc/fit.cu (no autograd / torch.optim)")
+ap.add_argument("--concurrent", type=int, default=1, help="native: frames of one GPU run side by side, one stream each")
 ap.add_argument("--ssim", action="store_true", help="loss_rgb = mse + (1 - SSIM) as in gflow/trainer.py:459-462")
 args = ap.parse_args()
 world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
@@ -75,7 +76,7 @@ if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-results, gathered = fit.fit_sequence_sharded(state0, sc.intr, targets, W, H, cfg, dev)
+results, gathered = fit.fit_sequence_sharded(state0, sc.intr, targets, W, H, cfg, dev, concurrent_frames=args.concurrent)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 if world > 1:
@@ -86,7 +87,7 @@ if rank == 0:
     first = results[min(results)]
     print(json.dumps({"metric": "per-frame Adam loop, frames x iterations / s", "value": args.frames * args.iters / dt,
                       "unit": "iters/s", "n_gpus": world, "frames": args.frames, "iterations": args.iters,
-                      "points": args.points, "resolution": [W, H], "seconds": dt, "fused": args.fused, "native": args.native, "ssim": args.ssim,
+                      "points": args.points, "resolution": [W, H], "seconds": dt, "fused": args.fused, "native": args.native, "ssim": args.ssim, "concurrent_frames": args.concurrent,
                       "depth_loss": not args.no_depth, "loss_first": first.losses[0], "loss_last": first.losses[-1],
                       "frames_per_rank": [len(frames.shard_frames(args.frames, world, r)) for r in range(world)]}))
 if world > 1:

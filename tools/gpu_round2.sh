@@ -27,6 +27,10 @@ for pdl in 0 1; do
   GFB_FIT_PDL=$pdl timeout 300 python tools/bench_fit.py --iters 300 --native > $OUT/fit_cfg3_native_pdl${pdl}_${TAG}.json 2>> $OUT/fit_cfg3_${TAG}.err; cat $OUT/fit_cfg3_native_pdl${pdl}_${TAG}.json
 done
 timeout 300 python tools/bench_fit.py --iters 300 --native --ssim > $OUT/fit_cfg3_native_ssim_${TAG}.json 2>> $OUT/fit_cfg3_${TAG}.err; cat $OUT/fit_cfg3_native_ssim_${TAG}.json
+echo "== frames side by side on one GPU (4 frames, 1 vs 2 vs 4 streams)"
+for c in 1 2 4; do
+  timeout 300 python tools/bench_fit.py --iters 300 --frames 4 --native --concurrent $c > $OUT/fit_concurrent${c}_${TAG}.json 2>> $OUT/fit_cfg3_${TAG}.err; cat $OUT/fit_concurrent${c}_${TAG}.json
+done
 echo "== in-situ kernel times of the native iteration"
 timeout 300 python tools/fit_kernel_times.py 20 > $OUT/fit_kernel_times_${TAG}.txt 2>&1; tail -25 $OUT/fit_kernel_times_${TAG}.txt
 echo "== ncu launch list (bench command)"

@@ -8,3 +8,6 @@ done
 python bench.py --gpus 1 --steps 100 --warmup 10 --no-cpu-baseline > $OUT/scale_${TAG}_n1.json 2> $OUT/scale_${TAG}_n1.err; echo "N=1 rc=$?"; cut -c1-400 $OUT/scale_${TAG}_n1.json
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 tools/bench_fit.py --iters 300 --frames 48 > $OUT/fit_cfg4_${TAG}_n8.json 2> $OUT/fit_cfg4_${TAG}_n8.err; echo "cfg4 N=8 rc=$?"; cat $OUT/fit_cfg4_${TAG}_n8.json
 python tools/bench_fit.py --iters 300 --frames 8 > $OUT/fit_cfg4_${TAG}_n1.json 2> $OUT/fit_cfg4_${TAG}_n1.err; echo "cfg4 N=1 (8 frames) rc=$?"; cat $OUT/fit_cfg4_${TAG}_n1.json
+# the same frame-sharded loop with the native iteration (csrc/fit.cu)
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29612 tools/bench_fit.py --iters 300 --frames 48 --native > $OUT/fit_cfg4_native_${TAG}_n8.json 2> $OUT/fit_cfg4_native_${TAG}_n8.err; echo "cfg4 native N=8 rc=$?"; cat $OUT/fit_cfg4_native_${TAG}_n8.json
+python tools/bench_fit.py --iters 300 --frames 8 --native > $OUT/fit_cfg4_native_${TAG}_n1.json 2> $OUT/fit_cfg4_native_${TAG}_n1.err; echo "cfg4 native N=1 (8 frames) rc=$?"; cat $OUT/fit_cfg4_native_${TAG}_n1.json
