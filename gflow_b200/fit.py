@@ -448,6 +448,10 @@ class NativeFitLoop:
                 self.sub_capacity = int(sub_capacity) if sub_capacity is not None else 8 * self.sub_N + 16384
                 self.dyn_mask = (torch.ones(self.H, self.W, dtype=torch.uint8, device=dev) if self.pixel_mask is None
                                  else self.pixel_mask.clone())
+            elif cfg.background > 0:
+                # an empty moving set renders the bare background, whose grey value is > 0: the reference then
+                # drops EVERY pixel from the losses (trainer.py:446-451)
+                self.pixel_mask = torch.zeros(self.H, self.W, dtype=torch.uint8, device=dev)
         # loss_scale runs over the still (camera-only) / moving (full stage) Gaussians once a still mask exists
         self.scale_sel = None
         if cfg.lambda_scale and self.still_mask is not None:

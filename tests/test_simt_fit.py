@@ -203,3 +203,11 @@ def test_frames_side_by_side_equal_frames_one_after_the_other():
         for k in fit.ATTRS:
             assert torch.equal(a.attrs[k].data, b.attrs[k].data)
         assert torch.equal(a.pose.data, b.pose.data) and torch.equal(a.depth_a.data, b.depth_a.data)
+
+
+def test_empty_moving_subset_with_a_bright_background_masks_everything():
+    """Reference quirk kept: with no tentatively-moving Gaussian the subset render is the bare background, grey > 0 for
+    any background > 0, so every pixel leaves the losses (trainer.py:446-451)."""
+    cfg = fit.FitConfig(iterations=3, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, camera_only=True, background=0.4, native=True)
+    fit_check.run_and_check(emu.fit_loop_class(), "cpu", cfg, n_iters=2, N=60, W=33, H=31, seed=3,
+                            tentative_still=torch.ones(40, dtype=torch.bool))
