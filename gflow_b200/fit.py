@@ -196,7 +196,9 @@ class FitResult:
     losses: List[float] = field(default_factory=list)
     image: Optional[torch.Tensor] = None   # (3,H,W) final render
     pose: Optional[torch.Tensor] = None    # (7,)
-    uv: Optional[torch.Tensor] = None      # (N,2)
+    uv: Optional[torch.Tensor] = None      # (N,2) of the final parameters
+    last_uv: Optional[torch.Tensor] = None     # (N,2) of the LAST iteration's forward (what trainer.py:619-622 keeps)
+    last_depth: Optional[torch.Tensor] = None  # (N,1) likewise
 
 
 class FrameFitter:
@@ -338,6 +340,8 @@ class FrameFitter:
                 if self._densify_operator_path(img.detach(), gt, gt_image, gt_depth, cfg, it):
                     opt = torch.optim.Adam(list(self.attrs.values()), lr=cfg.lr)
         res.losses = [float(v) for v in torch.stack(loss_hist).cpu()] if loss_hist else []
+        if cfg.iterations > 0 and uv is not None:
+            res.last_uv, res.last_depth = uv.detach(), depth.detach()
         with torch.no_grad():
             res.image, _, res.uv = self.render(cfg.background, want_depth=False)
             res.pose = self.pose.detach().clone()
@@ -393,6 +397,8 @@ class FrameFitter:
             loop.run(cfg.iterations - loop.done)
         res = FitResult()
         res.losses = [float(v) for v in loop.loss_history()[:, 0].cpu()]
+        if loop.done > 0:
+            res.last_uv, res.last_depth = loop.last_uv(), loop.last_depth()
         with torch.no_grad():
             res.image, _, res.uv = self.render(cfg.background, want_depth=False)
             res.pose = self.pose.detach().clone()
@@ -674,6 +680,13 @@ class NativeFitLoop:
                                              self._stream()), "fit init after densify")
             self.ws[: self.lay.adam_m].copy_(head)
         return count
+
+    def last_uv(self) -> torch.Tensor:
+        """(N,2) projected centres of the last iteration's forward pass."""
+        return self._view(self.lay.uv, 2 * self.N).reshape(self.N, 2).clone()
+
+    def last_depth(self) -> torch.Tensor:
+        return self._view(self.lay.depth, self.N).reshape(self.N, 1).clone()
 
     def pixel_keep_mask(self) -> Optional[torch.Tensor]:
         """(H,W) bool: pixels that still take part in the losses (static mask, or the one the moving subset carved)."""

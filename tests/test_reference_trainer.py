@@ -288,3 +288,94 @@ def test_later_frame_camera_only_stage_matches_the_fit_oracle(reference_trainer,
     assert not torch.equal(t.pose.detach(), pose0)
     assert torch.allclose(t.pose.detach(), pose, rtol=1e-4, atol=1e-6)
     assert torch.allclose(torch.cat([t.depth_a.detach(), t.depth_b.detach()]), ab, rtol=1e-4, atol=1e-6)
+
+
+def test_two_frame_sequence_bookkeeping_matches_the_reference(reference_trainer, tmp_path, monkeypatch):
+    """gflow_b200.sequence.SequenceFitter (frame loop of fit_video.py:104-349 over the native iteration, here executed
+    through the SIMT shim) against the unmodified reference run the same way: frame 0, then camera-only + full stage on
+    frame 1.  Compared after every stage: the discrete bookkeeping (still / tentative masks), last_uv / last_xyz, the
+    first loss of each stage (it sees the flow warp, the masks and the previous-frame state) and the parameters.
+    The two runs round differently and Adam's early steps are sign-like, so attribute comparisons allow a small fraction
+    of Gaussians with near-zero gradients to differ by a step."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "simt"))
+    import emu
+    from gflow_b200 import fit, sequence
+
+    ref_trainer, calls = reference_trainer
+    W, H, N = 48, 32, 300
+    img0, depth0 = _scene(W, H)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    t = ref_trainer.SimpleGaussian(gt_image=img0, gt_depth=depth0, num_points=N, sequence_path=str(tmp_path / "seq"))
+    t.load_camera(focal=0.6 * W, pp=[W / 2.0, H / 2.0], show=False)
+    t.init_gaussians_from_image(gt_image=img0, gt_depth=depth0, num_points=N)
+    raw0 = {k: v.detach().clone() for k, v in t._attributes.items()}
+    pose0 = t.pose.detach().clone()
+    import utils as ref_utils
+
+    class _Hull:
+        def __init__(self, pts, *a, **k):
+            pass
+
+        def mask(self, w, h):
+            return np.zeros((h, w), dtype=np.float32)
+
+    ref_utils.FastConcaveHull2D = _Hull
+    mm0 = torch.zeros(H, W, dtype=torch.bool)
+    mm0[10:20, 5:25] = True
+    mm1 = torch.zeros(H, W, dtype=torch.bool)
+    mm1[9:19, 7:27] = True
+    g = torch.Generator().manual_seed(5)
+    img1, depth1 = torch.roll(img0, shifts=1, dims=1).contiguous(), (depth0 * 1.02).contiguous()
+    gt_flow = torch.zeros(H, W, 2)
+    gt_flow[..., 0] = 1.0 + 0.2 * torch.rand(H, W, generator=g)
+    lam = dict(lambda_rgb=1.0, lambda_depth=0.1, lambda_var=0.2, lambda_scale=0.05)
+    it0, itc, ita = 3, 2, 3
+    # ---------------- ours (native iteration through the SIMT shim)
+    monkeypatch.setattr(fit, "NativeFitLoop", emu.fit_loop_class())
+    monkeypatch.setattr(fit.FrameFitter, "render", lambda self, bg=0.0, want_depth=True, with_depth=False: (None, None, None))
+    cfg = sequence.SequenceConfig(num_points=N, lr=4e-3, lr_camera=1e-3, iterations_first=it0, lr_after=2e-3, iterations_after=ita,
+                                  camera_first=True, lr_camera_after=2e-3, iterations_camera=itc, densify_interval=0,
+                                  densify_times=0, densify_interval_after=0, densify_times_after=0, lambda_still=0.3,
+                                  lambda_flow=0.01, native=True, **lam)
+    seq = sequence.SequenceFitter(raw0, t.intr, pose0, W, H, cfg)
+
+    def close(a, b, atol, frac=0.03):
+        bad = ((a - b).abs() > atol).any(dim=-1) if a.dim() > 1 else (a - b).abs() > atol
+        return float(bad.float().mean()) <= frac
+
+    def compare(stage):
+        assert torch.equal(seq.still_mask, t.still_mask), stage
+        assert torch.equal(seq.still_mask_tentative, t.still_mask_tentative), stage
+        assert close(seq.last_uv, t.last_uv, 0.05), stage
+        assert close(seq.last_xyz, t.last_xyz, 1e-3), stage
+        for k in FR.ATTRS:
+            assert close(seq.attrs[k], t._attributes[k].detach(), 2e-3), (stage, k)
+        assert torch.allclose(seq.pose, t.pose.detach(), atol=5e-3), stage
+
+    # ---------------- frame 0
+    _Bar.posted = []
+    t.train(iterations=it0, lr=4e-3, lr_camera=1e-3, move_mask=mm0, densify_interval=500, densify_times=0, **lam)
+    ref_first = [float(p["total"]) for p in _Bar.posted]
+    out0 = seq.fit_first(img0, depth0, mm0)
+    assert abs(out0.losses["first"][0] - ref_first[0]) <= 1e-4 * ref_first[0]
+    assert abs(out0.losses["first"][-1] - ref_first[-1]) <= 2e-2 * ref_first[-1]
+    compare("frame 0")
+    # ---------------- frame 1: camera-only, then everything
+    t.set_gt_image(img1)
+    t.set_gt_depth(depth1)
+    t.set_gt_flow(gt_flow)
+    _Bar.posted = []
+    t.train(iterations=itc, lr_camera=2e-3, camera_only=True, move_mask=mm1, lambda_rgb=1.0, lambda_depth=0.1, lambda_var=0.0,
+            lambda_still=0.0, lambda_flow=0.01, densify_interval=500, densify_times=0)
+    ref_cam = [float(p["total"]) for p in _Bar.posted]
+    _Bar.posted = []
+    t.train(iterations=ita, lr=2e-3, lr_camera=0.0, mask=torch.zeros(H, W, 1), move_mask=mm1, lambda_still=0.3, lambda_flow=0.01,
+            densify_interval=500, densify_times=0, **lam)
+    ref_all = [float(p["total"]) for p in _Bar.posted]
+    out1 = seq.fit_next(img1, depth1, gt_flow, mm1, occ_mask=torch.zeros(H, W, 1))
+    assert abs(out1.losses["camera"][0] - ref_cam[0]) <= 2e-2 * ref_cam[0], (out1.losses["camera"], ref_cam)
+    assert abs(out1.losses["all"][0] - ref_all[0]) <= 2e-2 * ref_all[0], (out1.losses["all"], ref_all)
+    assert abs(out1.losses["all"][-1] - ref_all[-1]) <= 3e-2 * ref_all[-1]
+    compare("frame 1")
+    assert seq.state().num_points == N
