@@ -31,6 +31,9 @@ echo "== frames side by side on one GPU (4 frames, 1 vs 2 vs 4 streams)"
 for c in 1 2 4; do
   timeout 300 python tools/bench_fit.py --iters 300 --frames 4 --native --concurrent $c > $OUT/fit_concurrent${c}_${TAG}.json 2>> $OUT/fit_cfg3_${TAG}.err; cat $OUT/fit_concurrent${c}_${TAG}.json
 done
+echo "== fit_video-style sequence (3 frames, shipped hyper-parameters), native vs operator path"
+timeout 600 python tools/bench_sequence.py --frames 3 > $OUT/sequence_native_${TAG}.json 2> $OUT/sequence_${TAG}.err; cat $OUT/sequence_native_${TAG}.json
+timeout 900 python tools/bench_sequence.py --frames 3 --operator --scale 0.2 > $OUT/sequence_operator_${TAG}.json 2>> $OUT/sequence_${TAG}.err; cat $OUT/sequence_operator_${TAG}.json
 echo "== in-situ kernel times of the native iteration"
 timeout 300 python tools/fit_kernel_times.py 20 > $OUT/fit_kernel_times_${TAG}.txt 2>&1; tail -25 $OUT/fit_kernel_times_${TAG}.txt
 echo "== ncu launch list (bench command)"
