@@ -205,3 +205,74 @@ def post_checks(name, loop, fitter, raw0, pose0, kwargs):
         assert torch.equal(cur["rgb"], raw0["rgb"])
         assert torch.equal(cur["xyz"][:n][still], raw0["xyz"][:n][still])
         assert not torch.equal(cur["xyz"][:n][~still], raw0["xyz"][:n][~still])
+
+
+# ----------------------------------------------------------------------------- golden vectors of the reference trainer
+GOLDEN_TRAINER = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden",
+                                            "trainer_stages.npz")
+
+
+def load_trainer_golden():
+    import numpy as np
+
+    z = np.load(GOLDEN_TRAINER)
+    return {k: (torch.from_numpy(z[k]) if z[k].ndim else z[k].item()) for k in z.files}
+
+
+def golden_stage_inputs(G, stage):
+    """(FitConfig, start state, pose, targets, masks, prev) of one recorded stage (tests/golden/make_trainer_golden.py)."""
+    it, lr, lr_cam, l_rgb, l_depth, l_var, l_scale, l_still, l_flow = (float(v) for v in G[f"{stage}/hyper"])
+    later = stage != "first"
+    cfg = fit.FitConfig(iterations=int(it), lr=lr, lr_camera=lr_cam, lambda_rgb=l_rgb, lambda_depth=l_depth, lambda_var=l_var,
+                        lambda_scale=l_scale, lambda_still=l_still, lambda_flow=l_flow, use_ssim=True, native=True,
+                        camera_only=(stage == "camera"), freeze_rgb=later, check_every=int(it))
+    raw = {k: G[f"{stage}/state/{k}"][0].clone() for k in ATTRS}
+    pose = G[f"{stage}/state/pose"][0].clone()
+    img, depth = (G["img1"], G["depth1"]) if later else (G["img0"], G["depth0"])
+    kw = dict(pixel_mask=None, still_mask=None, prev=None, tentative_still=None)
+    if later:
+        kw["still_mask"] = G[f"{stage}/still_mask"].bool()
+        kw["prev"] = dict(last_xyz=G[f"{stage}/last_xyz"], last_still_mask=G[f"{stage}/last_still_mask"].bool(),
+                          last_uv=G[f"{stage}/last_uv"], gt_flow=G["gt_flow"])
+    if stage == "camera":
+        kw["pixel_mask"] = ~G["move_mask1"].bool()
+        kw["tentative_still"] = G["camera/tentative"].bool()
+    return cfg, raw, pose, img, depth, kw
+
+
+def check_native_stage_against_reference_golden(loop_cls, device, stage, loss_rtol=3e-2, attr_atol=2e-3, attr_frac=0.04,
+                                                pose_atol=5e-3):
+    """Runs one whole recorded stage with the native loop from the reference's recorded start and compares with what
+    the UNMODIFIED reference posted / ended with.  Loss of iteration 0 tight (same state); later iterations and final
+    parameters with the slack two differently-rounded Adam trajectories need."""
+    G = load_trainer_golden()
+    W, H = int(G["W"]), int(G["H"])
+    cfg, raw, pose, img, depth, kw = golden_stage_inputs(G, stage)
+    dev = torch.device(device)
+    f = fit.FrameFitter({k: v.to(dev) for k, v in raw.items()}, G["intr"].to(dev), pose.to(dev), W, H)
+    ab0 = G[f"{stage}/state/ab"][0]
+    f.depth_a.data.fill_(float(ab0[0]))
+    f.depth_b.data.fill_(float(ab0[1]))
+    prev = None if kw["prev"] is None else fit.PrevFrame(**{k: v.to(dev) for k, v in kw["prev"].items()})
+    loop = loop_cls(f, img.to(dev), depth.to(dev), cfg, pixel_mask=None if kw["pixel_mask"] is None else kw["pixel_mask"].to(dev),
+                    still_mask=None if kw["still_mask"] is None else kw["still_mask"].to(dev), prev=prev,
+                    tentative_still=None if kw["tentative_still"] is None else kw["tentative_still"].to(dev), capacity=40 * int(G["N"]))
+    loop.run(cfg.iterations)
+    ours = loop.loss_history()[:, 0].cpu().double()
+    ref = G[f"{stage}/posted/total"].double()
+    assert abs(float(ours[0] - ref[0])) <= 3e-4 * abs(float(ref[0])), (stage, ours, ref)
+    assert torch.allclose(ours, ref, rtol=loss_rtol), (stage, ours, ref)
+
+    def close(a, b, atol, frac=attr_frac):
+        bad = ((a - b).abs() > atol).any(dim=-1)
+        return float(bad.float().mean()) <= frac
+
+    for k in ATTRS:
+        assert close(f.attrs[k].data.cpu(), G[f"{stage}/final/{k}"], attr_atol), (stage, k)
+    assert torch.allclose(f.pose.data.cpu(), G[f"{stage}/final/pose"], atol=pose_atol), stage
+    if stage == "camera":
+        assert all(torch.equal(f.attrs[k].data.cpu(), raw[k]) for k in ATTRS)
+        assert not torch.equal(f.pose.data.cpu(), pose)
+    if stage != "first":
+        assert torch.equal(f.attrs["rgb"].data.cpu(), raw["rgb"])
+    return loop

@@ -91,6 +91,13 @@ def main():
             results[name] = "ok"
         except Exception:  # noqa: BLE001
             results[name] = traceback.format_exc()[-1500:]
+    for stage in ("first", "camera", "all"):  # what the unmodified reference loop produced (tests/golden/trainer_stages.npz)
+        try:
+            fit_check.check_native_stage_against_reference_golden(NativeFitLoop, "cuda:0", stage)
+            torch.cuda.synchronize()
+            results[f"reference_golden_{stage}"] = "ok"
+        except Exception:  # noqa: BLE001
+            results[f"reference_golden_{stage}"] = traceback.format_exc()[-1500:]
     try:
         native_vs_operator_path()
         torch.cuda.synchronize()

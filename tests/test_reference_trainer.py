@@ -25,85 +25,18 @@ import torch
 from oracle import fit_ref as FR
 from oracle import splat_ref as R
 
-REF = "/root/reference/gflow"
-pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "trainer.py")), reason="reference sources not mounted")
+pytestmark = pytest.mark.skipif(not os.path.exists("/root/reference/gflow/trainer.py"), reason="reference sources not mounted")
 
 
-def _oracle_msplat(calls):
-    from gflow_b200 import ops
-
-    fake = types.ModuleType("msplat")
-
-    def wrap(name):
-        sig = inspect.signature(getattr(ops, name))
-        impl = getattr(R, name)
-
-        def f(*a, **k):
-            sig.bind(*a, **k)  # raises TypeError if the reference's call does not fit our signature
-            calls.append(name)
-            return impl(*a, **k)
-
-        return f
-
-    for n in ("project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "alpha_blending", "compute_sh"):
-        setattr(fake, n, wrap(n))
-    return fake
-
-
-class _Bar:
-    """tqdm stand-in that records the loss dictionaries the reference posts every iteration (trainer.py:556-557)."""
-    posted = []
-
-    def __init__(self, *a, **k):
-        pass
-
-    def set_postfix(self, d):
-        _Bar.posted.append(dict(d))
-
-    def update(self, n=1):
-        pass
-
-    def close(self):
-        pass
+import ref_harness
+from ref_harness import Bar as _Bar
+from ref_harness import scene as _scene
 
 
 @pytest.fixture()
-def reference_trainer(tmp_path, monkeypatch):
-    import shims
-
-    calls = []
-    added = shims.install()
-    saved = {k: sys.modules.get(k) for k in ("msplat", "utils", "trainer")}
-    sys.modules["msplat"] = _oracle_msplat(calls)
-    for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
-        sys.modules.pop(k)
-    sys.path.insert(0, REF)
-    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
-    monkeypatch.chdir(tmp_path)
-    try:
-        import trainer as ref_trainer  # noqa: the reference module, unmodified
-
-        monkeypatch.setattr(ref_trainer, "tqdm", _Bar)
-        _Bar.posted = []
-        yield ref_trainer, calls
-    finally:
-        sys.path.remove(REF)
-        for k in [k for k in sys.modules if k in ("trainer", "utils") or k.startswith("utils.")] + added:
-            sys.modules.pop(k, None)
-        for k, v in saved.items():
-            if v is not None:
-                sys.modules[k] = v
-            else:
-                sys.modules.pop(k, None)
-
-
-def _scene(W=48, H=32, seed=0):
-    g = torch.Generator().manual_seed(seed)
-    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
-    img = torch.stack([0.5 + 0.5 * torch.sin(9 * xx + 3 * yy), 0.5 + 0.5 * torch.cos(7 * yy), xx * yy], dim=-1)
-    img = (img + 0.05 * torch.rand(H, W, 3, generator=g)).clamp(0.02, 0.98).float()
-    depth = (1.5 + xx + 0.5 * torch.sin(5 * yy)).unsqueeze(-1).float()
-    return img, depth
+def reference_trainer(tmp_path):
+    with ref_harness.reference_trainer(tmp_path) as (mod, calls):
+        yield mod, calls
 
 
 def test_first_frame_stage_runs_unmodified_and_matches_the_fit_oracle(reference_trainer, tmp_path):
@@ -119,17 +52,6 @@ def test_first_frame_stage_runs_unmodified_and_matches_the_fit_oracle(reference_
     pose0 = t.pose.detach().clone()
     move_mask = torch.zeros(H, W, dtype=torch.bool)
     move_mask[10:20, 5:25] = True
-    # the post-training concave hull needs shapely; it is outside the path
-    import utils as ref_utils
-
-    class _Hull:
-        def __init__(self, pts, *a, **k):
-            pass
-
-        def mask(self, w, h):
-            return np.zeros((h, w), dtype=np.float32)
-
-    ref_utils.FastConcaveHull2D = _Hull
     lam = dict(lambda_rgb=1.0, lambda_depth=0.1, lambda_var=0.2, lambda_scale=0.05)
     t.train(iterations=iters, lr=4e-3, lr_camera=1e-3, move_mask=move_mask, densify_interval=500, densify_times=0, **lam)
     # --- the run went through the whole operator surface
@@ -165,16 +87,6 @@ def _first_frame(ref_trainer, tmp_path, W=48, H=32, N=300):
     t.init_gaussians_from_image(gt_image=img, gt_depth=depth, num_points=N)
     move_mask = torch.zeros(H, W, dtype=torch.bool)
     move_mask[10:20, 5:25] = True
-    import utils as ref_utils
-
-    class _Hull:
-        def __init__(self, pts, *a, **k):
-            pass
-
-        def mask(self, w, h):
-            return np.zeros((h, w), dtype=np.float32)
-
-    ref_utils.FastConcaveHull2D = _Hull
     t.train(iterations=2, lr=4e-3, lr_camera=1e-3, lambda_rgb=1.0, lambda_depth=0.1, move_mask=move_mask, densify_interval=500,
             densify_times=0)
     return t, img, depth, move_mask
@@ -311,16 +223,6 @@ def test_two_frame_sequence_bookkeeping_matches_the_reference(reference_trainer,
     t.init_gaussians_from_image(gt_image=img0, gt_depth=depth0, num_points=N)
     raw0 = {k: v.detach().clone() for k, v in t._attributes.items()}
     pose0 = t.pose.detach().clone()
-    import utils as ref_utils
-
-    class _Hull:
-        def __init__(self, pts, *a, **k):
-            pass
-
-        def mask(self, w, h):
-            return np.zeros((h, w), dtype=np.float32)
-
-    ref_utils.FastConcaveHull2D = _Hull
     mm0 = torch.zeros(H, W, dtype=torch.bool)
     mm0[10:20, 5:25] = True
     mm1 = torch.zeros(H, W, dtype=torch.bool)

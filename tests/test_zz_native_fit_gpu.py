@@ -18,7 +18,7 @@ import fit_check
 pytestmark = [pytest.mark.gpu,
               pytest.mark.xfail(strict=False, reason="native fit kernels: first hardware run pending (CPU-emulated parity green)")]
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = [c[0] for c in fit_check.case_list()] + ["native_vs_operator_path", "densification_both_paths",
+CASES = [c[0] for c in fit_check.case_list()] + ["reference_golden_first", "reference_golden_camera", "reference_golden_all"] + ["native_vs_operator_path", "densification_both_paths",
                                                   "concurrent_frames_on_streams"]
 
 
