@@ -49,8 +49,8 @@ def test_fit_oracle_reproduces_every_posted_loss(stage):
 @pytest.mark.parametrize("stage", STAGES)
 def test_native_loop_reproduces_the_recorded_stage(stage):
     # the emulated kernels follow the reference's trajectory to ~1e-6; the GPU run uses the function's looser defaults
-    fit_check.check_native_stage_against_reference_golden(emu.fit_loop_class(), "cpu", stage, loss_rtol=1e-4, attr_atol=1e-4,
-                                                          attr_frac=0.02, pose_atol=1e-5)
+    fit_check.check_native_stage_against_reference_golden(emu.fit_loop_class(), "cpu", stage, loss_rtol=1e-4, attr_atol=1e-3,
+                                                          attr_frac=0.0, pose_atol=1e-5)
 
 
 def test_flow_warp_reproduces_the_reference_pre_update():
