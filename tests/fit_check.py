@@ -7,6 +7,8 @@ Every iteration is checked at the kernel's own current parameters, so the compar
   * raw-attribute gradients (before masking), dL/d(pose) and the depth_a / depth_b update against autograd,
   * the in-kernel Adam + LinearLR update against torch.optim.Adam fed with the kernel's gradients.
 """
+import os
+
 import torch
 
 from conftest import assert_close
@@ -208,8 +210,7 @@ def post_checks(name, loop, fitter, raw0, pose0, kwargs):
 
 
 # ----------------------------------------------------------------------------- golden vectors of the reference trainer
-GOLDEN_TRAINER = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden",
-                                            "trainer_stages.npz")
+GOLDEN_TRAINER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trainer_stages.npz")
 
 
 def load_trainer_golden():
