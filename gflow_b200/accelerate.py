@@ -1,0 +1,173 @@
+"""Hands the optimisation stages of an UNMODIFIED GFlow trainer to the native loop.
+
+`patch(trainer_module)` replaces `SimpleGaussian.train` (/root/reference/gflow/trainer.py:332-711) with an adapter
+that keeps its signature, its side effects on the trainer object and its return tuple, but runs the iterations in
+csrc/fit.cu instead of ~150 PyTorch launches each:
+
+  pre-update flow warp (trainer.py:348-376)      -> fit.warp_moving_by_flow
+  optimisation loop (trainer.py:387-571)         -> fit.FrameFitter.train(native=True)  [losses, masks, densify, Adam]
+  post-update bookkeeping (trainer.py:587-625)   -> still / tentative masks, last_uv / last_depth / last_xyz / last_num;
+                                                    the concave hull of the moving centres is computed by the reference's
+                                                    own utils.FastConcaveHull2D when it is importable
+  final renders + checkpoint (trainer.py:627-709) -> the reference's own render.render_multiple / render2img /
+                                                    save_checkpoint; PNG / MP4 dumps and the every-10-iterations video
+                                                    frames are not produced (one frame per stage is returned)
+
+Zero-edit use:   GFLOW_B200_NATIVE_TRAIN=1 PYTHONPATH=<repo>/gflow_b200/dropin:<repo> python gflow/fit_video.py ...
+(the drop-in `msplat` module installs a post-import hook for the module named `trainer`), or call
+`gflow_b200.accelerate.patch(trainer)` yourself after importing it.
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+import torch
+
+from . import fit as _fit
+
+ATTRS = _fit.ATTRS
+
+
+def _as_bool_mask(m, H, W):
+    return None if m is None else (m.reshape(H, W) > 0) if m.dtype != torch.bool else m.reshape(H, W)
+
+
+def native_train(self, iterations=500, lr=1e-2, lr_camera=0., lambda_rgb=1., lambda_depth=0., lambda_flow=0., lambda_var=0.,
+                 lambda_still=0., lambda_scale=0., save_imgs=False, save_videos=False, save_ckpt=False, move_mask=None,
+                 ckpt_name="ckpt", densify_interval=500, densify_times=1, densify_iter=0, grad_threshold=5e-3, mask=None,
+                 camera_only=False, eps=10, min_samples=20, densify_occ_percent=0.1, densify_err_thre=1e-2,
+                 densify_err_percent=0.2):
+    """Same signature and contract as SimpleGaussian.train (trainer.py:332-337)."""
+    W, H = self.W, self.H
+    later = hasattr(self, "last_xyz")
+    has_still = hasattr(self, "still_mask")
+    move_mask = _as_bool_mask(move_mask, H, W)
+    raw = {k: (v.data if isinstance(v, torch.nn.Parameter) else v).detach() for k, v in self._attributes.items()}
+    pose = self.pose.detach()
+    prev = None
+    if later:
+        prev = _fit.PrevFrame(last_xyz=self.last_xyz, last_still_mask=self.last_still_mask, last_uv=self.last_uv,
+                              gt_flow=getattr(self, "gt_flow", None))
+        if not camera_only and has_still:  # pre-update processing
+            raw["xyz"] = _fit.warp_moving_by_flow(raw["xyz"], prev, self.gt_depth, self.intr, _fit.pose_to_extr(pose), W, H)
+    fitter = _fit.FrameFitter(raw, self.intr, pose, W, H)
+    use_densify = bool(densify_interval) and densify_times > 0
+    cfg = _fit.FitConfig(iterations=int(iterations), lr=float(lr), lr_camera=float(lr_camera), lambda_rgb=float(lambda_rgb),
+                         lambda_depth=float(lambda_depth), lambda_var=float(lambda_var), lambda_scale=float(lambda_scale),
+                         lambda_still=float(lambda_still) if has_still else 0.0,
+                         lambda_flow=float(lambda_flow) if hasattr(self, "gt_flow") and later else 0.0,
+                         camera_only=bool(camera_only), freeze_rgb=later, background=float(self.bg), use_ssim=True, native=True,
+                         depth_den_min=0.0, densify_interval=int(densify_interval) if use_densify else 0,
+                         densify_times=int(densify_times), densify_err_thre=float(densify_err_thre),
+                         densify_err_percent=float(densify_err_percent), densify_occ_percent=float(densify_occ_percent),
+                         num_points=int(self.num_points))
+    res = fitter.train(self.gt_image, self.gt_depth, cfg,  # the depth term itself is gated by lambda_depth > 0
+                       pixel_mask=(~move_mask) if (camera_only and move_mask is not None) else None,
+                       still_mask=self.still_mask if has_still else None, prev=prev,
+                       tentative_still=self.still_mask_tentative if (camera_only and hasattr(self, "still_mask_tentative")) else None,
+                       occlusion_mask=mask if (later and not camera_only) else None)
+    # ---- hand the state back the way the reference holds it
+    for k in ATTRS:
+        self._attributes[k] = torch.nn.Parameter(fitter.attrs[k].data).requires_grad_(True)
+    self.pose = torch.nn.Parameter(fitter.pose.data).requires_grad_(True)
+    self.depth_a = torch.nn.Parameter(fitter.depth_a.data)
+    self.depth_b = torch.nn.Parameter(fitter.depth_b.data)
+    self.lr, self.lr_camera = lr, lr_camera
+    self.native_losses = res.losses
+    uv = res.last_uv if res.last_uv is not None else res.uv
+    depth = res.last_depth
+    if uv is not None:
+        self.within_index = (uv[:, 0] > 0) & (uv[:, 0] < W - 1) & (uv[:, 1] > 0) & (uv[:, 1] < H - 1)
+    ref_utils = sys.modules.get("utils")
+    if not camera_only and uv is not None and move_mask is not None:  # post-update processing, trainer.py:587-625
+        within = (uv[:, 0] > 0) & (uv[:, 0] < W - 1) & (uv[:, 1] > 0) & (uv[:, 1] < H - 1)
+        labels = ~move_mask[uv[within][:, 1].long(), uv[within][:, 0].long()]
+        still = torch.ones(uv.shape[0], dtype=torch.bool, device=uv.device)
+        still[within] = labels
+        self.still_mask = still
+        self.still_mask_tentative = still.detach().clone()
+        if hasattr(self, "last_still_mask"):
+            self.still_mask[: self.last_still_mask.shape[0]] = self.last_still_mask
+        moving_uv = uv[within & ~self.still_mask]
+        hull_cls = getattr(ref_utils, "FastConcaveHull2D", None)
+        if moving_uv.size(0) > 5 and hull_cls is not None:
+            try:
+                self.move_seg = (hull_cls(moving_uv).mask(W, H) * 255).astype(np.uint8)
+                import cv2
+
+                self.move_seg_erode = cv2.erode(self.move_seg, np.ones((20, 20), np.uint8), iterations=1)
+            except Exception:  # the hull is visualisation; a missing shapely must not stop the fit
+                pass
+        self.last_still_mask = self.still_mask.detach()
+        self.last_uv = uv.detach()
+        self.last_depth = None if depth is None else depth.detach()
+        self.last_xyz = self.get_attribute("xyz").detach()
+        self.last_num = self.last_xyz.shape[0]
+    # ---- one frame per stage through the reference's own render glue
+    frames, frames_center, frames_depth = [], [], []
+    still_rgb = still_center = move_rgb = move_center = None
+    render = getattr(sys.modules.get(type(self).__module__), "render", None)
+    if render is not None:
+        with torch.no_grad():
+            group = [self.get_attribute("xyz"), self.get_attribute("scale"), self.get_attribute("rotate"),
+                     self.get_attribute("opacity"), self.get_attribute("rgb"), self.intr, self.get_extr(), self.bg, W, H]
+            out = render.render_multiple(group, ["rgb", "depth_map_color", "center"])
+            frames.append(render.render2img(out["rgb"]))
+            frames_depth.append(render.render2img(out["depth_map_color"]))
+            frames_center.append(render.render2img(out["center"]))
+            if hasattr(self, "still_mask"):
+                n = self.still_mask.shape[0]
+                for sel, name in ((self.still_mask, "still"), (~self.still_mask, "move")):
+                    g2 = [self.get_attribute(k)[:n][sel] for k in ATTRS] + [self.intr, self.get_extr(), self.bg, W, H]
+                    o2 = render.render_multiple(g2, ["rgb", "center"])
+                    if name == "still":
+                        still_rgb, still_center = render.render2img(o2["rgb"]), render.render2img(o2["center"])
+                    else:
+                        move_rgb, move_center = render.render2img(o2["rgb"]), render.render2img(o2["center"])
+    if save_ckpt:
+        self.save_checkpoint(ckpt_name=ckpt_name, camera_only=camera_only)
+    return frames, frames_center, frames_depth, still_rgb, still_center, move_rgb, move_center, getattr(self, "move_seg", None)
+
+
+def patch(trainer_module) -> None:
+    """Replaces trainer_module.SimpleGaussian.train with the native adapter (the original stays reachable as
+    SimpleGaussian.train_reference)."""
+    cls = trainer_module.SimpleGaussian
+    if getattr(cls, "_gflow_b200_native", False):
+        return
+    cls.train_reference = cls.train
+    cls.train = native_train
+    cls._gflow_b200_native = True
+
+
+def install_import_hook(module_name: str = "trainer") -> None:
+    """Patches `module_name` right after it is imported (sys.meta_path wrapper), for zero-edit runs."""
+    import importlib.abc
+    import importlib.util
+
+    class _GflowTrainerPatchFinder(importlib.abc.MetaPathFinder):
+        gflow_b200_target = module_name
+
+        def find_spec(self, name, path, target=None):
+            if name != module_name:
+                return None
+            sys.meta_path.remove(self)
+            try:
+                spec = importlib.util.find_spec(name)
+            finally:
+                sys.meta_path.insert(0, self)
+            if spec is None or spec.loader is None:
+                return None
+            orig_exec = spec.loader.exec_module
+
+            def exec_module(module):
+                orig_exec(module)
+                if hasattr(module, "SimpleGaussian"):
+                    patch(module)
+
+            spec.loader.exec_module = exec_module
+            return spec
+
+    if not any(getattr(f, "gflow_b200_target", None) == module_name for f in sys.meta_path):
+        sys.meta_path.insert(0, _GflowTrainerPatchFinder())

@@ -24,3 +24,9 @@ from gflow_b200.ops import (  # noqa: E402,F401
 __all__ = ["project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "alpha_blending", "compute_sh",
            "rasterization"]
 __version__ = "gflow_b200-1.0"
+
+# opt-in: run the optimisation stages of GFlow's trainer in the native loop (gflow_b200/accelerate.py)
+if _os.environ.get("GFLOW_B200_NATIVE_TRAIN") == "1":
+    from gflow_b200 import accelerate as _accelerate
+
+    _accelerate.install_import_hook("trainer")

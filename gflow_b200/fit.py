@@ -109,6 +109,7 @@ class FitConfig:
     lambda_flow: float = 0.0  # trainer.py:510-530 (needs `prev`)
     freeze_rgb: bool = False  # frames >= 1: rgb gradient zeroed (trainer.py:537-540)
     check_every: int = 50  # native path: iterations enqueued between two looks at the intersection count
+    depth_den_min: float = 1e-6  # lower clamp of the depth-loss denominator (0 = the reference's unclamped quotient)
     # error-driven densification, trainer.py:566-571 ((iteration + 1) % interval == 0, at most `times` times)
     densify_interval: int = 0
     densify_times: int = 0
@@ -297,7 +298,8 @@ class FrameFitter:
                 d = self.depth_a * dmap.permute(1, 2, 0) + self.depth_b
                 # (a D + b - D_gt)^2 / (a D + b + D_gt), /root/reference/gflow/trainer.py:476-488; the clamp only
                 # protects pixels where both depths are 0 (uncovered synthetic targets)
-                ld = (d - gt_depth) ** 2 / (d + gt_depth).clamp_min(1e-6)
+                den = d + gt_depth
+                ld = (d - gt_depth) ** 2 / (den.clamp_min(cfg.depth_den_min) if cfg.depth_den_min > 0 else den)
                 if pm is not None:
                     ld = ld * pm[..., None]
                 loss = loss + cfg.lambda_depth * torch.mean(ld)
@@ -558,7 +560,7 @@ class NativeFitLoop:
         pr.lambda_rgb, pr.lambda_depth = float(c.lambda_rgb), float(c.lambda_depth if self.use_depth else 0.0)
         pr.lambda_var, pr.lambda_scale = float(c.lambda_var), float(c.lambda_scale)
         pr.beta1, pr.beta2, pr.eps = 0.9, 0.999, 1e-8
-        pr.depth_den_min = 1e-6
+        pr.depth_den_min = float(c.depth_den_min)
         self.problem = pr
 
     def _view(self, off: int, count: int, dtype=torch.float32) -> torch.Tensor:

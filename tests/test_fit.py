@@ -72,3 +72,28 @@ def test_fit_recovers_colour_and_pose_gradient_flows():
     assert all(torch.equal(before[k], f.attrs[k].detach()) for k in before)
     assert abs(float(res.pose[4] - pose[4].to(dev))) < 0.02  # moved back towards the true pose
     assert res.losses[-1] < res.losses[0]
+
+
+def test_accelerate_import_hook_patches_the_trainer_module(tmp_path, monkeypatch):
+    """GFLOW_B200_NATIVE_TRAIN=1: the drop-in msplat module installs a post-import hook that swaps
+    SimpleGaussian.train for the native adapter as soon as GFlow's `trainer` module has been executed."""
+    import importlib
+    import sys
+
+    from gflow_b200 import accelerate
+
+    (tmp_path / "fake_gflow_trainer.py").write_text(
+        "class SimpleGaussian:\n    def train(self, iterations=1):\n        return 'reference loop'\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    before = list(sys.meta_path)
+    try:
+        accelerate.install_import_hook("fake_gflow_trainer")
+        mod = importlib.import_module("fake_gflow_trainer")
+        assert mod.SimpleGaussian.train is accelerate.native_train
+        assert mod.SimpleGaussian.train_reference(mod.SimpleGaussian()) == "reference loop"
+        import json  # unrelated imports are untouched
+
+        assert json.loads("1") == 1
+    finally:
+        sys.meta_path[:] = before
+        sys.modules.pop("fake_gflow_trainer", None)

@@ -281,3 +281,69 @@ def test_two_frame_sequence_bookkeeping_matches_the_reference(reference_trainer,
     assert abs(out1.losses["all"][-1] - ref_all[-1]) <= 3e-2 * ref_all[-1]
     compare("frame 1")
     assert seq.state().num_points == N
+
+
+def test_patched_trainer_runs_its_stages_natively_and_keeps_the_reference_state(reference_trainer, tmp_path, monkeypatch):
+    """gflow_b200.accelerate.patch(trainer): SimpleGaussian.train keeps its signature, side effects and return tuple but
+    the iterations run in csrc/fit.cu (here through the SIMT shim).  Two trainers from the same initial state, one
+    patched, are driven the way fit_video.py drives them for two frames (first stage; camera-only + full stage)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "simt"))
+    import emu
+    from gflow_b200 import accelerate, fit
+
+    ref_trainer, calls = reference_trainer
+    W, H, N = 48, 32, 300
+    monkeypatch.setattr(fit, "NativeFitLoop", emu.fit_loop_class())
+    monkeypatch.setattr(fit.FrameFitter, "render", lambda self, bg=0.0, want_depth=True, with_depth=False: (None, None, None))
+    t_ref, img0, depth0 = ref_harness.new_trainer(ref_trainer, tmp_path, W, H, N)
+    t_nat, _, _ = ref_harness.new_trainer(ref_trainer, tmp_path, W, H, N)  # same seeds -> same initial state
+    assert all(torch.equal(t_ref._attributes[k], t_nat._attributes[k]) for k in FR.ATTRS)
+    native_train = accelerate.native_train
+    mm0 = torch.zeros(H, W, dtype=torch.bool)
+    mm0[10:20, 5:25] = True
+    mm1 = torch.zeros(H, W, dtype=torch.bool)
+    mm1[9:19, 7:27] = True
+    g = torch.Generator().manual_seed(5)
+    img1, depth1 = torch.roll(img0, shifts=1, dims=1).contiguous(), (depth0 * 1.02).contiguous()
+    gt_flow = torch.zeros(H, W, 2)
+    gt_flow[..., 0] = 1.0 + 0.2 * torch.rand(H, W, generator=g)
+    lam = dict(lambda_rgb=1.0, lambda_depth=0.1, lambda_var=0.2, lambda_scale=0.05)
+
+    def both(**kw):
+        out_ref = t_ref.train(**kw)
+        out_nat = native_train(t_nat, **kw)
+        assert len(out_nat) == len(out_ref) == 8
+        assert out_nat[0][0].shape == (H, W, 3) and out_nat[0][0].dtype == np.uint8
+        return out_ref, out_nat
+
+    def compare(stage, check_masks=True):
+        for k in FR.ATTRS:
+            a, b = t_nat._attributes[k].detach(), t_ref._attributes[k].detach()
+            assert a.shape == b.shape and float(((a - b).abs() > 1e-3).any(dim=1).float().mean()) <= 0.02, (stage, k)
+        assert torch.allclose(t_nat.pose.detach(), t_ref.pose.detach(), atol=1e-4), stage
+        assert torch.allclose(t_nat.depth_a.detach(), t_ref.depth_a.detach(), atol=1e-4), stage
+        if check_masks:
+            assert torch.equal(t_nat.still_mask, t_ref.still_mask) and torch.equal(t_nat.still_mask_tentative, t_ref.still_mask_tentative)
+            assert torch.allclose(t_nat.last_uv, t_ref.last_uv, atol=2e-2) and t_nat.last_num == t_ref.last_num
+            assert torch.allclose(t_nat.last_xyz, t_ref.last_xyz, atol=1e-3)
+
+    both(iterations=3, lr=4e-3, lr_camera=1e-3, move_mask=mm0, densify_interval=500, densify_times=0, save_ckpt=True, ckpt_name="0000",
+         **lam)
+    compare("frame 0")
+    assert os.path.exists(os.path.join(t_nat.dir, "ckpt", "0000.tar")), "the reference's own save_checkpoint ran"
+    for t in (t_ref, t_nat):
+        t.set_gt_image(img1)
+        t.set_gt_depth(depth1)
+        t.set_gt_flow(gt_flow)
+    both(iterations=2, lr_camera=2e-3, camera_only=True, move_mask=mm1, lambda_rgb=1.0, lambda_depth=0.1, lambda_var=0.0, lambda_still=0.0,
+         lambda_flow=0.01, densify_interval=500, densify_times=0)
+    compare("frame 1 camera")
+    out_ref, out_nat = both(iterations=3, lr=2e-3, lr_camera=0.0, mask=torch.zeros(H, W, 1), move_mask=mm1, lambda_still=0.3,
+                            lambda_flow=0.01, densify_interval=500, densify_times=0, **lam)
+    compare("frame 1 all")
+    assert out_nat[3] is not None and out_nat[5] is not None  # still / moving renders exist once a still mask exists
+    # the patch itself
+    accelerate.patch(ref_trainer)
+    assert ref_trainer.SimpleGaussian.train is native_train and hasattr(ref_trainer.SimpleGaussian, "train_reference")
+    ref_trainer.SimpleGaussian.train = ref_trainer.SimpleGaussian.train_reference
+    del ref_trainer.SimpleGaussian.train_reference, ref_trainer.SimpleGaussian._gflow_b200_native
