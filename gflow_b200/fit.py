@@ -382,6 +382,12 @@ class FrameFitter:
 
     def _train_native(self, gt_image, gt_depth, cfg: FitConfig, pixel_mask, still_mask, prev=None,
                       tentative_still=None, occ=None) -> FitResult:
+        if cfg.iterations <= 0:  # nothing to optimise: the reference's loop body simply does not run
+            res = FitResult()
+            with torch.no_grad():
+                res.image, _, res.uv = self.render(cfg.background, want_depth=False)
+                res.pose = self.pose.detach().clone()
+            return res
         loop = NativeFitLoop(self, gt_image, gt_depth, cfg, pixel_mask=pixel_mask, still_mask=still_mask, prev=prev,
                              tentative_still=tentative_still)
         if occ is not None and cfg.iterations > 0:
