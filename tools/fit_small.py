@@ -35,3 +35,23 @@ res = f.train(gt_image, gt_depth, cfg, pixel_mask=(torch.rand(H, W, generator=g)
 torch.cuda.synchronize()
 print("losses", [round(v, 6) for v in res.losses])
 assert all(v == v for v in res.losses)
+if size == "small":
+    # the two other stage kinds: densification between iterations, and a camera-only stage whose moving subset is
+    # re-rendered every iteration (second pipeline pass + fit_move_mask)
+    cfg2 = fit.FitConfig(iterations=6, lr=4e-3, lambda_depth=0.1, native=True, densify_interval=2, densify_times=2,
+                         densify_err_thre=1e-6, densify_err_percent=0.5, check_every=2)
+    f2 = fit.FrameFitter(raw, sc.intr.to(dev), pose, W, H)
+    r2 = f2.train(gt_image, gt_depth, cfg2, prev=prev, occlusion_mask=(torch.rand(H, W, 1, generator=g) > 0.7).float().to(dev),
+                  still_mask=(torch.rand(N - 7, generator=g) > 0.5).to(dev))
+    torch.cuda.synchronize()
+    print("densify: N", N, "->", f2.attrs["xyz"].shape[0], "losses", [round(v, 6) for v in r2.losses])
+    assert f2.attrs["xyz"].shape[0] > N and all(v == v for v in r2.losses)
+    cfg3 = fit.FitConfig(iterations=4, lr_camera=1e-3, lambda_depth=0.1, lambda_flow=0.01, use_ssim=True, camera_only=True,
+                         native=True, check_every=2)
+    f3 = fit.FrameFitter(raw, sc.intr.to(dev), pose, W, H)
+    r3 = f3.train(gt_image, gt_depth, cfg3, prev=prev, pixel_mask=(torch.rand(H, W, generator=g) > 0.1).to(dev),
+                  still_mask=(torch.rand(N - 7, generator=g) > 0.5).to(dev),
+                  tentative_still=(torch.rand(N - 7, generator=g) > 0.2).to(dev))
+    torch.cuda.synchronize()
+    print("camera-only losses", [round(v, 6) for v in r3.losses])
+    assert all(v == v for v in r3.losses)
