@@ -27,6 +27,7 @@ ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--points", type=int, default=60000)
 ap.add_argument("--fused", action="store_true")
 ap.add_argument("--no-depth", action="store_true")
+ap.add_argument("--size", type=int, nargs=2, default=[854, 480], metavar=("W", "H"))
 ap.add_argument("--native", action="store_true", help="whole iteration in csrc/fit.cu (no autograd / torch.optim)")
 ap.add_argument("--concurrent", type=int, default=1, help="native: frames of one GPU run side by side, one stream each")
 ap.add_argument("--ssim", action="store_true", help="loss_rgb = mse + (1 - SSIM) as in gflow/trainer.py:459-462")
@@ -38,7 +39,7 @@ if world > 1:
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", ""):
         os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
-W, H = 854, 480
+W, H = args.size
 sc = make_scene(args.points, W, H, seed=0, profile="gflow")
 raw = {"xyz": sc.xyz, "scale": sc.scale, "rotate": sc.rotate,
        "opacity": fit.inverse_activate("opacity", sc.opacity.clamp(0.02, 0.98)),

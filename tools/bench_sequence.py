@@ -23,9 +23,10 @@ ap.add_argument("--frames", type=int, default=3)
 ap.add_argument("--points", type=int, default=50000)
 ap.add_argument("--operator", action="store_true", help="msplat operators + autograd + torch.optim (default: native kernels)")
 ap.add_argument("--scale", type=float, default=1.0, help="scales every iteration count (quick runs)")
+ap.add_argument("--size", type=int, nargs=2, default=[854, 480], metavar=("W", "H"))
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-W, H = 854, 480
+W, H = args.size
 sc = make_scene(args.points, W, H, seed=0, profile="gflow")
 raw = {"xyz": sc.xyz, "scale": sc.scale, "rotate": sc.rotate,
        "opacity": fit.inverse_activate("opacity", sc.opacity.clamp(0.02, 0.98)),
@@ -44,7 +45,7 @@ def target(i):
     with torch.no_grad():
         img, dmap, _ = f.render(0.0, want_depth=True)
     move = torch.zeros(H, W, dtype=torch.bool, device=dev)
-    move[150:300, 200 + 5 * i:400 + 5 * i] = True
+    move[H // 3:2 * H // 3, W // 4 + 5 * i:W // 2 + 5 * i] = True
     flow = torch.zeros(H, W, 2, device=dev)
     flow[..., 0] = 2.5
     return img.permute(1, 2, 0).contiguous(), dmap.permute(1, 2, 0).contiguous().clamp_min(0.05), flow, move

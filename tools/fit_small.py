@@ -13,7 +13,7 @@ from gflow_b200.synthetic import make_scene  # noqa: E402
 
 size = sys.argv[1] if len(sys.argv) > 1 else "small"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-N, W, H = (60000, 854, 480) if size == "cfg2" else (3001, 200, 120)  # odd N: unaligned tails
+N, W, H = (60000, 854, 480) if size == "cfg2" else ((301, 64, 40) if size == "tiny" else (3001, 200, 120))  # odd N: unaligned tails
 dev = torch.device("cuda:0")
 sc = make_scene(N, W, H, seed=0, profile="gflow" if size == "cfg2" else "synthetic")
 raw = {"xyz": sc.xyz, "scale": sc.scale, "rotate": sc.rotate,
@@ -35,7 +35,7 @@ res = f.train(gt_image, gt_depth, cfg, pixel_mask=(torch.rand(H, W, generator=g)
 torch.cuda.synchronize()
 print("losses", [round(v, 6) for v in res.losses])
 assert all(v == v for v in res.losses)
-if size == "small":
+if size in ("small", "tiny"):
     # the two other stage kinds: densification between iterations, and a camera-only stage whose moving subset is
     # re-rendered every iteration (second pipeline pass + fit_move_mask)
     cfg2 = fit.FitConfig(iterations=6, lr=4e-3, lambda_depth=0.1, native=True, densify_interval=2, densify_times=2,
