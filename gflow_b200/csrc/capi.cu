@@ -2,10 +2,34 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
+
+#ifndef GFB_SIMT_EMU
+#include <nvtx3/nvToolsExt.h>
+#endif
 
 static std::atomic<long long> g_launches{0};
 void gfb_internal_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static bool gfb_nvtx_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GFB_NVTX");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+#ifndef GFB_SIMT_EMU
+GfbRange::GfbRange(const char* name) : on(gfb_nvtx_enabled()) {
+    if (on) nvtxRangePushA(name);
+}
+GfbRange::~GfbRange() {
+    if (on) nvtxRangePop();
+}
+#else
+GfbRange::GfbRange(const char*) : on(gfb_nvtx_enabled()) {}
+GfbRange::~GfbRange() {}
+#endif
 
 namespace {
 // K hand-off: kernels store K straight into mapped pinned host memory (no D2H copy in the stream,

@@ -33,6 +33,17 @@ int gfb_internal_host_sync(int32_t** pinned, int32_t** mapped, cudaEvent_t* ev);
 
 static inline int gfb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// NVTX ranges around the multi-kernel entry points (render forward / backward, one fit iteration), so that
+// `nsys` timelines and `ncu --nvtx --nvtx-include "gfb_fit_iteration/"` can select them.  Header-only NVTX v3: no
+// link dependency, a no-op unless a profiler injects itself; set GFB_NVTX=0 to skip even the calls.
+struct GfbRange {
+    bool on;
+    explicit GfbRange(const char* name);
+    ~GfbRange();
+    GfbRange(const GfbRange&) = delete;
+    GfbRange& operator=(const GfbRange&) = delete;
+};
+
 // control buffer of the fused pipelines (gfb_render_control_bytes): counts[T*R] | ctrl[4] | offsets[T*R + 1]
 enum { GFB_CTRL_DONE = 0, GFB_CTRL_K = 1, GFB_CTRL_WORDS = 4 };
 

@@ -845,6 +845,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
     const FitRegs no_regs{0.0f, 0.0f, nullptr, nullptr, nullptr, 0, 0.0f, nullptr, nullptr, 0, 0.0f};
     int rc;
     for (int it = first_iter; it < first_iter + n_iters; ++it) {
+        const GfbRange nvtx_range("gfb_fit_iteration");
         GFB_TRY(cudaMemsetAsync(counts, 0, ((size_t)T * R + GFB_CTRL_WORDS) * sizeof(int32_t), st));
         fit_preprocess_kernel<<<nblk, kThreads, 0, st>>>(
             p->xyz, p->scale, reinterpret_cast<const float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest,

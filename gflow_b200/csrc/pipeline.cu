@@ -287,6 +287,7 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     if (N > 0 && (!xyz || !scale || !rotate || !opacity || !feature || !uv || !depth || !conic || !radius || !rect_ws))
         return GFB_E_BADARG;
     if (capacity > 0 && (!keys_ws || !gaussian_ids_sorted || !geom_stream || !feat_stream)) return GFB_E_BADARG;
+    const GfbRange nvtx_range("gfb_render_forward");
     cudaStream_t st = (cudaStream_t)stream;
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
     const int R = gfb_tile_replicas(T);
@@ -328,6 +329,7 @@ int gfb_render_backward(const float* xyz, const float* scale, const float* rotat
                         const int32_t* n_contrib, const float* g_out, void* grad_ws, float* d_xyz, float* d_scale,
                         float* d_rotate, float* d_opacity, float* d_feature, void* stream) {
     if (N < 0 || W <= 0 || H <= 0 || C < 1 || C > 4 || capacity < 0 || !grad_ws) return GFB_E_BADARG;
+    const GfbRange nvtx_range("gfb_render_backward");
     cudaStream_t st = (cudaStream_t)stream;
     float* grad_pack = (float*)grad_ws;
     float* d_cam = grad_pack + (size_t)N * 12;
