@@ -252,7 +252,10 @@ class FrameFitter:
         inside it right after iteration 0 (trainer.py:562-564).  Returns per-iteration losses and the final render."""
         occ = None
         if occlusion_mask is not None and prev is not None and not cfg.camera_only and bool((occlusion_mask > 0).any()):
-            occ = (occlusion_mask > 0).reshape(self.H, self.W)
+            om = occlusion_mask > 0
+            if om.dim() == 3:  # (H,W,1) from the reference's image reader, or an RGB mask image
+                om = om.any(dim=-1)
+            occ = om.reshape(self.H, self.W)
         if cfg.native:
             return self._train_native(gt_image, gt_depth, cfg, pixel_mask, still_mask, prev, tentative_still, occ)
         dynamic = cfg.camera_only and tentative_still is not None
