@@ -407,7 +407,7 @@ fit_loss_kernel(const float* __restrict__ out, int C, const float* __restrict__ 
             const float D = out[3 * P + pix], gd = gt_depth[pix];
             const float d = a * D + b, e = d - gd, den = d + gd;
             float l, dl;
-            if (den >= den_min) {  // den_min = 0: the reference's unclamped quotient
+            if (den_min <= 0.0f || den >= den_min) {  // den_min = 0: the reference's unclamped quotient, whatever its sign
                 l = e * e / den;
                 dl = (2.0f * e * den - e * e) / (den * den);
             } else {

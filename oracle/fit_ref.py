@@ -148,7 +148,8 @@ def iteration_loss(raw, pose, depth_ab, intr, gt_image, gt_depth, pixel_mask, W,
     loss = cfg.lambda_rgb * loss_rgb
     if use_depth:
         d = depth_ab[0] * dmap.permute(1, 2, 0) + depth_ab[1]
-        ld = (d - gt_depth) ** 2 / (d + gt_depth).clamp_min(cfg.depth_den_min)
+        den = d + gt_depth
+        ld = (d - gt_depth) ** 2 / (den.clamp_min(cfg.depth_den_min) if cfg.depth_den_min > 0 else den)
         if pixel_mask is not None:
             ld = ld * pixel_mask.to(ld.dtype)[..., None]
         ld = ld.mean()
