@@ -126,7 +126,8 @@ def run_and_check(loop_cls, device, cfg: fit.FitConfig, n_iters, N=350, W=64, H=
         if rcfg.lambda_flow and with_prev:
             assert abs(float(h[7]) - float(parts["flow"])) <= 1e-4 * float(parts["flow"]) + 1e-9
         if dynamic:
-            got = loop.pixel_keep_mask().cpu()
+            got = loop.pixel_keep_mask()
+            got = torch.ones(H, W, dtype=torch.bool) if got is None else got.cpu()  # None: nothing is masked
             assert int((got != keep).sum()) <= 2, "pixel mask carved by the moving subset (grey > 0 is a hard threshold)"
         st = loop.status().cpu()
         assert int(st[0]) == it + 1 and 0 < int(st[1]) <= loop.capacity
