@@ -3,7 +3,10 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round2.sh r20'
 # Order: established parity tests first, then the new kernels under compute-sanitizer on a tiny case, then
 # their parity runner (PDL off / on), then benches, then ncu.  Everything lands in gpurun_out/.
+# A second argument ("quick") stops after the parity runner and the bench line (about 10 minutes of box time); the
+# whole script needs about 25.
 TAG=${1:-r20}
+QUICK=${2:-}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,memory.total --format=csv > $OUT/gpu_${TAG}.txt 2>&1
@@ -21,6 +24,7 @@ for pdl in 0 1; do
   grep RESULT $OUT/fit_parity_pdl${pdl}_${TAG}.log | cut -c1-1500
 done
 echo "== bench"; timeout 900 python bench.py --steps 100 --warmup 10 > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err; echo "bench rc=$?"; cat $OUT/bench_${TAG}.json; tail -3 $OUT/bench_${TAG}.err
+if [ -n "$QUICK" ]; then ls -la $OUT | tail -20; exit 0; fi
 echo "== config 3 loop: operator path / native (PDL off, on) / native + SSIM"
 timeout 300 python tools/bench_fit.py --iters 100 > $OUT/fit_cfg3_operator_${TAG}.json 2> $OUT/fit_cfg3_${TAG}.err; cat $OUT/fit_cfg3_operator_${TAG}.json
 for pdl in 0 1; do
