@@ -38,6 +38,14 @@ done
 echo "== fit_video-style sequence (3 frames, shipped hyper-parameters), native vs operator path"
 timeout 600 python tools/bench_sequence.py --frames 3 > $OUT/sequence_native_${TAG}.json 2> $OUT/sequence_${TAG}.err; cat $OUT/sequence_native_${TAG}.json
 timeout 900 python tools/bench_sequence.py --frames 3 --operator --scale 0.2 > $OUT/sequence_operator_${TAG}.json 2>> $OUT/sequence_${TAG}.err; cat $OUT/sequence_operator_${TAG}.json
+echo "== experimental backward variant GFB_BWD_SPARSE (0 = default): parity subset + bench, synthetic and gflow-like scenes"
+for k in 2 4 8; do
+  GFB_BWD_SPARSE=$k timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -p no:cacheprovider -k "blend or render or raster or golden" > $OUT/pytest_sparse${k}_${TAG}.log 2>&1; echo "sparse=$k parity rc=$?"; tail -2 $OUT/pytest_sparse${k}_${TAG}.log
+done
+for prof in synthetic gflow; do for k in 0 2 4 8; do
+  GFB_BWD_SPARSE=$k timeout 300 python bench.py --steps 100 --warmup 10 --profile $prof --no-cpu-baseline --no-fit-loop > $OUT/bench_sparse${k}_${prof}_${TAG}.json 2>> $OUT/bench_${TAG}.err
+  python -c "import json,sys; d=json.load(open('$OUT/bench_sparse${k}_${prof}_${TAG}.json')); print('$prof sparse=$k', round(d['value'],1), 'it/s  blend_bwd', round(d['roofline']['kernel_ms']*1e3,1), 'us')"
+done; done
 echo "== in-situ kernel times of the native iteration"
 timeout 300 python tools/fit_kernel_times.py 20 > $OUT/fit_kernel_times_${TAG}.txt 2>&1; tail -25 $OUT/fit_kernel_times_${TAG}.txt
 echo "== ncu launch list (bench command)"
