@@ -430,7 +430,8 @@ struct FitMasks {
     int n_still, camera_only, freeze_rgb;
 };
 
-__global__ void __launch_bounds__(kThreads)
+// two CTAs per SM (<= 128 registers, 12 bytes of spill): this kernel waits on ~30 global loads per thread
+__global__ void __launch_bounds__(kThreads, 2)
 fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_raw, float4* __restrict__ rot_raw,
                              float* __restrict__ op_raw, float* __restrict__ rgb_raw, const float* __restrict__ cam,
                              int N, int W, int H, float nearest, float extent, int C,
