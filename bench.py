@@ -418,7 +418,7 @@ def run_ours(args):
 def fit_loop_section():
     """BASELINE config 3: 60k Gaussians, 854x480, per-frame Adam loop with rgb + depth loss, iterations/s.
     `operator_path` = msplat operators + autograd + torch.optim.Adam (how gflow/trainer.py drives them);
-    `native` = the same iteration as nine kernels (csrc/fit.cu); `native_ssim` adds the 1 - SSIM term GFlow's
+    `native` = the same iteration as eight kernels (csrc/fit.cu); `native_ssim` adds the 1 - SSIM term GFlow's
     loss_rgb carries (trainer.py:459-462)."""
     import subprocess
 

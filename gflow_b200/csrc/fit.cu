@@ -4,7 +4,7 @@
 // frame by /root/reference/gflow/fit_video.py:119-142,256-315.  In the reference every iteration is
 // ~150 PyTorch kernel launches plus several host synchronisations (loss.item(), colormap round trip)
 // around five msplat operators; the render itself is a small part of the iteration.  Here the whole
-// iteration is nine launches with no host synchronisation:
+// iteration is eight launches (ten with SSIM) with no host synchronisation:
 //
 //   fit_preprocess      raw attributes -> activations (trainer.py:62-69) + project + cov3d + EWA + tile
 //                       counting + scan (the fused pipeline's preprocess, fed from raw parameters); also
@@ -387,9 +387,18 @@ __global__ void __launch_bounds__(kThreads)
 fit_loss_kernel(const float* __restrict__ out, int C, const float* __restrict__ gt_image,
                 const float* __restrict__ gt_depth, const uint8_t* __restrict__ mask,
                 const float* __restrict__ depth_ab, int W, int H, float w_rgb, float w_depth, float den_min,
-                const float* __restrict__ ssim_grad, float* __restrict__ g_out, float* __restrict__ loss_acc) {
+                const float* __restrict__ ssim_grad, float* __restrict__ g_out, float* __restrict__ loss_acc,
+                uint32_t* __restrict__ zero_a, size_t n_zero_a, uint32_t* __restrict__ zero_b, size_t n_zero_b,
+                size_t zero_b_keep) {
     const size_t P = (size_t)W * H;
     const size_t pix = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    // this kernel sits between the forward and the backward of the iteration, so it also clears what the backward
+    // accumulates into (zero_a: packed gradients + camera gradients) and what the NEXT forward counts into (zero_b:
+    // tile counters + control words; this iteration's binning is over) -- two memset launches less per iteration.
+    // Word zero_b_keep (this iteration's K, read by fit_finish later and overwritten by the next scan) is left alone.
+    for (size_t k = pix; k < n_zero_a; k += (size_t)gridDim.x * kThreads) zero_a[k] = 0u;
+    for (size_t k = pix; k < n_zero_b; k += (size_t)gridDim.x * kThreads)
+        if (k != zero_b_keep) zero_b[k] = 0u;
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // sum r^2, sum depth term, d depth_a, d depth_b
     if (pix < P) {
         const float m = mask ? (mask[pix] ? 1.0f : 0.0f) : 1.0f;
@@ -845,9 +854,11 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
     const uint8_t* loss_mask = use_sub ? p->dyn_mask : p->pixel_mask;
     const FitRegs no_regs{0.0f, 0.0f, nullptr, nullptr, nullptr, 0, 0.0f, nullptr, nullptr, 0, 0.0f};
     int rc;
+    const size_t n_ctrl_words = (size_t)T * R + GFB_CTRL_WORDS, n_grad_words = (size_t)N * 12 + 16;
+    // the tile counters are cleared by fit_loss of the previous iteration; before the first one of a call, here
+    GFB_TRY(cudaMemsetAsync(counts, 0, n_ctrl_words * sizeof(int32_t), st));
     for (int it = first_iter; it < first_iter + n_iters; ++it) {
         const GfbRange nvtx_range("gfb_fit_iteration");
-        GFB_TRY(cudaMemsetAsync(counts, 0, ((size_t)T * R + GFB_CTRL_WORDS) * sizeof(int32_t), st));
         fit_preprocess_kernel<<<nblk, kThreads, 0, st>>>(
             p->xyz, p->scale, reinterpret_cast<const float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest,
             p->extent, C, reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect), op_act,
@@ -891,9 +902,11 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
         }
         fit_loss_kernel<<<gfb_div_up(P, kThreads), kThreads, 0, st>>>(out, C, p->gt_image, p->gt_depth, loss_mask,
                                                                      p->depth_ab, W, H, w_rgb, w_depth, p->depth_den_min,
-                                                                     p->use_ssim ? ssim_grad : nullptr, g_out, loss_acc);
+                                                                     p->use_ssim ? ssim_grad : nullptr, g_out, loss_acc,
+                                                                     reinterpret_cast<uint32_t*>(grad_ws), n_grad_words,
+                                                                     reinterpret_cast<uint32_t*>(counts), n_ctrl_words,
+                                                                     (size_t)T * R + GFB_CTRL_K);
         GFB_CHECK_LAUNCH();
-        GFB_TRY(cudaMemsetAsync(grad_ws, 0, ((size_t)N * 12 + 16) * sizeof(float), st));
         rc = gfb_alpha_blending_bwd(geom, fstream, capacity, ids, tile_range, C, 0, C, p->bg, W, H, final_T, n_contrib,
                                     g_out, grad_ws, stream);
         if (rc) return rc;
