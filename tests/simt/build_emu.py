@@ -203,3 +203,28 @@ if __name__ == "__main__":
     import sys
 
     print(build(force="--force" in sys.argv))
+
+
+SELFCHECK_LIB = os.path.join(BUILD, "libsimt_selfcheck.so")
+
+
+def build_selfcheck() -> str:
+    """tests/simt/selfcheck.cu (kernels that pin the shim's own semantics) -> _build/libsimt_selfcheck.so."""
+    os.makedirs(SRC_OUT, exist_ok=True)
+    src = os.path.join(HERE, "selfcheck.cu")
+    deps = [src, os.path.join(HERE, "simt_emu.h"), os.path.join(HERE, "simt_emu.cpp"), __file__]
+    if os.path.exists(SELFCHECK_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(SELFCHECK_LIB) for d in deps):
+        return SELFCHECK_LIB
+    with open(src) as fh:
+        text = rewrite_launches(fh.read())
+    out = os.path.join(SRC_OUT, "selfcheck.cpp")
+    with open(out, "w") as fh:
+        fh.write(text)
+    with open(os.path.join(SRC_OUT, "cuda_runtime.h"), "w") as fh:
+        fh.write('#pragma once\n#include "simt_emu.h"\n')
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
+           "-I", SRC_OUT, "-I", HERE, out, os.path.join(HERE, "simt_emu.cpp"), "-o", SELFCHECK_LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("selfcheck build failed:\n" + (res.stdout + res.stderr)[-4000:])
+    return SELFCHECK_LIB
