@@ -171,3 +171,46 @@ class SequenceFitter:
         return _ck.FrameState(attributes={k: v.detach() for k, v in self.attrs.items()}, intr=self.intr,
                               extr=_fit.pose_to_extr(self.pose), width=self.W, height=self.H, still_mask=self.still_mask,
                               last_uv=self.last_uv)
+
+
+def fit_video_sharded(state0: Optional[Dict[str, torch.Tensor]], intr: torch.Tensor, pose0: torch.Tensor, num_frames: int,
+                      frame_inputs, W: int, H: int, cfg: SequenceConfig, device):
+    """The frame loop of fit_video.py sharded by frame across the ranks of one box: one NCCL broadcast
+    of the frame-0 Gaussian state at sequence start, no collective inside the loop, one gather of the per-frame
+    outputs (final render + pose) at the end.
+
+    Rank r owns the contiguous chunk frames.shard_frames(num_frames, world, r) and runs it SEQUENTIALLY with the
+    reference's state carry-over inside the chunk (its first frame is fitted like fit_video's frame 0, starting from
+    the broadcast state; the following ones with camera-only + full stages, flow warp and still-mask bookkeeping).
+    Chunks do not see each other -- the reference itself is strictly sequential, so this is a throughput mode.
+
+    frame_inputs(i) -> dict(image (H,W,3), depth (H,W,1), move_mask (H,W) bool[, flow (H,W,2), occ_mask (H,W,1), extr (3,4)]).
+    Returns (outputs of the local frames keyed by frame index, list of (image, extr) per rank on rank 0 or None).
+    """
+    import torch.distributed as dist
+
+    from . import frames as _frames
+
+    world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+    state = _frames.broadcast_state(state0, src=0, device=device) if world > 1 else {k: v.to(device) for k, v in state0.items()}
+    mine = list(_frames.shard_frames(num_frames, world, rank))
+    outputs: Dict[int, FrameOutput] = {}
+    seq = None
+    for j, i in enumerate(mine):
+        fi = frame_inputs(i)
+        to = lambda t: None if t is None else t.to(device)  # noqa: E731
+        if j == 0:
+            seq = SequenceFitter(state, intr.to(device), pose0.to(device), W, H, cfg)
+            if fi.get("extr") is not None:
+                seq.pose = _fit.extr_to_pose(fi["extr"].detach().float().cpu()).to(device)
+            outputs[i] = seq.fit_first(to(fi["image"]), to(fi["depth"]), to(fi["move_mask"]))
+        else:
+            outputs[i] = seq.fit_next(to(fi["image"]), to(fi["depth"]), to(fi["flow"]), to(fi["move_mask"]),
+                                      occ_mask=to(fi.get("occ_mask")), extr=fi.get("extr"))
+    gathered = None
+    if world > 1:
+        last = outputs[mine[-1]] if mine else None
+        img = last.image if last is not None and last.image is not None else torch.zeros(3, H, W, device=device)
+        extr = _fit.pose_to_extr(last.pose) if last is not None else torch.zeros(3, 4, device=device)
+        gathered = _frames.gather_frames(img, extr, dst=0)
+    return outputs, gathered

@@ -162,6 +162,20 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, opt: str = "-O2") -> str:
+    """Builds (or reuses) the emulated library.  Serialised across processes with a file lock: the world-size-2
+    tests load it from two processes at once."""
+    import fcntl
+
+    os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, opt)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, opt: str) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(SRC_OUT, exist_ok=True)

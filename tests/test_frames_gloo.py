@@ -76,3 +76,66 @@ def test_broadcast_and_gather_world2_gloo():
         p.join(timeout=60)
     assert res[0][1] and res[1][1], res
     assert res[0][2] == [0, 1, 2] and res[1][2] == [3, 4]
+
+
+# ----------------------------------------------------------------------------- sharded fit_video loop (world 2, gloo)
+def _seq_worker(rank, world, port, q):
+    """Each rank fits its chunk of a 4-frame synthetic video with SequenceFitter; the native iteration runs through the
+    SIMT shim (no GPU here), the collectives through gloo."""
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.join(here, "simt"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu
+        import fit_check
+        from gflow_b200 import fit, sequence
+
+        fit.NativeFitLoop = emu.fit_loop_class()
+        fit.FrameFitter.render = lambda self, bg=0.0, want_depth=True, with_depth=False: (torch.full((3, self.H, self.W), float(rank)), None, None)
+        W, H, N = 48, 32, 150
+        sc, raw, pose, gt_image, gt_depth = fit_check.make_problem(N, W, H, seed=50)
+        move = torch.zeros(H, W, dtype=torch.bool)
+        move[8:20, 10:30] = True
+        flow = torch.zeros(H, W, 2)
+        flow[..., 0] = 1.0
+
+        def frame_inputs(i):
+            return dict(image=torch.roll(gt_image, shifts=i, dims=1), depth=gt_depth, move_mask=move, flow=flow,
+                        occ_mask=torch.zeros(H, W, 1))
+
+        cfg = sequence.SequenceConfig(num_points=N, iterations_first=2, iterations_camera=1, iterations_after=2, densify_interval=0,
+                                      densify_times=0, densify_interval_after=0, densify_times_after=0, lambda_var=0.1, native=True)
+        outs, gathered = sequence.fit_video_sharded(raw if rank == 0 else None, sc.intr, pose, 4, frame_inputs, W, H, cfg,
+                                                    torch.device("cpu"))
+        ok = sorted(outs) == ([0, 1] if rank == 0 else [2, 3])
+        ok = ok and all(set(o.losses) == ({"first"} if i in (0, 2) else {"camera", "all"}) for i, o in outs.items())
+        ok = ok and all(len(v) > 0 and all(x == x for x in v) for o in outs.values() for v in o.losses.values())
+        if rank == 0:
+            ok = ok and gathered is not None and len(gathered) == world
+            ok = ok and all(float(gathered[r][0].mean()) == float(r) and gathered[r][1].shape == (3, 4) for r in range(world))
+        else:
+            ok = ok and gathered is None
+        q.put((rank, bool(ok)))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+
+        q.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_fit_video_loop_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seq_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res
