@@ -41,8 +41,8 @@ PTX_WRAPPERS = {
     "splat_rcp": "return 1.0f / x;",
     "gfb_pdl_wait": "",
     "gfb_pdl_launch_dependents": "",
-    "red_add_s32": "*p += v;",
-    "red_add_f32": "*p += v;",
+    "red_add_s32": "++gfb_emu_counts[1]; *p += v;",
+    "red_add_f32": "++gfb_emu_counts[1]; *p += v;",
 }
 
 

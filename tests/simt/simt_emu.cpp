@@ -8,6 +8,14 @@
 
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
+unsigned long long gfb_emu_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+extern "C" void gfb_emu_stats(unsigned long long* out) {
+    for (int i = 0; i < 8; ++i) out[i] = gfb_emu_counts[i];
+}
+extern "C" void gfb_emu_stats_reset() {
+    for (int i = 0; i < 8; ++i) gfb_emu_counts[i] = 0;
+}
 
 [[noreturn]] void gfb_emu_fail(const char* what) {
     fprintf(stderr, "simt_emu: %s (block %u,%u,%u thread %u,%u,%u)\n", what, blockIdx.x, blockIdx.y, blockIdx.z,
@@ -108,6 +116,7 @@ void try_complete_warp(Warp& w) {
     w.want = 0;
     ++w.gen;
     ++g_progress;
+    ++gfb_emu_counts[0];
 }
 
 void try_complete_barrier() {
@@ -123,6 +132,7 @@ void try_complete_barrier() {
     c.bar_and = 1;
     ++c.bar_gen;
     ++g_progress;
+    ++gfb_emu_counts[2];
 }
 
 void fiber_exit() {
@@ -164,6 +174,8 @@ void run_cta(dim3 block) {
     const int n = (int)(block.x * block.y * block.z);
     if (n <= 0 || n > kMaxThreads) gfb_emu_fail("bad block size");
     c.nthreads = c.alive = n;
+    ++gfb_emu_counts[4];
+    gfb_emu_counts[5] += (unsigned long long)n;
     c.bar_arrived = c.bar_count = c.bar_or = 0;
     c.bar_and = 1;
     c.bar_gen = 0;
@@ -322,6 +334,7 @@ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
     if (((uintptr_t)dst & 15u) || ((uintptr_t)src & 15u) || (bytes & 15u) || bytes == 0)
         gfb_emu_fail("cp.async.bulk: dst, src and size must be non-zero multiples of 16 bytes");
     Bar& b = bar_of(bar);
+    gfb_emu_counts[3] += bytes;
     memset(dst, 0xff, bytes);  // poison: the data is NOT there until somebody waits on the mbarrier
     b.copies.push_back(Bar::Copy{dst, src, bytes});
 }

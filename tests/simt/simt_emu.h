@@ -98,18 +98,23 @@ static inline void __threadfence_system() {}
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 static inline size_t __cvta_generic_to_global(const void* p) { return (size_t)p; }
 
+// dynamic operation counts of everything launched since the last reset (gfb_emu_stats / gfb_emu_stats_reset):
+// [0] warp collectives (one per warp-level shuffle / vote / reduce), [1] lane-level atomics, [2] CTA barriers (one per
+// CTA-wide barrier), [3] bytes moved by emulated cp.async.bulk, [4] CTAs run, [5] threads run
+extern unsigned long long gfb_emu_counts[8];
+
 // atomics: one OS thread, fibers switch only at collectives, so plain read-modify-write is atomic
 template <class T>
-static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
-static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
-static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
-static inline int atomicSub(int* p, int v) { int o = *p; *p = o - v; return o; }
-static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
-static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
-static inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
-static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
-static inline unsigned atomicMin(unsigned* p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
-static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+static inline T atomicAdd(T* p, T v) { ++gfb_emu_counts[1]; T o = *p; *p = o + v; return o; }
+static inline float atomicAdd(float* p, float v) { ++gfb_emu_counts[1]; float o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int* p, int v) { ++gfb_emu_counts[1]; int o = *p; *p = o + v; return o; }
+static inline int atomicSub(int* p, int v) { ++gfb_emu_counts[1]; int o = *p; *p = o - v; return o; }
+static inline int atomicMax(int* p, int v) { ++gfb_emu_counts[1]; int o = *p; if (v > o) *p = v; return o; }
+static inline int atomicMin(int* p, int v) { ++gfb_emu_counts[1]; int o = *p; if (v < o) *p = v; return o; }
+static inline int atomicExch(int* p, int v) { ++gfb_emu_counts[1]; int o = *p; *p = v; return o; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { ++gfb_emu_counts[1]; unsigned o = *p; *p = o + v; return o; }
+static inline unsigned atomicMin(unsigned* p, unsigned v) { ++gfb_emu_counts[1]; unsigned o = *p; if (v < o) *p = v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { ++gfb_emu_counts[1]; unsigned o = *p; if (v > o) *p = v; return o; }
 
 // ------------------------------------------------------------------ scheduler interface
 namespace gfb_emu {

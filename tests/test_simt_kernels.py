@@ -203,3 +203,14 @@ def test_experimental_sparse_backward_variant_matches_oracle(lanes):
                          capture_output=True, text=True, env=env, cwd=os.path.dirname(here), timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-1000:]
     assert " passed" in res.stdout and "failed" not in res.stdout
+
+
+def test_full_size_config2_fused_pipeline():
+    """BASELINE config 2 at full size (60 000 Gaussians, 854x480, K = 197 461) through the shim: ids / tile_range /
+    per-Gaussian geometry bit-exact, image 1e-4, gradients 1e-3 against the C oracle (about 20 s)."""
+    sc = make_scene(60000, 854, 480, seed=0, profile="synthetic")
+    Gimg = make_grad_image(3, 854, 480)
+    o = _oracle(sc, Gimg)
+    r = emu.fused_pipeline(sc, Gimg, capacity=400000)
+    assert r["rc"] == 0 and r["K"] == 197461
+    _check(r, o, "cfg2 fused pipeline")
