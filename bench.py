@@ -429,7 +429,7 @@ def fit_loop_section():
                               ("native_ssim", ["--native", "--ssim"], 300)):
         try:
             res = subprocess.run([sys.executable, tool, "--iters", str(iters), *extra], capture_output=True, text=True,
-                                 timeout=240)
+                                 timeout=120)
             rec = None
             for ln in res.stdout.splitlines():
                 if ln.startswith("{"):
