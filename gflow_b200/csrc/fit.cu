@@ -30,6 +30,7 @@
 #include "splat_math.cuh"
 
 // pipeline.cu / blend.cu
+bool gfb_tight_tiles();
 int gfb_internal_scatter_sort_pack(const void*, const float*, int, int, int, void*, int64_t, void*, int32_t*,
                                    const float*, const float*, const float*, const float*, int, int32_t*, void*, void*,
                                    void*, bool);
@@ -134,7 +135,7 @@ fit_preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ s
                       float* __restrict__ conic, int32_t* __restrict__ radius, ushort4* __restrict__ rect,
                       float* __restrict__ op_act, float* __restrict__ feat, int32_t* __restrict__ counts,
                       int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int T, int R, FitRegs rg,
-                      float* __restrict__ loss_acc, float* __restrict__ dbg_act) {
+                      float* __restrict__ loss_acc, float* __restrict__ dbg_act, int tight) {
     __shared__ float s_cam[16];
     __shared__ int s_scan[34];
     __shared__ int s_buf[kScanSmemInts];
@@ -172,7 +173,8 @@ fit_preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ s
                 cb2 = -m.b * dinv;
                 cc = m.a * dinv;
                 rad = (int)rf;
-                rc = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+                if (!tight || tighten_rect(u, v, ca, cb2, cc, o, x0, y0, x1, y1))  // GFB_TIGHT_TILES (pipeline.cu)
+                    rc = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
             }
         }
         uv[i] = ok ? make_float2(u, v) : make_float2(0.0f, 0.0f);
@@ -846,6 +848,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                      p->lambda_flow * inv_flow2};
     const int nblk = gfb_div_up(N, kThreads);
     const bool pdl = fit_pdl();
+    const int tight = gfb_tight_tiles() ? 1 : 0;
     // camera-only stage: the moving subset is rendered every iteration and its footprint leaves the losses
     const bool use_sub = p->sub_N > 0 && p->camera_only;
     SubLayout S;
@@ -862,7 +865,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
         fit_preprocess_kernel<<<nblk, kThreads, 0, st>>>(
             p->xyz, p->scale, reinterpret_cast<const float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest,
             p->extent, C, reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect), op_act,
-            feat, counts, offsets, ctrl, T, R, rg, loss_acc, p->dbg_act);
+            feat, counts, offsets, ctrl, T, R, rg, loss_acc, p->dbg_act, tight);
         GFB_CHECK_LAUNCH();
         rc = gfb_internal_scatter_sort_pack(rect, depth, N, W, H, counts, capacity, keys, tile_range, uv, conic, op_act,
                                             feat, C, ids, geom, fstream, stream, pdl);
@@ -879,7 +882,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                 p->sub_N, W, H, p->nearest, p->extent, 3, reinterpret_cast<float2*>(sw + S.uv), (float*)(sw + S.depth),
                 (float*)(sw + S.conic), (int32_t*)(sw + S.radius), reinterpret_cast<ushort4*>(sw + S.rect),
                 (float*)(sw + S.op_act), (float*)(sw + S.feat), s_counts, s_ctrl + GFB_CTRL_WORDS, s_ctrl, T, R, no_regs,
-                loss_acc, nullptr);
+                loss_acc, nullptr, tight);
             GFB_CHECK_LAUNCH();
             rc = gfb_internal_scatter_sort_pack(sw + S.rect, (float*)(sw + S.depth), p->sub_N, W, H, s_counts, p->sub_capacity,
                                                 sw + S.keys, (int32_t*)(sw + S.tile_range), (float*)(sw + S.uv),

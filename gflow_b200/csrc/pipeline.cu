@@ -21,8 +21,12 @@
 // into mapped pinned host memory.  The host waits on that copy only -- the GPU keeps working on
 // the speculatively enqueued kernels -- and a call whose K exceeded the capacity returns
 // GFB_E_CAPACITY so the caller can retry with a larger buffer.
+#include <cstdlib>
+
 #include "sort_network.cuh"
 #include "splat_math.cuh"
+
+bool gfb_tight_tiles();
 
 // blend.cu
 int gfb_internal_blend_fwd(const void*, const void*, int64_t, const int32_t*, int, int, int, float, int, int, float*,
@@ -37,12 +41,15 @@ using namespace gfbm;
 // ctrl words that follow the T tile counters in the control buffer
 enum { CTRL_DONE = GFB_CTRL_DONE, CTRL_K = GFB_CTRL_K, CTRL_WORDS = GFB_CTRL_WORDS };
 
+// TIGHT (opt-in, GFB_TIGHT_TILES=1): bin by the alpha >= 1/255 box instead of the 3-sigma rectangle (tighten_rect)
+template <bool TIGHT>
 __global__ void __launch_bounds__(kThreads)
 preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale, const float4* __restrict__ rotate,
                   const float* __restrict__ intr, const float* __restrict__ extr, int N, int W, int H, float nearest,
                   float extent, float2* __restrict__ uv, float* __restrict__ depth, float* __restrict__ conic,
                   int32_t* __restrict__ radius, ushort4* __restrict__ rect, int32_t* __restrict__ counts,
-                  int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int32_t* __restrict__ k_mapped, int T, int R) {
+                  int32_t* __restrict__ offsets, int32_t* __restrict__ ctrl, int32_t* __restrict__ k_mapped, int T, int R,
+                  const float* __restrict__ opacity) {
     gfb_pdl_launch_dependents();  // scatter may take SM slots while the counting tail drains
     __shared__ float s_cam[16];
     __shared__ int s_scan[34];
@@ -73,7 +80,12 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
                 cb = -m.b * dinv;
                 cc = m.a * dinv;
                 rad = (int)rf;
-                rc = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+                if constexpr (TIGHT) {
+                    if (tighten_rect(u, v, ca, cb, cc, opacity[i], x0, y0, x1, y1))
+                        rc = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+                } else {
+                    rc = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+                }
             }
         }
         uv[i] = ok ? make_float2(u, v) : make_float2(0.0f, 0.0f);
@@ -236,6 +248,17 @@ geometry_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ sca
 
 }  // namespace
 
+// GFB_TIGHT_TILES=1: opt-in tile culling by the alpha >= 1/255 box in the fused pipeline and the native fit loop
+// (their gaussian_ids_sorted / tile_range then list fewer pairs than msplat.sort_gaussian would; images and
+// gradients are unchanged).  Off by default until measured.
+bool gfb_tight_tiles() {
+    static const bool on = [] {
+        const char* e = getenv("GFB_TIGHT_TILES");
+        return e && atoi(e) != 0;
+    }();
+    return on;
+}
+
 // Second and third forward kernels for a caller that has run its own preprocess (gfb_render_forward
 // above, the native fit iteration in fit.cu): claim slots + write keys, then per-tile sort + pack.
 // control_ws is laid out as gfb_render_control_bytes() describes and holds the scanned offsets.
@@ -300,10 +323,16 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     if (rc) return rc;
     GFB_TRY(cudaMemsetAsync(control_ws, 0, ((size_t)T * R + CTRL_WORDS) * sizeof(int32_t), st));
     // N == 0 still runs one CTA so the scan zeroes the offsets
-    preprocess_kernel<<<max(1, gfb_div_up(N, kThreads)), kThreads, 0, st>>>(
-        xyz, scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent,
-        reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect_ws), counts,
-        tile_offsets, ctrl, mapped, T, R);
+    if (gfb_tight_tiles())
+        preprocess_kernel<true><<<max(1, gfb_div_up(N, kThreads)), kThreads, 0, st>>>(
+            xyz, scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent,
+            reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect_ws), counts,
+            tile_offsets, ctrl, mapped, T, R, opacity);
+    else
+        preprocess_kernel<false><<<max(1, gfb_div_up(N, kThreads)), kThreads, 0, st>>>(
+            xyz, scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent,
+            reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect_ws), counts,
+            tile_offsets, ctrl, mapped, T, R, opacity);
     GFB_CHECK_LAUNCH();
     GFB_TRY(cudaEventRecord(ev, st));
     // speculative part: enqueued before K is known on the host

@@ -269,4 +269,22 @@ __device__ __forceinline__ void splat_bbox(float a, float b, float c, float o, f
     }
 }
 
+// Opt-in tile culling for the paths whose intersection list is internal (fused pipeline, native fit loop): shrink
+// the 3-sigma tile rectangle [x0,x1) x [y0,y1) to the tiles the alpha >= 1/255 box of splat_bbox() reaches.  A pair
+// dropped here has no pixel with alpha >= 1/255, so images and gradients are unchanged; the operator-level
+// sort_gaussian keeps the reference's 3-sigma rule.  Returns false when no tile is left.
+__device__ __forceinline__ bool tighten_rect(float u, float v, float a, float b, float c, float o, int& x0, int& y0,
+                                             int& x1, int& y1) {
+    float hx, hy;
+    splat_bbox(a, b, c, o, hx, hy);
+    if (hx < 0.0f) return false;             // -inf: the Gaussian never reaches 1/255
+    if (hx < 3.0e38f && hy < 3.0e38f) {      // +inf: conic not positive definite -> keep the 3-sigma rectangle
+        x0 = max(x0, (int)floorf((u - hx) / (float)GFB_TILE));
+        x1 = min(x1, (int)floorf((u + hx) / (float)GFB_TILE) + 1);
+        y0 = max(y0, (int)floorf((v - hy) / (float)GFB_TILE));
+        y1 = min(y1, (int)floorf((v + hy) / (float)GFB_TILE) + 1);
+    }
+    return x1 > x0 && y1 > y0;
+}
+
 }  // namespace gfbm

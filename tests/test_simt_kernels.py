@@ -214,3 +214,14 @@ def test_full_size_config2_fused_pipeline():
     r = emu.fused_pipeline(sc, Gimg, capacity=400000)
     assert r["rc"] == 0 and r["K"] == 197461
     _check(r, o, "cfg2 fused pipeline")
+
+
+def test_experimental_tight_tile_culling_keeps_images_and_gradients():
+    """GFB_TIGHT_TILES=1 (off by default; fused pipeline + native fit loop only): tests/simt/tight_tiles_check.py in a
+    process of its own."""
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, os.path.join(here, "simt", "tight_tiles_check.py")], capture_output=True, text=True,
+                         env=dict(os.environ, GFB_TIGHT_TILES="1"), cwd=os.path.dirname(here), timeout=900)
+    assert res.returncode == 0 and "TIGHT_TILES_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]

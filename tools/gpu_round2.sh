@@ -46,6 +46,13 @@ for prof in synthetic gflow; do for k in 0 2 4 8; do
   GFB_BWD_SPARSE=$k timeout 300 python bench.py --steps 100 --warmup 10 --profile $prof --no-cpu-baseline --no-fit-loop > $OUT/bench_sparse${k}_${prof}_${TAG}.json 2>> $OUT/bench_${TAG}.err
   python -c "import json,sys; d=json.load(open('$OUT/bench_sparse${k}_${prof}_${TAG}.json')); print('$prof sparse=$k', round(d['value'],1), 'it/s  blend_bwd', round(d['roofline']['kernel_ms']*1e3,1), 'us')"
 done; done
+echo "== experimental tile culling GFB_TIGHT_TILES (fused pipeline + native loop)"
+for prof in synthetic gflow; do for t in 0 1; do
+  GFB_TIGHT_TILES=$t timeout 300 python bench.py --steps 100 --warmup 10 --profile $prof --no-cpu-baseline --no-fit-loop > $OUT/bench_tight${t}_${prof}_${TAG}.json 2>> $OUT/bench_${TAG}.err
+  python -c "import json; d=json.load(open('$OUT/bench_tight${t}_${prof}_${TAG}.json')); print('$prof tight=$t', round(d['value'],1), 'it/s  K', d['config']['K'])"
+done; done
+GFB_TIGHT_TILES=1 timeout 900 python tests/gpu_native_fit_runner.py > $OUT/fit_parity_tight_${TAG}.log 2>&1; grep RESULT $OUT/fit_parity_tight_${TAG}.log | cut -c1-1500
+GFB_TIGHT_TILES=1 timeout 300 python tools/bench_fit.py --iters 300 --native > $OUT/fit_cfg3_native_tight_${TAG}.json 2>> $OUT/fit_cfg3_${TAG}.err; cat $OUT/fit_cfg3_native_tight_${TAG}.json
 echo "== in-situ kernel times of the native iteration"
 timeout 300 python tools/fit_kernel_times.py 20 > $OUT/fit_kernel_times_${TAG}.txt 2>&1; tail -25 $OUT/fit_kernel_times_${TAG}.txt
 echo "== ncu launch list (bench command)"
