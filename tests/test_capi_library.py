@@ -90,3 +90,27 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
                 assert "splat_oracle" not in txt and "c_oracle" not in txt, f"{f} references the oracle"
+
+
+def test_measured_kernels_still_compile_to_the_measured_instructions():
+    """profiles/sass_hashes_measured.json: SASS hash of every kernel whose timings in profiles/ and DESIGN.md were taken
+    on hardware.  Work done without GPU access (new kernels, template variants, refactors) must leave them untouched;
+    after an intentional, re-measured change the registry is refreshed with `python tools/sass_hashes.py --write`."""
+    import importlib.util
+    import json
+
+    if not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    from gflow_b200 import _build
+
+    if _build.needs_build():
+        _build.build()
+    spec = importlib.util.spec_from_file_location("sass_hashes", os.path.join(ROOT, "tools", "sass_hashes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.kernel_hashes()
+    with open(os.path.join(ROOT, "profiles", "sass_hashes_measured.json")) as fh:
+        measured = json.load(fh)
+    assert len(measured) >= 25
+    changed = [k for k, v in measured.items() if now.get(k, {}).get("sha1") != v["sha1"]]
+    assert not changed, f"measured kernels whose SASS changed (re-measure, then refresh the registry): {changed}"
