@@ -22,7 +22,8 @@ def load():
     if _lib is None:
         from gflow_b200.capi import SIGNATURES
 
-        path = build_emu.build()
+        # GFB_EMU_LIB: an alternative build of the same sources (the UBSan one, tests/test_simt_kernels.py)
+        path = os.environ.get("GFB_EMU_LIB") or build_emu.build()
         lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)

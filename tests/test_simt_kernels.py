@@ -225,3 +225,25 @@ def test_experimental_tight_tile_culling_keeps_images_and_gradients():
     res = subprocess.run([sys.executable, os.path.join(here, "simt", "tight_tiles_check.py")], capture_output=True, text=True,
                          env=dict(os.environ, GFB_TIGHT_TILES="1"), cwd=os.path.dirname(here), timeout=900)
     assert res.returncode == 0 and "TIGHT_TILES_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
+
+
+def test_no_misaligned_vector_access_or_static_overrun_under_ubsan():
+    """The emulated kernels rebuilt with -fsanitize=alignment,bounds (aborting) and run over odd sizes: a float4 / float2 /
+    ushort4 access through a misaligned pointer faults on the GPU but not on x86, so the shim alone would not see it."""
+    import subprocess
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "simt"))
+    import build_emu
+
+    rt = build_emu.ubsan_runtime()
+    if not os.path.isabs(rt) or not os.path.exists(rt):
+        pytest.skip("libubsan not available")
+    lib = build_emu.build_sanitized()
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, LD_PRELOAD=rt, GFB_EMU_LIB=lib, UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.join(here, "test_simt_kernels.py"),
+                          os.path.join(here, "test_simt_fit.py"), os.path.join(here, "test_simt_densify.py"), "-k",
+                          "randomised or channel_groups or every_term or masks or moving_footprint or densif or compute_sh or empty"],
+                         capture_output=True, text=True, env=env, cwd=os.path.dirname(here), timeout=1500)
+    assert res.returncode == 0 and " passed" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "runtime error" not in res.stderr
