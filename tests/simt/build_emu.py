@@ -244,26 +244,37 @@ def build_selfcheck() -> str:
     return SELFCHECK_LIB
 
 
-UBSAN_LIB = os.path.join(BUILD, "libgflow_b200_emu_ubsan.so")
+SANITIZED_LIB = os.path.join(BUILD, "libgflow_b200_emu_san.so")
 
 
 def build_sanitized() -> str:
-    """The same generated sources with -fsanitize=alignment,bounds (aborting): a float4 / float2 / ushort4 access through
-    a pointer that is not 16 / 8 byte aligned faults on the GPU but is silently tolerated by x86 -- UBSan makes the
-    emulated run abort on it too.  Loading it needs libubsan preloaded (see tests/test_simt_kernels.py)."""
+    """The same generated sources with -fsanitize=address,alignment,bounds (aborting):
+      * alignment: a float4 / float2 / ushort4 access through a pointer that is not 16 / 8 byte aligned faults on the
+        GPU but is silently tolerated by x86;
+      * address: an emulated kernel that writes or reads past a caller's buffer (host tensors get red zones once
+        libasan is preloaded) -- the CPU counterpart of compute-sanitizer memcheck;
+      * bounds: indexing past a static (shared-memory) array.
+    Loading it needs libasan + libubsan preloaded (sanitizer_preload(); see tests/test_simt_kernels.py)."""
     build()  # generated sources are current after this
-    deps_newer = (not os.path.exists(UBSAN_LIB)) or os.path.getmtime(UBSAN_LIB) < os.path.getmtime(LIB_PATH)
-    if not deps_newer:
-        return UBSAN_LIB
+    if os.path.exists(SANITIZED_LIB) and os.path.getmtime(SANITIZED_LIB) >= os.path.getmtime(LIB_PATH):
+        return SANITIZED_LIB
     cpps = [os.path.join(SRC_OUT, f) for f in sorted(os.listdir(SRC_OUT)) if f.endswith(".cpp") and f != "selfcheck.cpp"]
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing",
-           "-fsanitize=alignment,bounds", "-fno-sanitize-recover=all", "-Wno-unknown-pragmas", "-Wno-attributes", "-I", SRC_OUT,
-           "-I", HERE, "-I", INCLUDE, *cpps, os.path.join(HERE, "simt_emu.cpp"), "-o", UBSAN_LIB]
+           "-fsanitize=address,alignment,bounds", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer", "-Wno-unknown-pragmas",
+           "-Wno-attributes", "-I", SRC_OUT, "-I", HERE, "-I", INCLUDE, *cpps, os.path.join(HERE, "simt_emu.cpp"), "-o",
+           SANITIZED_LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("sanitised emulation build failed:\n" + (res.stdout + res.stderr)[-4000:])
-    return UBSAN_LIB
+    return SANITIZED_LIB
 
 
-def ubsan_runtime() -> str:
-    return subprocess.run(["gcc", "-print-file-name=libubsan.so"], capture_output=True, text=True).stdout.strip()
+def sanitizer_preload():
+    """LD_PRELOAD value (libasan first, then libubsan) or None when the runtimes are not installed."""
+    libs = []
+    for name in ("libasan.so", "libubsan.so"):
+        path = subprocess.run(["gcc", "-print-file-name=" + name], capture_output=True, text=True).stdout.strip()
+        if not os.path.isabs(path) or not os.path.exists(path):
+            return None
+        libs.append(path)
+    return ":".join(libs)

@@ -227,23 +227,27 @@ def test_experimental_tight_tile_culling_keeps_images_and_gradients():
     assert res.returncode == 0 and "TIGHT_TILES_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
 
 
-def test_no_misaligned_vector_access_or_static_overrun_under_ubsan():
-    """The emulated kernels rebuilt with -fsanitize=alignment,bounds (aborting) and run over odd sizes: a float4 / float2 /
-    ushort4 access through a misaligned pointer faults on the GPU but not on x86, so the shim alone would not see it."""
+def test_sanitized_build_finds_no_out_of_bounds_or_misaligned_access():
+    """The emulated kernels rebuilt with AddressSanitizer + UBSan (alignment, bounds), aborting on the first finding, and
+    run over odd sizes -- the CPU counterpart of compute-sanitizer memcheck: host tensors get red zones (libasan is
+    preloaded), so a kernel writing one element past a caller's buffer, or reading a float4 through a pointer that is
+    only 8-byte aligned (fine on x86, a fault on the GPU), stops the run."""
     import subprocess
 
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "simt"))
     import build_emu
 
-    rt = build_emu.ubsan_runtime()
-    if not os.path.isabs(rt) or not os.path.exists(rt):
-        pytest.skip("libubsan not available")
+    preload = build_emu.sanitizer_preload()
+    if preload is None:
+        pytest.skip("libasan / libubsan not available")
     lib = build_emu.build_sanitized()
     here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, LD_PRELOAD=rt, GFB_EMU_LIB=lib, UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    env = dict(os.environ, LD_PRELOAD=preload, GFB_EMU_LIB=lib, UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1",
+               ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:detect_stack_use_after_return=0")
     res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.join(here, "test_simt_kernels.py"),
                           os.path.join(here, "test_simt_fit.py"), os.path.join(here, "test_simt_densify.py"), "-k",
-                          "randomised or channel_groups or every_term or masks or moving_footprint or densif or compute_sh or empty"],
-                         capture_output=True, text=True, env=env, cwd=os.path.dirname(here), timeout=1500)
-    assert res.returncode == 0 and " passed" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "runtime error" not in res.stderr
+                          "randomised or channel_groups or every_term or masks or moving_footprint or densif or compute_sh or empty "
+                          "or rolled_back or dense_tiles"],
+                         capture_output=True, text=True, env=env, cwd=os.path.dirname(here), timeout=1800)
+    assert res.returncode == 0 and " passed" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "runtime error" not in res.stderr and "AddressSanitizer" not in res.stderr
