@@ -286,7 +286,10 @@ __device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
 // SPARSE (experimental, off by default, GFB_BWD_SPARSE=k): a (warp, record) pair with at most k active lanes skips
 // the butterfly and lets every active lane add its own values (k x 10 reductions in L2 instead of ~45
 // shuffle / select / add instructions).  With the ~1 px splats GFlow fits, 40 % of the pairs have <= 4 active lanes.
-template <int CG, bool SPARSE>
+// NO_RGB (CG == 4 only; the native fit loop on frames >= 1, where GFlow zeroes the colour gradient, trainer.py:537-540):
+// channels 0..2 still enter dalpha through f . g, but their own gradient is neither reduced nor added -- the depth
+// channel's gradient rides in the butterfly's seventh slot, so one reduce8 replaces reduce8 + two warp sums.
+template <int CG, bool SPARSE, bool NO_RGB = false>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, const float4* __restrict__ gF,
                  const int32_t* __restrict__ ids, const int2* __restrict__ tile_range, int gx, int c0, float bg,
@@ -413,10 +416,14 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                                 v[3] = -gdx * dy * dG;
                                 v[4] = -0.5f * gdy * dy * dG;
                                 v[5] = G * dalpha;
-                                v[6] = df[0];
-                                if (CG > 1) v[7] = df[1];
-                                if (CG > 2) v8 = df[2];
-                                if (CG > 3) v9 = df[3];
+                                if constexpr (NO_RGB) {
+                                    v[6] = df[3];
+                                } else {
+                                    v[6] = df[0];
+                                    if (CG > 1) v[7] = df[1];
+                                    if (CG > 2) v8 = df[2];
+                                    if (CG > 3) v9 = df[3];
+                                }
                             }
                         }
                     }
@@ -427,10 +434,15 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                             if (act) {
                                 float* gp = grad_pack + (size_t)ids[(long long)range.x + pos] * 12;
 #pragma unroll
-                                for (int i = 0; i < 7; ++i) atomicAdd(gp + i, v[i]);
-                                if (CG > 1) atomicAdd(gp + 7, v[7]);
-                                if (CG > 2) atomicAdd(gp + 8, v8);
-                                if (CG > 3) atomicAdd(gp + 9, v9);
+                                for (int i = 0; i < 6; ++i) atomicAdd(gp + i, v[i]);
+                                if constexpr (NO_RGB) {
+                                    atomicAdd(gp + 9, v[6]);
+                                } else {
+                                    atomicAdd(gp + 6, v[6]);
+                                    if (CG > 1) atomicAdd(gp + 7, v[7]);
+                                    if (CG > 2) atomicAdd(gp + 8, v8);
+                                    if (CG > 3) atomicAdd(gp + 9, v9);
+                                }
                             }
                             continue;
                         }
@@ -438,6 +450,12 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
                         if (!__any_sync(kFull, act)) continue;
                     }
                     const float r = warp_reduce8(v, lane);
+                    if constexpr (NO_RGB) {  // slots 0..5 -> gp[0..5], slot 6 (depth channel) -> gp[9]
+                        const int slot = lane >> 2;
+                        if ((lane & 3) == 0 && slot < 7)
+                            atomicAdd(grad_pack + (size_t)ids[(long long)range.x + pos] * 12 + (slot < 6 ? slot : 9), r);
+                        continue;
+                    }
                     if (CG > 2) v8 = gfb_warp_sum(v8);
                     if (CG > 3) v9 = gfb_warp_sum(v9);
                     const int id = ids[(long long)range.x + pos];
@@ -568,6 +586,9 @@ int gfb_internal_blend_fwd(const void* geom_stream, const void* feat_stream, int
     return 0;
 }
 
+int gfb_internal_blend_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int, float, int, int,
+                           const float*, const int32_t*, const float*, float*, void*, bool no_rgb);
+
 extern "C" {
 
 int gfb_alpha_blending_fwd(const void* geom_stream, const void* feat_stream, int64_t K, const int32_t* tile_range,
@@ -581,6 +602,18 @@ int gfb_alpha_blending_bwd(const void* geom_stream, const void* feat_stream, int
                            const int32_t* gaussian_ids_sorted, const int32_t* tile_range, int C, int c0, int Cg,
                            float bg, int W, int H, const float* final_T, const int32_t* n_contrib, const float* g_out,
                            float* grad_pack, void* stream) {
+    return gfb_internal_blend_bwd(geom_stream, feat_stream, K, gaussian_ids_sorted, tile_range, C, c0, Cg, bg, W, H, final_T,
+                                  n_contrib, g_out, grad_pack, stream, false);
+}
+
+}  // extern "C"
+
+// no_rgb: only with Cg == 4 and c0 == 0 (rgb + depth in one blend): skip the colour channels' own gradient
+int gfb_internal_blend_bwd(const void* geom_stream, const void* feat_stream, int64_t K,
+                           const int32_t* gaussian_ids_sorted, const int32_t* tile_range, int C, int c0, int Cg,
+                           float bg, int W, int H, const float* final_T, const int32_t* n_contrib, const float* g_out,
+                           float* grad_pack, void* stream, bool no_rgb) {
+    if (no_rgb && (Cg != 4 || c0 != 0)) return GFB_E_BADARG;
     if (W <= 0 || H <= 0 || K < 0 || C <= 0 || c0 < 0 || Cg < 1 || Cg > 4 || c0 + Cg > C) return GFB_E_BADARG;
     if (K == 0) return 0;
     if (!geom_stream || !feat_stream || !gaussian_ids_sorted || !tile_range || !final_T || !n_contrib || !g_out ||
@@ -598,7 +631,14 @@ int gfb_alpha_blending_bwd(const void* geom_stream, const void* feat_stream, int
 #define GFB_BWD_LAUNCH(CGV, SP)                                                                                          \
     blend_bwd_kernel<CGV, SP><<<grid, block, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H, final_T, \
                                                       n_contrib, g_out, grad_pack, sparse)
-    if (sparse > 0) {
+    if (no_rgb) {
+        if (sparse > 0)
+            blend_bwd_kernel<4, true, true><<<grid, block, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H,
+                                                                     final_T, n_contrib, g_out, grad_pack, sparse);
+        else
+            blend_bwd_kernel<4, false, true><<<grid, block, 0, st>>>(gA, gB, gF, gaussian_ids_sorted, tr, gx, c0, bg, W, H,
+                                                                      final_T, n_contrib, g_out, grad_pack, sparse);
+    } else if (sparse > 0) {
         switch (Cg) {
             case 1: GFB_BWD_LAUNCH(1, true); break;
             case 2: GFB_BWD_LAUNCH(2, true); break;
@@ -617,6 +657,8 @@ int gfb_alpha_blending_bwd(const void* geom_stream, const void* feat_stream, int
     GFB_CHECK_LAUNCH();
     return 0;
 }
+
+extern "C" {
 
 int gfb_blend_unpack_grads(const float* grad_pack, int N, int C, int c0, int Cg, float* d_uv, float* d_conic,
                            float* d_opacity, float* d_feature, int accumulate, void* stream) {

@@ -36,8 +36,8 @@ int gfb_internal_scatter_sort_pack(const void*, const float*, int, int, int, voi
                                    void*, bool);
 int gfb_internal_blend_fwd(const void*, const void*, int64_t, const int32_t*, int, int, int, float, int, int, float*,
                            float*, int32_t*, void*, bool pdl);
-extern "C" int gfb_alpha_blending_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int,
-                                      float, int, int, const float*, const int32_t*, const float*, float*, void*);
+int gfb_internal_blend_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int, float, int, int,
+                           const float*, const int32_t*, const float*, float*, void*, bool no_rgb);
 
 namespace {
 
@@ -756,6 +756,14 @@ AdamStep adam_step(const gfb_fit_problem* p, double lr, int iter) {
 
 // Programmatic dependent launch between the iteration's kernels, the way pipeline.cu chains its own
 // (preprocess -> scatter -> sort -> blend, blend_bwd -> geometry_bwd).  Off until measured on hardware.
+bool fit_skip_rgb_grad() {
+    static const bool on = [] {
+        const char* e = getenv("GFB_FIT_SKIP_RGB_GRAD");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 bool fit_pdl() {
     static const bool on = [] {
         const char* e = getenv("GFB_FIT_PDL");
@@ -849,6 +857,9 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
     const int nblk = gfb_div_up(N, kThreads);
     const bool pdl = fit_pdl();
     const int tight = gfb_tight_tiles() ? 1 : 0;
+    // frames >= 1 freeze the colours (trainer.py:537-540) and a camera-only stage freezes every attribute: the blend
+    // backward then does not reduce the rgb channels' own gradient (GFB_FIT_SKIP_RGB_GRAD=0 keeps the full backward)
+    const bool no_rgb = C == 4 && (p->freeze_rgb || p->camera_only) && fit_skip_rgb_grad();
     // camera-only stage: the moving subset is rendered every iteration and its footprint leaves the losses
     const bool use_sub = p->sub_N > 0 && p->camera_only;
     SubLayout S;
@@ -910,8 +921,8 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                                                                      reinterpret_cast<uint32_t*>(counts), n_ctrl_words,
                                                                      (size_t)T * R + GFB_CTRL_K);
         GFB_CHECK_LAUNCH();
-        rc = gfb_alpha_blending_bwd(geom, fstream, capacity, ids, tile_range, C, 0, C, p->bg, W, H, final_T, n_contrib,
-                                    g_out, grad_ws, stream);
+        rc = gfb_internal_blend_bwd(geom, fstream, capacity, ids, tile_range, C, 0, C, p->bg, W, H, final_T, n_contrib,
+                                    g_out, grad_ws, stream, no_rgb);
         if (rc) return rc;
         GFB_TRY(gfb_launch_pdl(fit_geometry_bwd_adam_kernel, dim3(nblk), dim3(kThreads), st, pdl, p->xyz, p->scale,
                                reinterpret_cast<float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest, p->extent,

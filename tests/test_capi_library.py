@@ -112,5 +112,9 @@ def test_measured_kernels_still_compile_to_the_measured_instructions():
     with open(os.path.join(ROOT, "profiles", "sass_hashes_measured.json")) as fh:
         measured = json.load(fh)
     assert len(measured) >= 25
-    changed = [k for k, v in measured.items() if now.get(k, {}).get("sha1") != v["sha1"]]
+    def still_there(key, sha1):  # a template that gained a defaulted parameter is renamed, not changed: match by hash
+        base = key.split("<")[0]
+        return any(v["sha1"] == sha1 for k, v in now.items() if k.split("<")[0] == base)
+
+    changed = [k for k, v in measured.items() if not still_there(k, v["sha1"])]
     assert not changed, f"measured kernels whose SASS changed (re-measure, then refresh the registry): {changed}"
