@@ -89,6 +89,21 @@ __device__ __forceinline__ void gfb_tile_rect(float u, float v, float r, int gx,
     y1 = min(gy, max(0, (int)(((v + r) + (float)(GFB_TILE - 1)) / (float)GFB_TILE)));
 }
 
+// Record stream A of the blend kernels = {u, v, extents, id}: `extents` holds the half extents (hx, hy) of the
+// alpha >= 1/255 box as two bfloat16 values rounded UP in magnitude (the box only grows, so the bbox cull stays
+// conservative; +/-inf survive), `id` the Gaussian index as raw bits.  One LDS.128 per surviving record then
+// carries everything but conic / opacity / features, and the backward needs no gaussian_ids_sorted lookup.
+__device__ __forceinline__ float4 gfb_pack_record_a(float u, float v, float hx, float hy, int id) {
+    const unsigned int bx = (__float_as_uint(hx) + 0xffffu) & 0xffff0000u;
+    const unsigned int by = (__float_as_uint(hy) + 0xffffu) & 0xffff0000u;
+    return make_float4(u, v, __uint_as_float(bx | (by >> 16)), __int_as_float(id));
+}
+__device__ __forceinline__ void gfb_unpack_extents(float packed, float& hx, float& hy) {
+    const unsigned int w = __float_as_uint(packed);
+    hx = __uint_as_float(w & 0xffff0000u);
+    hy = __uint_as_float(w << 16);
+}
+
 __device__ __forceinline__ float gfb_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

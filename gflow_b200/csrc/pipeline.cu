@@ -175,7 +175,7 @@ __device__ __forceinline__ void write_record(const PackArgs& a, long long k, int
     if (a.C > 2) fr.z = f[2];
     if (a.C > 3) fr.w = f[3];
     a.ids[k] = id;
-    a.sA[k] = make_float4(p.x, p.y, hx, hy);
+    a.sA[k] = gfb_pack_record_a(p.x, p.y, hx, hy, id);
     a.sB[k] = make_float4(ca, cb, cc, o);
     a.sF[k] = fr;
 }

@@ -37,7 +37,13 @@ PTX_WRAPPERS = {
     "mbar_arrive": "gfb_emu::mbar_arrive(bar);",
     "bulk_g2s": "gfb_emu::bulk_g2s(dst, src, bytes, bar);",
     "mbar_wait": "gfb_emu::mbar_wait(bar, parity);",
-    "splat_exp": "return exp2f(power * 1.4426950408889634f);",
+    "splat_ex2": "return exp2f(x);",
+    "trace_now": "return 0ull;",
+    "trace_smid": "return 0u;",
+    "fma2": "return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));",
+    "mul2": "return make_float2(a.x * b.x, a.y * b.y);",
+    "add2": "return make_float2(a.x + b.x, a.y + b.y);",
+    "sub2": "return make_float2(a.x - b.x, a.y - b.y);",
     "splat_rcp": "return 1.0f / x;",
     "gfb_pdl_wait": "",
     "gfb_pdl_launch_dependents": "",
@@ -151,6 +157,7 @@ def _fingerprint() -> str:
         with open(f, "rb") as fh:
             h.update(f.encode())
             h.update(fh.read())
+    h.update(os.environ.get("GFB_EMU_DEFINES", "").encode())
     return h.hexdigest()
 
 
@@ -201,8 +208,8 @@ def _build_locked(force: bool, opt: str) -> str:
     with open(os.path.join(SRC_OUT, "cuda_runtime.h"), "w") as fh:
         fh.write('#pragma once\n#include "simt_emu.h"\n')
     cmd = ["g++", opt, "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing",
-           "-Wno-unknown-pragmas", "-Wno-attributes", "-I", SRC_OUT, "-I", HERE, "-I", INCLUDE, *cpps,
-           os.path.join(HERE, "simt_emu.cpp"), "-o", LIB_PATH]
+           "-Wno-unknown-pragmas", "-Wno-attributes", *os.environ.get("GFB_EMU_DEFINES", "").split(),  # kernel build knobs
+           "-I", SRC_OUT, "-I", HERE, "-I", INCLUDE, *cpps, os.path.join(HERE, "simt_emu.cpp"), "-o", LIB_PATH]
     res = subprocess.run(cmd, capture_output=True, text=True)
     with open(os.path.join(BUILD, "build.log"), "w") as fh:
         fh.write("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr + f"\nwrappers emulated: {sorted(found)}\n")

@@ -190,21 +190,6 @@ def test_randomised_edge_cases():
             emu.set_schedule(0)
 
 
-@pytest.mark.parametrize("lanes", [2, 8])
-def test_experimental_sparse_backward_variant_matches_oracle(lanes):
-    """GFB_BWD_SPARSE=k (off by default): (warp, record) pairs with <= k active lanes skip the butterfly and add
-    per lane.  The switch is read once per process, so the check runs in a process of its own."""
-    import subprocess
-
-    env = dict(os.environ, GFB_BWD_SPARSE=str(lanes))
-    here = os.path.dirname(os.path.abspath(__file__))
-    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(here, "test_simt_kernels.py"), "-k",
-                          "operator_chain_matches_oracle or fused_pipeline_matches_oracle or channel_groups or randomised"],
-                         capture_output=True, text=True, env=env, cwd=os.path.dirname(here), timeout=900)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-1000:]
-    assert " passed" in res.stdout and "failed" not in res.stdout
-
-
 def test_full_size_config2_fused_pipeline():
     """BASELINE config 2 at full size (60 000 Gaussians, 854x480, K = 197 461) through the shim: ids / tile_range /
     per-Gaussian geometry bit-exact, image 1e-4, gradients 1e-3 against the C oracle (about 20 s)."""
