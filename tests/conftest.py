@@ -22,6 +22,35 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+# every assert_close() of the session: (name, elements, max-norm worst, element-wise p50 / p99 / p99.9 / max)
+PARITY_LOG = []
+ELEMENTWISE_FLOOR = 1e-3  # element-wise error = |a-b| / max(|b|, 1e-3 max|b|): small-magnitude elements count too
+
+
+def elementwise_err(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a = a.detach().double().cpu().reshape(-1)
+    b = b.detach().double().cpu().reshape(-1)
+    floor = ELEMENTWISE_FLOOR * b.abs().max().clamp_min(1e-30)
+    return (a - b).abs() / b.abs().clamp_min(floor)
+
+
+def pytest_terminal_summary(terminalreporter):
+    if not PARITY_LOG or not (torch.cuda.is_available() or os.environ.get("GFB_PARITY_SUMMARY")):
+        return  # the table is for the GPU parity run; the CPU suite stays quiet
+    tr = terminalreporter
+    tr.section("parity: max-norm relative error (asserted) beside the element-wise figure (reported)")
+    tr.write_line(f"element-wise = |a-b| / max(|b|, {ELEMENTWISE_FLOOR:g} max|b|); one line per comparison against the oracle")
+    tr.write_line(f"{'comparison':58s} {'n':>9s} {'maxnorm':>9s} {'ew p50':>9s} {'ew p99':>9s} {'ew p99.9':>9s} {'ew max':>9s}")
+    for name, n, worst, p50, p99, p999, mx in PARITY_LOG:
+        tr.write_line(f"{name[:58]:58s} {n:9d} {worst:9.2e} {p50:9.2e} {p99:9.2e} {p999:9.2e} {mx:9.2e}")
+    out = os.environ.get("GFB_PARITY_REPORT")
+    if out:
+        import json
+
+        with open(out, "w") as fh:
+            json.dump([dict(zip(("name", "n", "maxnorm", "ew_p50", "ew_p99", "ew_p999", "ew_max"), r)) for r in PARITY_LOG], fh, indent=1)
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """|a-b| / max|b| elementwise (max-norm relative error; b is the oracle)."""
     a = a.detach().double().cpu()
@@ -43,6 +72,9 @@ def assert_close(a, b, rel, name, outlier_frac=0.0, outlier_rel=None):
         return
     e = rel_err(a, b)
     assert torch.isfinite(a).all(), f"{name}: non-finite values"
+    ew = elementwise_err(a, b)
+    q = torch.quantile(ew[: 4_000_000], torch.tensor([0.5, 0.99, 0.999], dtype=torch.float64)) if ew.numel() > 1 else ew.repeat(3)
+    PARITY_LOG.append((name, int(ew.numel()), float(e.max()), float(q[0]), float(q[1]), float(q[2]), float(ew.max())))
     n_bad = int((e > rel).sum())
     allowed = int(outlier_frac * e.numel())
     worst = float(e.max())

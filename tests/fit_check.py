@@ -284,3 +284,37 @@ def check_native_stage_against_reference_golden(loop_cls, device, stage, loss_rt
     if stage != "first":
         assert torch.equal(f.attrs["rgb"].data.cpu(), raw["rgb"])
     return loop
+
+
+def check_operator_stage_against_reference_golden(device, stage, loss_rtol=3e-2, attr_atol=2e-3, attr_frac=0.04,
+                                                  pose_atol=5e-3):
+    """The same recorded stage through the OPERATOR path (FrameFitter.train with native=False: the msplat operators one
+    by one + torch autograd + torch.optim.Adam, i.e. the way the unmodified gflow/trainer.py:387-582 drives the drop-in)
+    against what the reference posted / ended with."""
+    G = load_trainer_golden()
+    W, H = int(G["W"]), int(G["H"])
+    cfg, raw, pose, img, depth, kw = golden_stage_inputs(G, stage)
+    cfg.native = False
+    dev = torch.device(device)
+    f = fit.FrameFitter({k: v.to(dev) for k, v in raw.items()}, G["intr"].to(dev), pose.to(dev), W, H)
+    ab0 = G[f"{stage}/state/ab"][0]
+    f.depth_a.data.fill_(float(ab0[0]))
+    f.depth_b.data.fill_(float(ab0[1]))
+    prev = None if kw["prev"] is None else fit.PrevFrame(**{k: v.to(dev) for k, v in kw["prev"].items()})
+    res = f.train(img.to(dev), depth.to(dev), cfg, pixel_mask=None if kw["pixel_mask"] is None else kw["pixel_mask"].to(dev),
+                  still_mask=None if kw["still_mask"] is None else kw["still_mask"].to(dev), prev=prev,
+                  tentative_still=None if kw["tentative_still"] is None else kw["tentative_still"].to(dev))
+    ours = torch.tensor(res.losses, dtype=torch.float64)
+    ref = G[f"{stage}/posted/total"].double()
+    assert abs(float(ours[0] - ref[0])) <= 3e-4 * abs(float(ref[0])), (stage, ours, ref)
+    assert torch.allclose(ours, ref, rtol=loss_rtol), (stage, ours, ref)
+    for k in ATTRS:
+        bad = ((f.attrs[k].data.cpu() - G[f"{stage}/final/{k}"]).abs() > attr_atol).any(dim=-1)
+        assert float(bad.float().mean()) <= attr_frac, (stage, k, float(bad.float().mean()))
+    assert torch.allclose(f.pose.data.cpu(), G[f"{stage}/final/pose"], atol=pose_atol), stage
+    if stage == "camera":
+        assert all(torch.equal(f.attrs[k].data.cpu(), raw[k]) for k in ATTRS)
+    if stage != "first":
+        assert torch.equal(f.attrs["rgb"].data.cpu(), raw["rgb"])
+    return res
+

@@ -78,6 +78,16 @@ def concurrent_frames_on_streams():
         assert abs(float(a[0]) - float(b[0])) <= 1e-4 * float(a[0])
 
 
+def native_iterations_at_config3_size():
+    """Two native iterations at BASELINE config 3's size (60 000 Gaussians, 854x480, mse + 1-SSIM + depth, camera
+    learning on) checked one by one against oracle/fit_ref.py: loss terms, raw-attribute gradients, dL/dpose and the
+    in-kernel Adam update (fit_check.run_and_check).  The oracle needs ~12 s per iteration on the host."""
+    from gflow_b200.fit import NativeFitLoop
+
+    cfg = fit.FitConfig(iterations=300, lr=4e-3, lr_camera=1e-3, lambda_depth=0.1, use_ssim=True, native=True)
+    fit_check.run_and_check(NativeFitLoop, "cuda:0", cfg, n_iters=2, N=60000, W=854, H=480, seed=0, capacity=400000)
+
+
 def main():
     results = {}
     cases = fit_check.case_list()
@@ -98,6 +108,19 @@ def main():
             results[f"reference_golden_{stage}"] = "ok"
         except Exception:  # noqa: BLE001
             results[f"reference_golden_{stage}"] = traceback.format_exc()[-1500:]
+    for stage in ("first", "camera", "all"):  # the same recorded stages through the operator path
+        try:
+            fit_check.check_operator_stage_against_reference_golden("cuda:0", stage)
+            torch.cuda.synchronize()
+            results[f"operator_golden_{stage}"] = "ok"
+        except Exception:  # noqa: BLE001
+            results[f"operator_golden_{stage}"] = traceback.format_exc()[-1500:]
+    try:
+        native_iterations_at_config3_size()
+        torch.cuda.synchronize()
+        results["native_config3_size"] = "ok"
+    except Exception:  # noqa: BLE001
+        results["native_config3_size"] = traceback.format_exc()[-1500:]
     try:
         native_vs_operator_path()
         torch.cuda.synchronize()

@@ -64,3 +64,16 @@ def test_flow_warp_reproduces_the_reference_pre_update():
     after = G["all/state/xyz"][0]
     assert not torch.equal(before, after)
     assert torch.allclose(warped, after, rtol=1e-4, atol=1e-5)
+
+
+def test_operator_path_reproduces_the_recorded_stages():
+    """The operator path (FrameFitter.train, native=False: operators + autograd + torch.optim.Adam, the way
+    gflow/trainer.py:387-582 drives the drop-in) against the same recording, with the operators answered by the CPU
+    oracle (tests/simt/fake_cuda_run.py); the GPU suite runs the identical check body on the real kernels."""
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, os.path.join(here, "simt", "fake_cuda_run.py"),
+                          os.path.join(here, "simt", "operator_golden_check.py")], capture_output=True, text=True, cwd=here,
+                         timeout=900)
+    assert res.returncode == 0 and "OPERATOR_GOLDEN_OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
