@@ -12,6 +12,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_void_p
 from . import _build
 
 _lib = None
+GFB_E_CAPACITY, GFB_E_STALE, GFB_E_NOTREADY = -3, -4, -5
 
 # symbol -> (restype, argtypes); mirrors include/gflow_b200.h declaration by declaration
 P, I, F, L = c_void_p, c_int, c_float, c_int64
@@ -33,6 +34,9 @@ SIGNATURES = {
     "gfb_sort_gaussian": (I, [P, P, P, P, I, I, I, P, L, P, P, P, P, P]),
     "gfb_render_control_bytes": (c_size_t, [I, I]),
     "gfb_wait_k": (I, [P]),
+    "gfb_k_ticket": (c_int64, []),
+    "gfb_wait_k_ticket": (I, [L, P]),
+    "gfb_query_k_ticket": (I, [L, P]),
     "gfb_render_forward": (I, [P, P, P, P, P, I, P, P, I, I, I, F, F, F, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P,
                                P, P]),
     "gfb_render_grad_bytes": (c_size_t, [I]),

@@ -378,10 +378,70 @@ struct ComputeSH : public torch::autograd::Function<ComputeSH> {
 };
 
 // ------------------------------------------------------------------ rasterization (fused pipeline)
+bool has_k_hint(int dev, int64_t N, int64_t W, int64_t H) {
+    std::lock_guard<std::mutex> lock(g_hint_mutex);
+    return g_hint.find({dev, N, W, H}) != g_hint.end();
+}
+bool lazy_k_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("GFLOW_B200_LAZY_K");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+// Buffers of one gfb_render_forward call.  scratch (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N |
+// final_T 4HW | n_contrib 4HW | tile_range 8T | control;  kbuf (bytes): geom 32c | feat 16c | keys 8c | ids 4c.
+struct RasterForward {
+    Tensor scratch, kbuf;
+    int64_t cap = 0, K = -1, ticket = -1;
+};
+struct RasterLayout {
+    int64_t o_rect, o_depth, o_conic, o_radius, o_ft, o_nc, o_rng, o_ctl, ctl;
+    RasterLayout(int64_t N, int64_t W, int64_t H) {
+        const int64_t T = ((W + 15) / 16) * ((H + 15) / 16), HW = H * W;
+        ctl = (int64_t)gfb_render_control_bytes((int)W, (int)H);
+        o_rect = 8 * N, o_depth = 16 * N, o_conic = 20 * N, o_radius = 32 * N, o_ft = 36 * N;
+        o_nc = o_ft + 4 * HW, o_rng = ((o_nc + 4 * HW + 7) / 8) * 8, o_ctl = o_rng + 8 * T;
+    }
+};
+
+// Enqueues the forward with capacity `cap`.  lazy: returns at once with the ticket of the pending K hand-off
+// (validated by the backward); otherwise waits for K and retries until it fits.
+RasterForward raster_forward(const Tensor& xyz, const Tensor& scale, const Tensor& rotate, const Tensor& opacity,
+                             const Tensor& feature, const Tensor& intr, const Tensor& extr, int64_t W, int64_t H, double bg,
+                             double nearest, double extent, int64_t cap, Tensor& out, bool lazy) {
+    const int64_t N = xyz.size(0), C = feature.size(1);
+    const RasterLayout L(N, W, H);
+    RasterForward r;
+    r.scratch = at::empty({L.o_ctl + L.ctl + 16}, xyz.options().dtype(at::kByte));
+    char* sp = (char*)r.scratch.data_ptr();
+    for (;;) {
+        r.kbuf = at::empty({15 * std::max<int64_t>(cap, 1)}, f32(xyz));
+        char* kp = (char*)r.kbuf.data_ptr();
+        check_rc(gfb_render_forward(fp(xyz), fp(scale), fp(rotate), fp(opacity), fp(feature), (int)C, fp(intr), fp(extr),
+                                    (int)N, (int)W, (int)H, (float)bg, (float)nearest, (float)extent, (float*)sp,
+                                    (float*)(sp + L.o_depth), (float*)(sp + L.o_conic), (int32_t*)(sp + L.o_radius),
+                                    sp + L.o_rect, sp + L.o_ctl, (int32_t*)(sp + L.o_rng), cap, kp + 48 * cap,
+                                    (int32_t*)(kp + 56 * cap), kp, kp + 32 * cap, fp(out), (float*)(sp + L.o_ft),
+                                    (int32_t*)(sp + L.o_nc), nullptr, stream()),
+                 "rasterization forward");
+        r.cap = cap;
+        r.ticket = gfb_k_ticket();
+        if (lazy) return r;
+        check_rc(gfb_wait_k_ticket(r.ticket, &r.K), "rasterization forward (K)");
+        if (r.K > cap) {
+            cap = r.K + r.K / 8 + 1024;
+            continue;
+        }
+        return r;
+    }
+}
+
 struct Rasterize : public torch::autograd::Function<Rasterize> {
     static Tensor forward(AutogradContext* ctx, const Tensor& xyz_, const Tensor& scale_, const Tensor& rotate_,
                           const Tensor& opacity_, const Tensor& feature_, const Tensor& intr_, const Tensor& extr_,
-                          int64_t W, int64_t H, double bg, double nearest, double extent) {
+                          int64_t W, int64_t H, double bg, double nearest, double extent, bool lazy) {
         Tensor xyz = prep(xyz_, "xyz");
         check_shape(xyz, "xyz", {-1, 3});
         const int64_t N = xyz.size(0);
@@ -399,44 +459,22 @@ struct Rasterize : public torch::autograd::Function<Rasterize> {
         check_shape(extr, "extr", {3, 4});
         c10::cuda::CUDAGuard guard(xyz.device());
         const int dev = xyz.device().index();
-        const int64_t T = ((W + 15) / 16) * ((H + 15) / 16);
-        const int64_t ctl = (int64_t)gfb_render_control_bytes((int)W, (int)H);
-        // one scratch block (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N | final_T 4HW |
-        //                            n_contrib 4HW | tile_range 8T | control
-        const int64_t HW = H * W;
-        const int64_t o_rect = 8 * N, o_depth = 16 * N, o_conic = 20 * N, o_radius = 32 * N, o_ft = 36 * N,
-                      o_nc = o_ft + 4 * HW, o_rng = ((o_nc + 4 * HW + 7) / 8) * 8, o_ctl = o_rng + 8 * T;
-        Tensor scratch = at::empty({o_ctl + ctl + 16}, xyz.options().dtype(at::kByte));
-        char* sp = (char*)scratch.data_ptr();
+        // lazy validation of the speculative K (see gflow_b200/ops.py): only in steady state and only when a
+        // backward will follow
+        lazy = lazy && lazy_k_enabled() && has_k_hint(dev, N, W, H);
         Tensor out = at::empty({C, H, W}, f32(xyz));
-        int64_t cap = capacity_for(dev, N, W, H), K = 0;
-        Tensor kbuf, grad_ws, dbuf;
-        for (;;) {
-            // K-sized block (bytes): geom 32c | feat 16c | keys 8c | ids 4c
-            kbuf = at::empty({15 * std::max<int64_t>(cap, 1)}, f32(xyz));
-            char* kp = (char*)kbuf.data_ptr();
-            check_rc(gfb_render_forward(fp(xyz), fp(scale), fp(rotate), fp(opacity), fp(feature), (int)C, fp(intr), fp(extr),
-                                        (int)N, (int)W, (int)H, (float)bg, (float)nearest, (float)extent, (float*)sp,
-                                        (float*)(sp + o_depth), (float*)(sp + o_conic), (int32_t*)(sp + o_radius),
-                                        sp + o_rect, sp + o_ctl, (int32_t*)(sp + o_rng), cap, kp + 48 * cap,
-                                        (int32_t*)(kp + 56 * cap), kp, kp + 32 * cap, fp(out), (float*)(sp + o_ft),
-                                        (int32_t*)(sp + o_nc), nullptr, stream()),
-                     "rasterization forward");
-            if (!grad_ws.defined()) {  // host bookkeeping overlaps `preprocess`
-                grad_ws = at::empty({12 * N + 16}, f32(xyz));
-                dbuf = at::empty({(11 + C) * std::max<int64_t>(N, 1)}, f32(xyz));
-            }
-            check_rc(gfb_wait_k(&K), "rasterization forward (K)");
-            if (K > cap) {
-                cap = K + K / 8 + 1024;
-                continue;
-            }
-            break;
-        }
-        remember_k(dev, N, W, H, K);
-        ctx->save_for_backward({xyz, scale, rotate, intr, extr, scratch, kbuf, grad_ws, dbuf});
+        RasterForward f = raster_forward(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg, nearest, extent,
+                                         capacity_for(dev, N, W, H), out, lazy);
+        Tensor grad_ws = at::empty({12 * N + 16}, f32(xyz));
+        Tensor dbuf = at::empty({(11 + C) * std::max<int64_t>(N, 1)}, f32(xyz));
+        if (!lazy) remember_k(dev, N, W, H, f.K);
+        if (lazy)
+            ctx->save_for_backward({xyz, scale, rotate, intr, extr, f.scratch, f.kbuf, grad_ws, dbuf, opacity, feature});
+        else
+            ctx->save_for_backward({xyz, scale, rotate, intr, extr, f.scratch, f.kbuf, grad_ws, dbuf});
         ctx->saved_data["C"] = C;
-        ctx->saved_data["cap"] = cap;
+        ctx->saved_data["cap"] = f.cap;
+        ctx->saved_data["ticket"] = lazy ? f.ticket : (int64_t)-1;
         ctx->saved_data["W"] = W;
         ctx->saved_data["H"] = H;
         ctx->saved_data["bg"] = bg;
@@ -447,12 +485,37 @@ struct Rasterize : public torch::autograd::Function<Rasterize> {
     }
     static variable_list backward(AutogradContext* ctx, variable_list g) {
         auto s = ctx->get_saved_variables();
-        const Tensor &xyz = s[0], &scale = s[1], &rotate = s[2], &intr = s[3], &extr = s[4], &scratch = s[5], &kbuf = s[6];
-        Tensor grad_ws = s[7], dbuf = s[8];
-        const int64_t N = xyz.size(0), C = ctx->saved_data["C"].toInt(), cap = ctx->saved_data["cap"].toInt();
-        const int64_t W = ctx->saved_data["W"].toInt(), H = ctx->saved_data["H"].toInt(), HW = H * W;
-        const int64_t T = ((W + 15) / 16) * ((H + 15) / 16);
+        const Tensor &xyz = s[0], &scale = s[1], &rotate = s[2], &intr = s[3], &extr = s[4];
+        Tensor scratch = s[5], kbuf = s[6], grad_ws = s[7], dbuf = s[8];
+        const int64_t N = xyz.size(0), C = ctx->saved_data["C"].toInt();
+        int64_t cap = ctx->saved_data["cap"].toInt();
+        const int64_t W = ctx->saved_data["W"].toInt(), H = ctx->saved_data["H"].toInt();
+        const double bg = ctx->saved_data["bg"].toDouble(), nearest = ctx->saved_data["nearest"].toDouble(),
+                     extent = ctx->saved_data["extent"].toDouble();
         c10::cuda::CUDAGuard guard(xyz.device());
+        const int dev = xyz.device().index();
+        const int64_t ticket = ctx->saved_data["ticket"].toInt();
+        if (ticket >= 0) {  // lazy validation of the forward's speculative capacity
+            ctx->saved_data["ticket"] = (int64_t)-1;
+            int64_t K = -1;
+            const int rc = gfb_wait_k_ticket(ticket, &K);
+            if (rc != 0 && rc != GFB_E_STALE) check_rc(rc, "rasterization backward (K)");
+            if (rc == 0) remember_k(dev, N, W, H, std::max<int64_t>(K, 1));
+            if (rc != 0 || K > cap) {  // corrective pass (or an expired ticket: nothing can be proven)
+                if (rc == 0)
+                    TORCH_WARN("gflow_b200.rasterization: the intersection count grew by more than 25 % between two "
+                               "consecutive calls; the image returned by the earlier forward missed the tail of some tile "
+                               "lists (gradients were recomputed from a corrected pass).  Set GFLOW_B200_LAZY_K=0 to "
+                               "validate K inside every forward.");
+                Tensor discard = at::empty({C, H, W}, f32(xyz));
+                RasterForward f = raster_forward(xyz, scale, rotate, s[9], s[10], intr, extr, W, H, bg, nearest, extent,
+                                                 rc == 0 ? K + K / 8 + 1024 : cap, discard, false);
+                remember_k(dev, N, W, H, std::max<int64_t>(f.K, 1));
+                scratch = f.scratch;
+                kbuf = f.kbuf;
+                cap = f.cap;
+            }
+        }
         if (ctx->saved_data["bwd_done"].toBool()) {  // retain_graph: earlier gradients alias the first buffers
             grad_ws = at::empty_like(grad_ws);
             dbuf = at::empty_like(dbuf);
@@ -460,18 +523,16 @@ struct Rasterize : public torch::autograd::Function<Rasterize> {
         ctx->saved_data["bwd_done"] = true;
         Tensor g_out = prep(g[0], "grad feature_map");
         check_shape(g_out, "grad feature_map", {C, H, W});
-        const int64_t o_ft = 36 * N, o_nc = o_ft + 4 * HW, o_rng = ((o_nc + 4 * HW + 7) / 8) * 8;
-        (void)T;
+        const RasterLayout L(N, W, H);
         char* sp = (char*)scratch.data_ptr();
         char* kp = (char*)kbuf.data_ptr();
         float* dp = fp(dbuf);
         check_rc(gfb_render_backward(fp(xyz), fp(scale), fp(rotate), fp(intr), fp(extr), (int)N, (int)W, (int)H, (int)C,
-                                     (float)ctx->saved_data["bg"].toDouble(), (float)ctx->saved_data["nearest"].toDouble(),
-                                     (float)ctx->saved_data["extent"].toDouble(), (int32_t*)(kp + 56 * cap),
-                                     (int32_t*)(sp + o_rng), cap, kp, kp + 32 * cap, (float*)(sp + o_ft),
-                                     (int32_t*)(sp + o_nc), fp(g_out), grad_ws.data_ptr(), dp + 4 * N, dp + 7 * N, dp,
+                                     (float)bg, (float)nearest, (float)extent, (int32_t*)(kp + 56 * cap),
+                                     (int32_t*)(sp + L.o_rng), cap, kp, kp + 32 * cap, (float*)(sp + L.o_ft),
+                                     (int32_t*)(sp + L.o_nc), fp(g_out), grad_ws.data_ptr(), dp + 4 * N, dp + 7 * N, dp,
                                      dp + 10 * N, dp + 11 * N, stream()),
-                     "rasterization backward");
+                 "rasterization backward");
         Tensor d_rotate = dbuf.narrow(0, 0, 4 * N).view({N, 4});
         Tensor d_xyz = dbuf.narrow(0, 4 * N, 3 * N).view({N, 3});
         Tensor d_scale = dbuf.narrow(0, 7 * N, 3 * N).view({N, 3});
@@ -479,7 +540,7 @@ struct Rasterize : public torch::autograd::Function<Rasterize> {
         Tensor d_feature = dbuf.narrow(0, 11 * N, C * N).view({N, C});
         Tensor d_cam = grad_ws.narrow(0, 12 * N, 16);
         return {d_xyz, d_scale, d_rotate, d_opacity, d_feature, d_cam.narrow(0, 12, 4), d_cam.narrow(0, 0, 12).view({3, 4}),
-                Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
+                Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
     }
 };
 
@@ -508,7 +569,11 @@ Tensor compute_sh(const Tensor& shs, const Tensor& dirs, const c10::optional<Ten
 }
 Tensor rasterization_fused(const Tensor& xyz, const Tensor& scale, const Tensor& rotate, const Tensor& opacity,
                            const Tensor& feature, const Tensor& intr, const Tensor& extr, int64_t W, int64_t H, double bg) {
-    return Rasterize::apply(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg, 0.2, 1.3);
+    // a backward will follow (and validate K) only when autograd records this call
+    const bool lazy = at::GradMode::is_enabled() &&
+                      (xyz.requires_grad() || scale.requires_grad() || rotate.requires_grad() || opacity.requires_grad() ||
+                       feature.requires_grad() || intr.requires_grad() || extr.requires_grad());
+    return Rasterize::apply(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg, 0.2, 1.3, lazy);
 }
 
 }  // namespace

@@ -465,11 +465,65 @@ def compute_sh(shs, dirs, visible=None):
 
 
 # --------------------------------------------------------------------------- rasterization
+import os as _os
+import warnings as _warnings
+
+# Lazy validation of the speculative K (GFLOW_B200_LAZY_K=0 switches it off): in a training loop the forward
+# does not wait for `preprocess` to deliver K -- the capacity guessed from the previous call (+25 %) is checked
+# when the backward starts, by which time the K ticket has long completed.  The host then never blocks on the
+# GPU inside a step and can run ahead of it.  If K did outgrow the guess (it would have to grow by a quarter
+# between two consecutive calls), the backward re-runs the forward with the right capacity before computing
+# gradients and warns that the image already handed out missed the tail of some tile lists.
+_LAZY_K = _os.environ.get("GFLOW_B200_LAZY_K", "1") != "0"
+_CLIPPED_WARNING = ("gflow_b200.rasterization: the intersection count grew by more than 25 % between two consecutive "
+                    "calls; the image returned by the earlier forward missed the tail of some tile lists (gradients were "
+                    "recomputed from a corrected pass).  Set GFLOW_B200_LAZY_K=0 to validate K inside every forward.")
+
+
+def _raster_forward(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr_c, N, C, W, H, bg, nearest, extent, dev,
+                    cap, out, lazy):
+    """Enqueues gfb_render_forward with capacity `cap`.  Returns (kbuf, tbuf, aux, cap, K, ticket): K is None and
+    ticket names the pending hand-off when `lazy`, otherwise K is final (the call retried until it fitted)."""
+    gx, gy = _grid(W, H)
+    T = gx * gy
+    k_host = _ctypes.c_int64(0)
+    # per-Gaussian buffer (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N
+    gbuf = torch.empty(9 * max(N, 1), device=dev, dtype=torch.float32)
+    gp = gbuf.data_ptr()
+    p_uv, p_rect, p_depth, p_conic, p_radius = gp, gp + 8 * N, gp + 16 * N, gp + 20 * N, gp + 32 * N
+    # tile buffer: range 2T int32 (8-byte aligned) | control workspace
+    tbuf = torch.empty(8 * T + _lib.gfb_render_control_bytes(W, H), device=dev, dtype=torch.uint8)
+    tp = tbuf.data_ptr()
+    p_rng, p_ctl = tp, tp + 8 * T
+    aux = torch.empty(2, H, W, device=dev, dtype=torch.float32)  # final_T | n_contrib (int32 bits)
+    while True:
+        # K-sized buffer (bytes): geom 32c | feat 16c | keys 8c | ids 4c
+        kbuf = torch.empty(15 * max(cap, 1), device=dev, dtype=torch.float32)
+        kp = kbuf.data_ptr()
+        rc = _lib.gfb_render_forward(
+            xyz_c.data_ptr(), scale_c.data_ptr(), rotate_c.data_ptr(), opacity_c.data_ptr(),
+            feature_c.data_ptr(), C, intr_c.data_ptr(), extr_c.data_ptr(), N, W, H, bg, nearest, extent,
+            p_uv, p_depth, p_conic, p_radius, p_rect, p_ctl, p_rng, cap, kp + 48 * cap, kp + 56 * cap,
+            kp, kp + 32 * cap, out.data_ptr(), aux.data_ptr(), aux.data_ptr() + 4 * H * W,
+            None, _stream())
+        capi.check(rc, "rasterization forward")
+        ticket = int(_lib.gfb_k_ticket())
+        if lazy:
+            return kbuf, tbuf, aux, cap, None, ticket
+        # everything is enqueued; pick up K (stored by the kernel into mapped pinned memory)
+        capi.check(_lib.gfb_wait_k_ticket(ticket, _ctypes.byref(k_host)), "rasterization forward (K)")
+        K = int(k_host.value)
+        if K > cap:
+            cap = K + K // 8 + 1024
+            continue
+        return kbuf, tbuf, aux, cap, K, ticket
+
+
 class _Rasterize(torch.autograd.Function):
     """Fused chain (gfb_render_forward / gfb_render_backward): 4 + 2 kernels, no mid-pipeline drain."""
 
     @staticmethod
-    def forward(ctx, xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg, nearest, extent):
+    def forward(ctx, xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg, nearest, extent, lazy=False):
         xyz_c = _prep(xyz, "xyz", shape=(None, 3))
         N = xyz_c.shape[0]
         scale_c = _prep(scale, "scale", shape=(N, 3))
@@ -482,59 +536,56 @@ class _Rasterize(torch.autograd.Function):
         intr_c = _prep(intr, "intr", shape=(4,))
         extr_c = _prep(extr, "extr", shape=(3, 4))
         dev = _same_device(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr_c)
-        gx, gy = _grid(W, H)
-        T = gx * gy
+        T = _grid(W, H)[0] * _grid(W, H)[1]
         key = (dev.index, N, W, H)
-        cap = _capacity_for(key, N)
-        k_host = _ctypes.c_int64(0)
+        lazy = bool(lazy) and _LAZY_K and key in _K_HINT
         with _on_device(dev):
-            # per-Gaussian buffer (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N
-            gbuf = torch.empty(9 * max(N, 1), device=dev, dtype=torch.float32)
-            gp = gbuf.data_ptr()
-            p_uv, p_rect, p_depth, p_conic, p_radius = gp, gp + 8 * N, gp + 16 * N, gp + 20 * N, gp + 32 * N
-            # tile buffer: range 2T int32 (8-byte aligned) | control workspace
-            tbuf = torch.empty(8 * T + _lib.gfb_render_control_bytes(W, H), device=dev, dtype=torch.uint8)
-            tp = tbuf.data_ptr()
-            p_rng, p_ctl = tp, tp + 8 * T
             out = torch.empty(C, H, W, device=dev, dtype=torch.float32)
-            aux = torch.empty(2, H, W, device=dev, dtype=torch.float32)  # final_T | n_contrib (int32 bits)
-            bufs = None
-            while True:
-                # K-sized buffer (bytes): geom 32c | feat 16c | keys 8c | ids 4c
-                kbuf = torch.empty(15 * max(cap, 1), device=dev, dtype=torch.float32)
-                kp = kbuf.data_ptr()
-                rc = _lib.gfb_render_forward(
-                    xyz_c.data_ptr(), scale_c.data_ptr(), rotate_c.data_ptr(), opacity_c.data_ptr(),
-                    feature_c.data_ptr(), C, intr_c.data_ptr(), extr_c.data_ptr(), N, W, H, bg, nearest, extent,
-                    p_uv, p_depth, p_conic, p_radius, p_rect, p_ctl, p_rng, cap, kp + 48 * cap, kp + 56 * cap,
-                    kp, kp + 32 * cap, out.data_ptr(), aux.data_ptr(), aux.data_ptr() + 4 * H * W,
-                    None, _stream())
-                capi.check(rc, "rasterization forward")
-                # everything is enqueued; do the host-side bookkeeping while `preprocess` runs, then
-                # pick up K (stored by the kernel into mapped pinned memory)
-                if bufs is None:
-                    # backward buffers: grad pack 12N+16 | d_rotate 4N | d_xyz 3N | d_scale 3N | d_opacity N | d_feature CN
-                    bufs = (torch.empty(12 * N + 16, device=dev, dtype=torch.float32),
-                            torch.empty((11 + C) * max(N, 1), device=dev, dtype=torch.float32))
-                    ctx.save_for_backward(xyz_c, scale_c, rotate_c, intr_c, extr_c)
-                capi.check(_lib.gfb_wait_k(_ctypes.byref(k_host)), "rasterization forward (K)")
-                K = int(k_host.value)
-                if K > cap:
-                    cap = K + K // 8 + 1024
-                    continue
-                break
-        _K_HINT[key] = K
+            kbuf, tbuf, aux, cap, K, ticket = _raster_forward(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr_c,
+                                                              N, C, W, H, bg, nearest, extent, dev, _capacity_for(key, N), out,
+                                                              lazy)
+            # backward buffers: grad pack 12N+16 | d_rotate 4N | d_xyz 3N | d_scale 3N | d_opacity N | d_feature CN
+            bufs = (torch.empty(12 * N + 16, device=dev, dtype=torch.float32),
+                    torch.empty((11 + C) * max(N, 1), device=dev, dtype=torch.float32))
+        if lazy:  # validated when the backward starts; opacity / feature are kept for a corrective pass
+            ctx.save_for_backward(xyz_c, scale_c, rotate_c, intr_c, extr_c, opacity_c, feature_c)
+            ctx.pending = (ticket, key)
+        else:
+            ctx.save_for_backward(xyz_c, scale_c, rotate_c, intr_c, extr_c)
+            ctx.pending = None
+            _K_HINT[key] = K
         ctx.bufs = (kbuf, tbuf, aux) + bufs
         ctx.meta = (N, C, T, cap, W, H, bg, nearest, extent)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        xyz, scale, rotate, intr, extr = ctx.saved_tensors
+        xyz, scale, rotate, intr, extr = ctx.saved_tensors[:5]
         kbuf, tbuf, aux, grad_ws, dbuf = ctx.bufs
         N, C, T, cap, W, H, bg, nearest, extent = ctx.meta
         dev = xyz.device
         with _on_device(dev):
+            if ctx.pending is not None:  # lazy validation of the forward's speculative capacity
+                ticket, key = ctx.pending
+                ctx.pending = None
+                k_host = _ctypes.c_int64(0)
+                rc = _lib.gfb_wait_k_ticket(ticket, _ctypes.byref(k_host))
+                if rc not in (0, capi.GFB_E_STALE):
+                    capi.check(rc, "rasterization backward (K)")
+                K = int(k_host.value) if rc == 0 else None
+                if K is not None:
+                    _K_HINT[key] = max(K, 1)
+                if K is None or K > cap:  # corrective pass (or the ticket expired and nothing can be proven)
+                    if K is not None:
+                        _warnings.warn(_CLIPPED_WARNING, RuntimeWarning, stacklevel=2)
+                    opacity_c, feature_c = ctx.saved_tensors[5:7]
+                    scratch = torch.empty(C, H, W, device=dev, dtype=torch.float32)
+                    cap2 = cap if K is None else K + K // 8 + 1024
+                    kbuf, tbuf, aux, cap, K, _ = _raster_forward(xyz, scale, rotate, opacity_c, feature_c, intr, extr, N, C, W, H,
+                                                                 bg, nearest, extent, dev, cap2, scratch, False)
+                    _K_HINT[key] = max(K, 1)
+                    ctx.bufs = (kbuf, tbuf, aux, grad_ws, dbuf)
+                    ctx.meta = (N, C, T, cap, W, H, bg, nearest, extent)
             if getattr(ctx, "bwd_done", False):  # retain_graph: earlier gradients alias the first buffers
                 grad_ws, dbuf = torch.empty_like(grad_ws), torch.empty_like(dbuf)
             ctx.bwd_done = True
@@ -553,7 +604,7 @@ class _Rasterize(torch.autograd.Function):
         d_feature = dbuf[11 * N:(11 + C) * N].view(N, C)
         d_cam = grad_ws[12 * N:]
         return (d_xyz, d_scale, d_rotate, d_opacity, d_feature, d_cam[12:16], d_cam[:12].view(3, 4), None, None, None,
-                None, None)
+                None, None, None)
 
 
 def rasterization_unfused(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):
@@ -572,7 +623,10 @@ def rasterization(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg):
     Up to four channels run through the fused pipeline; more channels fall back to the operator chain.
     """
     if isinstance(feature, torch.Tensor) and feature.dim() == 2 and 1 <= feature.shape[1] <= 4:
-        return _Rasterize.apply(xyz, scale, rotate, opacity, feature, intr, extr, int(W), int(H), float(bg), 0.2, 1.3)
+        # a backward will follow (and validate K) only when autograd records this call
+        lazy = torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad
+                                               for t in (xyz, scale, rotate, opacity, feature, intr, extr))
+        return _Rasterize.apply(xyz, scale, rotate, opacity, feature, intr, extr, int(W), int(H), float(bg), 0.2, 1.3, lazy)
     return rasterization_unfused(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg)
 
 

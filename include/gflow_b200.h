@@ -34,6 +34,8 @@ extern "C" {
 #define GFB_E_BADARG (-1)     /* NULL pointer / negative size / unsupported channel count */
 #define GFB_E_UNSUPPORTED (-2)
 #define GFB_E_CAPACITY (-3)    /* K exceeded the caller's capacity: outputs are truncated, retry larger */
+#define GFB_E_STALE (-4)       /* K ticket expired: its hand-off slot has been reused (256 later hand-offs on the device) */
+#define GFB_E_NOTREADY (-5)    /* gfb_query_k_ticket: the producing kernel has not finished yet */
 
 /* library / build information */
 int gfb_version(void);                 /* 100 * major + minor */
@@ -142,9 +144,20 @@ int gfb_blend_unpack_grads(const float *grad_pack, int N, int C, int c0, int Cg,
  *   out (C,H,W), final_T (H,W), n_contrib (H,W)
  * K is delivered to *K_host (HOST pointer); GFB_E_CAPACITY as in gfb_sort_gaussian.  With K_host == NULL
  * the call returns without waiting; the caller overlaps host work and then calls gfb_wait_k(&K), which
- * blocks until the most recent K of the current device has landed (compare it with capacity). */
+ * blocks until the K of the calling thread's most recent hand-off has landed (compare it with capacity).
+ *
+ * Every hand-off (gfb_sort_gaussian, gfb_render_forward) owns a slot of a per-device ring of pinned words +
+ * events and is named by a ticket, so calls interleaved from several streams or host threads never see each
+ * other's K, and a caller may validate its speculative capacity late (msplat.rasterization does so in its
+ * backward, which keeps the host out of the forward path):
+ *   gfb_k_ticket()                 ticket of the calling thread's most recent hand-off (-1: none yet)
+ *   gfb_wait_k_ticket(t, &K)       blocks on that hand-off only; GFB_E_STALE if the slot has been reused
+ *   gfb_query_k_ticket(t, &K)      same without blocking; GFB_E_NOTREADY while the kernel is still running */
 size_t gfb_render_control_bytes(int W, int H);
 int gfb_wait_k(int64_t *K_host);
+int64_t gfb_k_ticket(void);
+int gfb_wait_k_ticket(int64_t ticket, int64_t *K_host);
+int gfb_query_k_ticket(int64_t ticket, int64_t *K_host);
 int gfb_render_forward(const float *xyz, const float *scale, const float *rotate, const float *opacity,
                        const float *feature, int C, const float *intr, const float *extr, int N, int W, int H,
                        float bg, float nearest, float extent, float *uv, float *depth, float *conic, int32_t *radius,

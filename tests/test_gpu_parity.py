@@ -614,3 +614,115 @@ def test_against_real_msplat(G):
     assert torch.equal(o["radius"].reshape(-1).cpu(), r["radius"].reshape(-1).cpu().to(torch.int32)), "radius vs msplat"
     assert torch.equal(o["ids"].cpu(), r["ids"].cpu().to(torch.int32)), "gaussian_ids_sorted vs msplat"
     assert_close(o["img"], r["img"], 1e-4, "image vs msplat", **IMG_OUTLIERS)
+
+
+def test_k_handoff_is_reentrant_across_streams_and_threads(G):
+    """Every K hand-off owns a slot of a per-device ring (ticket): two streams interleaving gfb_render_forward get
+    their own K each, in any pick-up order, and host threads rasterising different scenes concurrently get the
+    images a single thread gets (round 1 kept ONE pinned word per device and overwrote it)."""
+    import ctypes
+    import threading
+
+    from gflow_b200 import capi, ops
+
+    lib = capi.load()
+    scenes = [make_scene(3000, 160, 120, seed=31), make_scene(9000, 160, 120, seed=32, profile="gflow")]
+    want, refs = [], []
+    for sc in scenes:
+        args = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
+        uv, depth = G.project_point(args[0], args[5], args[6], sc.W, sc.H)
+        vis = depth != 0
+        conic, radius, tiles = G.ewa_project(args[0], G.compute_cov3d(args[1], args[2], vis), args[5], args[6], uv, sc.W, sc.H, vis)
+        want.append(int(tiles.sum()))
+        refs.append(G.rasterization(*args, sc.W, sc.H, 0.0).clone())
+    assert want[0] != want[1]
+    # two streams, forwards enqueued back to back without waiting, K picked up in reverse order
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    tickets, keep = [], []
+    for sc, st in zip(scenes, streams):
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            a = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
+            out = torch.empty(3, sc.H, sc.W, device=DEV)
+            res = ops._raster_forward(a[0], a[1], a[2], a[3].reshape(-1).contiguous(), a[4], a[5], a[6], sc.xyz.shape[0], 3,
+                                      sc.W, sc.H, 0.0, 0.2, 1.3, torch.device(DEV), 4 * sc.xyz.shape[0] + 4096, out, True)
+            tickets.append(res[5])
+            keep.append((a, out, res))
+    assert tickets[0] != tickets[1] and min(tickets) >= 0
+    for i in (1, 0):
+        k = ctypes.c_int64(-1)
+        capi.check(lib.gfb_wait_k_ticket(tickets[i], ctypes.byref(k)), "wait ticket")
+        assert int(k.value) == want[i], (i, int(k.value), want)
+    k = ctypes.c_int64(-1)
+    assert lib.gfb_query_k_ticket(tickets[0], ctypes.byref(k)) == 0 and int(k.value) == want[0]
+    torch.cuda.synchronize()
+    for (a, out, res), ref in zip(keep, refs):
+        assert torch.equal(out, ref)
+    # a ticket expires once its slot has been reused (ring of 256 hand-offs per device)
+    sc = scenes[0]
+    a = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
+    for _ in range(260):
+        G.rasterization(*a, sc.W, sc.H, 0.0)
+    assert lib.gfb_wait_k_ticket(tickets[0], ctypes.byref(k)) == capi.GFB_E_STALE
+    # two host threads, each on its own stream and scene
+    errors = []
+
+    def worker(i):
+        try:
+            sc = scenes[i]
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                a = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
+                ps = [t.clone().requires_grad_(True) for t in a[:5]]
+                for _ in range(40):
+                    img = G.rasterization(*ps, a[5], a[6], sc.W, sc.H, 0.0)
+                    img.sum().backward()
+                    if not torch.equal(img.detach(), refs[i]):
+                        errors.append(f"thread {i}: image differs")
+                        break
+            st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+def test_lazy_k_validation_corrects_an_outgrown_capacity(G):
+    """In a training loop msplat.rasterization does not wait for K in the forward (the host stays out of the step);
+    the guess is validated when the backward starts.  Steady state: identical images / gradients with and without.
+    Outgrown guess (forced here): the backward warns, re-runs the forward and still returns the right gradients."""
+    import warnings
+
+    from gflow_b200 import ops
+
+    sc = make_scene(4000, 160, 120, seed=9)
+    Gimg = cu(make_grad_image(3, sc.W, sc.H))
+    args = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
+
+    def run():
+        ps = [a.clone().requires_grad_(True) for a in args]
+        img = G.rasterization(*ps, sc.W, sc.H, 0.0)
+        img.backward(Gimg)
+        return img.detach().clone(), [p.grad.clone() for p in ps]
+
+    ref_img = G.rasterization(*args, sc.W, sc.H, 0.0)  # no grad: synchronous K, also seeds the hint
+    img1, g1 = run()   # first recorded call: a hint exists -> lazy
+    img2, g2 = run()
+    assert torch.equal(img1, ref_img) and torch.equal(img2, ref_img)
+    for a, b in zip(g1, g2):
+        assert_close(a, b, 1e-5, "lazy steady state grads")
+    ops.debug_set_k_hints(1)  # the next forward speculates with room for ~4k intersections only
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        img3, g3 = run()
+    assert any("grew by more than 25" in str(x.message) for x in w), [str(x.message) for x in w]
+    assert not torch.equal(img3, ref_img), "the forced under-sized forward must have clipped the image (test premise)"
+    for a, b in zip(g3, g1):
+        assert_close(a, b, 1e-5, "grads after the corrective pass")
+    img4, g4 = run()  # the hint is healed
+    assert torch.equal(img4, ref_img)
