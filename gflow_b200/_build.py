@@ -34,13 +34,34 @@ def _nvcc() -> str:
 
 
 def _fingerprint() -> str:
+    """Hash of the sources by NAME and content: the repository is copied to other roots (the GPU box), and a
+    fingerprint over absolute paths made every process there rebuild the library on import."""
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "gflow_b200.h"), __file__]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())
             h.update(fh.read())
     return h.hexdigest()
+
+
+class _BuildLock:
+    """Inter-process lock around stale-check + build + stamp: under torchrun every rank imports the package at once,
+    and two ranks compiling into the same files handed a half-written libgflow_b200.so to dlopen."""
+
+    def __enter__(self):
+        import fcntl
+
+        os.makedirs(LIB_DIR, exist_ok=True)
+        self.fh = open(os.path.join(LIB_DIR, ".build.lock"), "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
 
 
 def needs_build() -> bool:
@@ -54,7 +75,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a and link libgflow_b200.so."""
     if not force and not needs_build():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    with _BuildLock():
+        if not force and not needs_build():  # another process built it while we waited
+            return LIB_PATH
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     env = dict(os.environ)
     if os.path.exists("/usr/bin/g++"):
@@ -71,11 +98,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + log[-1])
         objs.append(obj)
-    cmd = [nvcc, *ARCH_FLAGS, *host, "-shared", "-o", LIB_PATH, *objs]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    cmd = [nvcc, *ARCH_FLAGS, *host, "-shared", "-o", tmp, *objs]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
     log.append("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + log[-1])
+    os.replace(tmp, LIB_PATH)  # atomic: a concurrent dlopen sees the old or the new file, never a partial one
     with open(os.path.join(LIB_DIR, "build.log"), "w") as fh:
         fh.write("\n".join(log))
     with open(_STAMP, "w") as fh:
@@ -116,6 +145,14 @@ def build_torch_ext(force: bool = False) -> str:
     """g++ csrc/torch_ext.cpp -> _lib/_gfb_torch.so (needs libgflow_b200.so to exist)."""
     if not force and not ext_needs_build():
         return EXT_PATH
+    build()
+    with _BuildLock():
+        if not force and not ext_needs_build():
+            return EXT_PATH
+        return _build_torch_ext_locked()
+
+
+def _build_torch_ext_locked() -> str:
     import sysconfig
     import warnings
 
@@ -123,7 +160,6 @@ def build_torch_ext(force: bool = False) -> str:
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         from torch.utils import cpp_extension as ce
-    build()
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     inc = [os.path.join(os.path.dirname(torch.__file__), "include"),
            os.path.join(os.path.dirname(torch.__file__), "include", "torch", "csrc", "api", "include"),
@@ -133,7 +169,7 @@ def build_torch_ext(force: bool = False) -> str:
     extra = list(getattr(ce, "_get_pybind11_abi_build_flags", lambda: [])())
     cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={int(bool(abi))}",
            f"-DTORCH_EXTENSION_NAME={EXT_NAME}", "-DTORCH_API_INCLUDE_EXTENSION_H", *extra,
-           *[f"-I{i}" for i in inc], os.path.join(CSRC, "torch_ext.cpp"), "-o", EXT_PATH,
+           *[f"-I{i}" for i in inc], os.path.join(CSRC, "torch_ext.cpp"), "-o", EXT_PATH + f".tmp{os.getpid()}",
            f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
            f"-L{LIB_DIR}", "-lgflow_b200", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -141,6 +177,7 @@ def build_torch_ext(force: bool = False) -> str:
         fh.write("$ " + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("torch extension build failed:\n" + (res.stdout + res.stderr)[-4000:])
+    os.replace(EXT_PATH + f".tmp{os.getpid()}", EXT_PATH)
     with open(_EXT_STAMP, "w") as fh:
         fh.write(_ext_fingerprint())
     return EXT_PATH

@@ -202,9 +202,9 @@ def sort_gaussian(uv, depth, W, H, radius, tiles_touched):
     v = uv[:, 1].detach().to(torch.float32)
     r = radius.reshape(-1)
     tt = tiles_touched.reshape(-1)
-    x0, y0, x1, y1 = (a.numpy() for a in _tile_rect(u, v, r.to(torch.float32), W, H))
-    live = ((r > 0) & (tt > 0)).numpy()
-    dbits = depth.detach().reshape(-1).to(torch.float32).contiguous().numpy().view(np.uint32)
+    x0, y0, x1, y1 = (a.cpu().numpy() for a in _tile_rect(u, v, r.to(torch.float32), W, H))
+    live = ((r > 0) & (tt > 0)).cpu().numpy()
+    dbits = depth.detach().reshape(-1).to(torch.float32).contiguous().cpu().numpy().view(np.uint32)
     tiles_l, ids_l, d_l = [], [], []
     for i in np.nonzero(live)[0]:
         ys, xs = np.meshgrid(np.arange(y0[i], y1[i]), np.arange(x0[i], x1[i]), indexing="ij")
@@ -213,7 +213,7 @@ def sort_gaussian(uv, depth, W, H, radius, tiles_touched):
         ids_l.append(np.full(t.shape, i, dtype=np.int64))
         d_l.append(np.full(t.shape, dbits[i], dtype=np.uint64))
     if not tiles_l:
-        return torch.zeros(0, dtype=torch.int32), torch.zeros(T, 2, dtype=torch.int32)
+        return torch.zeros(0, dtype=torch.int32, device=uv.device), torch.zeros(T, 2, dtype=torch.int32, device=uv.device)
     tiles = np.concatenate(tiles_l).astype(np.uint64)
     ids = np.concatenate(ids_l)
     keys = (tiles << np.uint64(32)) | np.concatenate(d_l)
@@ -226,7 +226,7 @@ def sort_gaussian(uv, depth, W, H, radius, tiles_touched):
     nz = ends > starts
     rng[nz, 0] = starts[nz]
     rng[nz, 1] = ends[nz]
-    return torch.from_numpy(ids_sorted), torch.from_numpy(rng)
+    return torch.from_numpy(ids_sorted).to(uv.device), torch.from_numpy(rng).to(uv.device)
 
 
 # --------------------------------------------------------------------------- a6 / a7
@@ -247,9 +247,10 @@ def alpha_blending(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range,
     gx = (W + TILE - 1) // TILE
     gy = (H + TILE - 1) // TILE
     rows = []
-    finalT = torch.ones(H, W, dtype=dt)
-    ncontrib = torch.zeros(H, W, dtype=torch.int32)
-    rng = tile_range.to(torch.int64)
+    dev = feature.device  # the oracle is device agnostic: with CUDA tensors it doubles as the eager-PyTorch proxy
+    finalT = torch.ones(H, W, dtype=dt, device=dev)
+    ncontrib = torch.zeros(H, W, dtype=torch.int32, device=dev)
+    rng = tile_range.to(torch.int64).cpu()
     ids_all = gaussian_ids_sorted.to(torch.int64)
     for ty in range(gy):
         row = []
@@ -259,12 +260,12 @@ def alpha_blending(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range,
             hh = min(TILE, H - ty * TILE)
             ww = min(TILE, W - tx * TILE)
             if e <= s:
-                row.append(torch.full((C, hh, ww), float(bg), dtype=dt))
+                row.append(torch.full((C, hh, ww), float(bg), dtype=dt, device=dev))
                 continue
             ids = ids_all[s:e]
             py, px = torch.meshgrid(
-                torch.arange(ty * TILE, ty * TILE + hh, dtype=dt),
-                torch.arange(tx * TILE, tx * TILE + ww, dtype=dt),
+                torch.arange(ty * TILE, ty * TILE + hh, dtype=dt, device=dev),
+                torch.arange(tx * TILE, tx * TILE + ww, dtype=dt, device=dev),
                 indexing="ij",
             )
             px = px.reshape(-1, 1)
@@ -294,7 +295,7 @@ def alpha_blending(uv, conic, opacity, feature, gaussian_ids_sorted, tile_range,
             if return_aux:
                 n = e - s
                 contrib = (wgt.detach() > 0) | (valid & ~excluded)
-                idx = torch.arange(1, n + 1, dtype=torch.int32).reshape(1, -1)
+                idx = torch.arange(1, n + 1, dtype=torch.int32, device=dev).reshape(1, -1)
                 last = torch.where(contrib, idx, torch.zeros_like(idx)).max(dim=1).values
                 finalT[ty * TILE: ty * TILE + hh, tx * TILE: tx * TILE + ww] = t_fin.detach().reshape(hh, ww)
                 ncontrib[ty * TILE: ty * TILE + hh, tx * TILE: tx * TILE + ww] = last.reshape(hh, ww)

@@ -227,7 +227,7 @@ static inline int __reduce_add_sync(unsigned mask, int v) {
 
 // ------------------------------------------------------------------ CUDA runtime subset (host side)
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorNotReady = 600 };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum { cudaHostAllocMapped = 2, cudaEventDisableTiming = 2 };
@@ -250,6 +250,7 @@ static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = cal
 static inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)1; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 
