@@ -370,12 +370,31 @@ def run_ours(args):
     launches = (lib.gfb_kernel_launch_count() - launches0) // max(1, args.blocks)
     value = world * args.steps / (blk_ms / 1e3)
 
+    # ---- the same step as ONE CUDA graph (gflow_b200.GraphedRenderStep): no autograd engine, one launch per step
+    graphed = None
+    if not use_sh:
+        gstep = G.GraphedRenderStep(*[p.detach() for p in params], intr, extr, W, H, sc.bg)
+        gstep.g_image.copy_(Gimg)
+        for _ in range(3):
+            gstep()
+        g_ms, g_blocks, _, _ = timed_blocks(gstep, args.steps, max(1, args.blocks))
+        gstep.check()
+        graphed = {"value": world * args.steps / (g_ms / 1e3), "unit": UNIT, "ms_per_step": g_ms / args.steps,
+                   "blocks_ms": [round(b, 4) for b in g_blocks], "K": gstep.k(), "capacity": gstep.capacity,
+                   "what": "gflow_b200.GraphedRenderStep: gfb_render_forward + gfb_render_backward captured once into a CUDA "
+                           "graph over static buffers, one cudaGraphLaunch per step (same kernels, same inputs, same L2 "
+                           "flush); the eager autograd step above spends ~125 us of host time per step"}
+        del gstep
+
     # ---- e2e: the same step with pinned HOST buffers (gflow_b200.hostapi.HostRenderStep): H2D of the step's inputs
     #      and D2H of loss + gradients inside the timed region, copies double buffered against the kernels
+    host_in = torch.empty(sum(p.numel() for p in params) + 16, dtype=torch.float32).pin_memory()
+    o = 0
+    for t in [p.detach() for p in params] + [intr, extr]:
+        host_in[o:o + t.numel()].copy_(t.reshape(-1).cpu())
+        o += t.numel()
     host = hostapi.HostRenderStep(N, W, H, tuple(params[4].shape[1:]), Gimg, sc.bg, dev, depth=2,
-                                  colour=sh_colour if use_sh else None)
-    host_in = host.host_input_block()
-    host.pack_input(host_in, [p.detach() for p in params] + [intr, extr])
+                                  colour=sh_colour if use_sh else None, sample_input=host_in)
     host_outs = [host.host_output_block() for _ in range(2)]
     n_e2e = max(5, min(args.steps, 50))
     for i in range(3):
@@ -398,8 +417,9 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t = float(tt.item())
         e2e_blocks.append(t)
+    host.check()
     e2e_value = world * n_e2e / (statistics.median(e2e_blocks) / 1e3)
-    e2e_loss = float(host.unpack_output(host_outs[(n_e2e - 1) % 2])[6][0])
+    e2e_loss = float(host.unpack_output(host_outs[(n_e2e - 1) % 2])["loss"][0])
 
     # ---- roofline of the dominant kernel (alpha-blending backward), timed alone with CUDA events
     roof = kernel_roofline(G, lib, params, intr, extr, Gimg, sc.bg, N, W, H, T, P, flush_l2, dev, clocks,
@@ -469,7 +489,8 @@ def run_ours(args):
                        "api": f"msplat.rasterization (gflow_b200.ops, fused pipeline, {G.BACKEND} binding) -> C ABI",
                        "timing": f"median of {max(1, args.blocks)} blocks of {args.steps} steps, max over ranks per block"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
-                    "steps": n_e2e, "api": "gflow_b200.hostapi.HostRenderStep (pinned host blocks, copy stream, 2 steps in flight)",
+                    "steps": n_e2e, "api": "gflow_b200.hostapi.HostRenderStep (pinned host blocks, copy stream, 2 steps in flight, compute as "
+                           + ("one CUDA graph per slot)" if host.graphed else "eager autograd: SH colour)"),
                     "loss_read_back": e2e_loss},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
@@ -480,7 +501,7 @@ def run_ours(args):
         }
         if cores_per_rank is not None:
             line["config"]["host_cores_per_rank"] = cores_per_rank
-        for k, v in (("operator_chain", chain), ("gflow_iteration", iteration), ("sequence", sequence), ("cpu_baseline", cpu),
+        for k, v in (("graphed", graphed), ("operator_chain", chain), ("gflow_iteration", iteration), ("sequence", sequence), ("cpu_baseline", cpu),
                      ("fit_loop", fit_loop), ("gpu_proxy_baseline", proxy)):
             if v is not None:
                 line[k] = v

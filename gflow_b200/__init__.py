@@ -20,7 +20,9 @@ from .ops import (  # noqa: F401
     sort_gaussian,
 )
 
-__version__ = "1.0"
+from .graphs import GraphedRenderStep  # noqa: F401,E402  (forward + backward as one CUDA graph)
+
+__version__ = "1.1"
 DROPIN_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "dropin")
 
 

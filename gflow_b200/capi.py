@@ -33,6 +33,7 @@ SIGNATURES = {
     "gfb_sort_tile_workspace_bytes": (c_size_t, [I, I]),
     "gfb_sort_gaussian": (I, [P, P, P, P, I, I, I, P, L, P, P, P, P, P]),
     "gfb_render_control_bytes": (c_size_t, [I, I]),
+    "gfb_render_control_k_offset": (c_size_t, [I, I]),
     "gfb_wait_k": (I, [P]),
     "gfb_k_ticket": (c_int64, []),
     "gfb_wait_k_ticket": (I, [L, P]),

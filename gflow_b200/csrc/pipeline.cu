@@ -117,7 +117,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
     const int total = cta_exclusive_scan(counts, T * R, offsets, s_buf, s_scan);
     if (threadIdx.x == 0) {
         ctrl[CTRL_K] = total;
-        *k_mapped = total;  // mapped pinned host word: no D2H copy in the stream
+        if (k_mapped) *k_mapped = total;  // mapped pinned host word: no D2H copy in the stream
         __threadfence_system();
     }
 }
@@ -290,6 +290,12 @@ int gfb_internal_scatter_sort_pack(const void* rect_ws, const float* depth, int 
 
 extern "C" {
 
+size_t gfb_render_control_k_offset(int W, int H) {
+    if (W <= 0 || H <= 0) return 0;
+    const size_t T = (size_t)((W + GFB_TILE - 1) / GFB_TILE) * ((H + GFB_TILE - 1) / GFB_TILE);
+    return (T * (size_t)gfb_tile_replicas((int)T) + CTRL_K) * sizeof(int32_t);
+}
+
 size_t gfb_render_control_bytes(int W, int H) {
     if (W <= 0 || H <= 0) return 0;
     const size_t T = (size_t)((W + GFB_TILE - 1) / GFB_TILE) * ((H + GFB_TILE - 1) / GFB_TILE);
@@ -319,8 +325,18 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     int32_t* tile_offsets = ctrl + CTRL_WORDS;
     int32_t *pinned = nullptr, *mapped = nullptr;
     cudaEvent_t ev = nullptr;
-    int rc = gfb_internal_host_sync(&pinned, &mapped, &ev);
-    if (rc) return rc;
+    // Captured into a CUDA graph: no K hand-off (an event recorded inside a capture cannot be waited on, and the
+    // ring slot would not be the replay's).  K still lands in the control block (gfb_render_control_k_offset), where
+    // the owner of the graph reads it after a replay; kernels clamp at `capacity` as always.
+    cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+    GFB_TRY(cudaStreamIsCapturing(st, &cap_status));
+    const bool capturing = cap_status != cudaStreamCaptureStatusNone;
+    if (capturing && K_host) return GFB_E_UNSUPPORTED;
+    int rc = 0;
+    if (!capturing) {
+        rc = gfb_internal_host_sync(&pinned, &mapped, &ev);
+        if (rc) return rc;
+    }
     GFB_TRY(cudaMemsetAsync(control_ws, 0, ((size_t)T * R + CTRL_WORDS) * sizeof(int32_t), st));
     // N == 0 still runs one CTA so the scan zeroes the offsets
     if (gfb_tight_tiles())
@@ -334,7 +350,7 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
             reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect_ws), counts,
             tile_offsets, ctrl, mapped, T, R, opacity);
     GFB_CHECK_LAUNCH();
-    GFB_TRY(cudaEventRecord(ev, st));
+    if (!capturing) GFB_TRY(cudaEventRecord(ev, st));
     // speculative part: enqueued before K is known on the host
     rc = gfb_internal_scatter_sort_pack(rect_ws, depth, N, W, H, control_ws, capacity, keys_ws, tile_range, uv, conic,
                                         opacity, feature, C, gaussian_ids_sorted, geom_stream, feat_stream, stream,

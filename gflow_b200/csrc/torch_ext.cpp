@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "gflow_b200.h"
 
@@ -382,6 +383,18 @@ bool has_k_hint(int dev, int64_t N, int64_t W, int64_t H) {
     std::lock_guard<std::mutex> lock(g_hint_mutex);
     return g_hint.find({dev, N, W, H}) != g_hint.end();
 }
+// lazy validation is only used for a call that continues a loop over the SAME parameter tensor: the storage of xyz
+// was seen by one of the last few calls of this size (a different scene of the same size takes the synchronous path)
+std::map<std::tuple<int, int64_t, int64_t, int64_t>, std::vector<const void*>> g_lazy_seen;
+bool continues_a_loop(int dev, int64_t N, int64_t W, int64_t H, const void* xyz_ptr) {
+    std::lock_guard<std::mutex> lock(g_hint_mutex);
+    auto& seen = g_lazy_seen[{dev, N, W, H}];
+    for (const void* p : seen)
+        if (p == xyz_ptr) return true;
+    seen.push_back(xyz_ptr);
+    if (seen.size() > 4) seen.erase(seen.begin());
+    return false;
+}
 bool lazy_k_enabled() {
     static const bool on = [] {
         const char* e = getenv("GFLOW_B200_LAZY_K");
@@ -461,7 +474,7 @@ struct Rasterize : public torch::autograd::Function<Rasterize> {
         const int dev = xyz.device().index();
         // lazy validation of the speculative K (see gflow_b200/ops.py): only in steady state and only when a
         // backward will follow
-        lazy = lazy && lazy_k_enabled() && has_k_hint(dev, N, W, H);
+        lazy = continues_a_loop(dev, N, W, H, xyz.data_ptr()) && lazy && lazy_k_enabled() && has_k_hint(dev, N, W, H);
         Tensor out = at::empty({C, H, W}, f32(xyz));
         RasterForward f = raster_forward(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg, nearest, extent,
                                          capacity_for(dev, N, W, H), out, lazy);

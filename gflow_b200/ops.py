@@ -474,7 +474,21 @@ import warnings as _warnings
 # GPU inside a step and can run ahead of it.  If K did outgrow the guess (it would have to grow by a quarter
 # between two consecutive calls), the backward re-runs the forward with the right capacity before computing
 # gradients and warns that the image already handed out missed the tail of some tile lists.
+# It is only used for a call that continues a loop over the SAME parameter tensor (the storage of `xyz` was seen by one
+# of the last few calls of this size): a different scene of the same size takes the synchronous path, so an image is
+# never clipped because an unrelated earlier call left a small K behind.
 _LAZY_K = _os.environ.get("GFLOW_B200_LAZY_K", "1") != "0"
+_LAZY_SEEN = {}  # (device index, N, W, H) -> data pointers of the last few xyz tensors rasterised at this size
+
+
+def _continues_a_loop(key, xyz_c) -> bool:
+    seen = _LAZY_SEEN.setdefault(key, [])
+    ptr = xyz_c.data_ptr()
+    hit = ptr in seen
+    if not hit:
+        seen.append(ptr)
+        del seen[:-4]
+    return hit
 _CLIPPED_WARNING = ("gflow_b200.rasterization: the intersection count grew by more than 25 % between two consecutive "
                     "calls; the image returned by the earlier forward missed the tail of some tile lists (gradients were "
                     "recomputed from a corrected pass).  Set GFLOW_B200_LAZY_K=0 to validate K inside every forward.")
@@ -538,7 +552,7 @@ class _Rasterize(torch.autograd.Function):
         dev = _same_device(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr_c)
         T = _grid(W, H)[0] * _grid(W, H)[1]
         key = (dev.index, N, W, H)
-        lazy = bool(lazy) and _LAZY_K and key in _K_HINT
+        lazy = _continues_a_loop(key, xyz_c) and bool(lazy) and _LAZY_K and key in _K_HINT
         with _on_device(dev):
             out = torch.empty(C, H, W, device=dev, dtype=torch.float32)
             kbuf, tbuf, aux, cap, K, ticket = _raster_forward(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr_c,

@@ -154,6 +154,10 @@ int gfb_blend_unpack_grads(const float *grad_pack, int N, int C, int c0, int Cg,
  *   gfb_wait_k_ticket(t, &K)       blocks on that hand-off only; GFB_E_STALE if the slot has been reused
  *   gfb_query_k_ticket(t, &K)      same without blocking; GFB_E_NOTREADY while the kernel is still running */
 size_t gfb_render_control_bytes(int W, int H);
+/* Byte offset, inside control_ws, of the int32 word that receives K (device memory).  A forward captured into a CUDA
+ * graph makes no K hand-off (gfb_k_ticket() is unchanged, K_host must be NULL); the owner of the graph reads this
+ * word after a replay and compares it with the capacity the graph was captured with. */
+size_t gfb_render_control_k_offset(int W, int H);
 int gfb_wait_k(int64_t *K_host);
 int64_t gfb_k_ticket(void);
 int gfb_wait_k_ticket(int64_t ticket, int64_t *K_host);

@@ -704,15 +704,20 @@ def test_lazy_k_validation_corrects_an_outgrown_capacity(G):
     Gimg = cu(make_grad_image(3, sc.W, sc.H))
     args = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
 
+    ps = [a.clone().requires_grad_(True) for a in args]  # one set of parameter tensors, as in a training loop
+
     def run():
-        ps = [a.clone().requires_grad_(True) for a in args]
+        for p in ps:
+            p.grad = None
         img = G.rasterization(*ps, sc.W, sc.H, 0.0)
         img.backward(Gimg)
         return img.detach().clone(), [p.grad.clone() for p in ps]
 
     ref_img = G.rasterization(*args, sc.W, sc.H, 0.0)  # no grad: synchronous K, also seeds the hint
-    img1, g1 = run()   # first recorded call: a hint exists -> lazy
+    img0, g0 = run()   # first call on these tensors: synchronous
+    img1, g1 = run()   # continues the loop on the same tensors: lazy
     img2, g2 = run()
+    assert torch.equal(img0, ref_img)
     assert torch.equal(img1, ref_img) and torch.equal(img2, ref_img)
     for a, b in zip(g1, g2):
         assert_close(a, b, 1e-5, "lazy steady state grads")
@@ -726,3 +731,85 @@ def test_lazy_k_validation_corrects_an_outgrown_capacity(G):
         assert_close(a, b, 1e-5, "grads after the corrective pass")
     img4, g4 = run()  # the hint is healed
     assert torch.equal(img4, ref_img)
+    # another scene of the same size right after a small one must not inherit its K (synchronous path: exact image)
+    big = make_scene(4000, 160, 120, seed=10, profile="synthetic")
+    small = make_scene(4000, 160, 120, seed=11, profile="gflow")
+    for scn in (small, big):
+        a = [t.requires_grad_(True) for t in cu(scn.xyz, scn.scale, scn.rotate, scn.opacity, scn.rgb)]
+        fused = G.rasterization(*a, *cu(scn.intr, scn.extr), scn.W, scn.H, 0.0)
+        chain = G.rasterization_unfused(*a, *cu(scn.intr, scn.extr), scn.W, scn.H, 0.0)
+        assert torch.equal(fused, chain)
+
+
+def test_graphed_render_step_equals_the_eager_step(G):
+    """GraphedRenderStep: forward + backward captured into one CUDA graph over static buffers.  Replays give the eager
+    step's image bit for bit and its gradients to atomics ordering, follow in-place parameter updates, report K, and
+    refuse results once the scene outgrows the captured capacity."""
+    sc = make_scene(8000, 320, 200, seed=14, profile="gflow", bg=0.2)
+    args = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
+    Gimg = cu(make_grad_image(3, sc.W, sc.H))
+
+    def eager(a):
+        ps = [t.clone().requires_grad_(True) for t in a]
+        img = G.rasterization(*ps, sc.W, sc.H, sc.bg)
+        img.backward(Gimg)
+        return img.detach(), ps
+
+    step = G.GraphedRenderStep(*args, sc.W, sc.H, sc.bg)
+    step.g_image.copy_(Gimg)
+    for trial in range(2):
+        img = step()
+        ref_img, ps = eager([step.xyz, step.scale, step.rotate, step.opacity.reshape(-1, 1), step.feature, step.intr, step.extr])
+        assert torch.equal(img, ref_img), "graph replay must reproduce the eager image"
+        for name, p in zip(["xyz", "scale", "rotate", "opacity", "feature", "intr", "extr"], ps):
+            assert_close(step.grads[name].reshape(p.grad.shape), p.grad, 1e-4, "graphed grad " + name)
+        with torch.no_grad():  # in-place update of the static parameters: the next replay must see it
+            step.xyz.add_(0.01 * torch.randn_like(step.xyz))
+            step.feature.mul_(0.9)
+    uv, depth = G.project_point(step.xyz, step.intr, step.extr, sc.W, sc.H)
+    vis = depth != 0
+    _, _, tiles = G.ewa_project(step.xyz, G.compute_cov3d(step.scale, step.rotate, vis), step.intr, step.extr, uv, sc.W, sc.H, vis)
+    step()
+    assert step.k() == int(tiles.sum())
+    step.check()
+    small = G.GraphedRenderStep(*args, sc.W, sc.H, sc.bg, capacity=1000)
+    small()
+    assert small.k() > 1000
+    with pytest.raises(RuntimeError, match="captured for"):
+        small.check()
+
+
+def test_host_render_step_matches_the_device_step(G):
+    """gflow_b200.hostapi.HostRenderStep (pinned host blocks in, gradients + loss out; the compute of a slot is one
+    CUDA graph): every submitted step returns the gradients of the device-resident autograd step for ITS inputs, also
+    when consecutive steps carry different inputs through the two slots."""
+    from gflow_b200 import hostapi
+
+    sc = make_scene(6000, 320, 200, seed=21, bg=0.1)
+    Gimg = cu(make_grad_image(3, sc.W, sc.H))
+    host = None
+    ins, outs, refs = [], [], []
+    for i in range(3):
+        xyz = sc.xyz + 0.02 * i
+        tens = [xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb * (1.0 - 0.1 * i), sc.intr, sc.extr]
+        if host is None:
+            block = torch.cat([t.reshape(-1) for t in tens]).pin_memory()
+            host = hostapi.HostRenderStep(6000, sc.W, sc.H, (3,), Gimg, sc.bg, DEV, depth=2, sample_input=block)
+            assert host.graphed
+        hin = host.host_input_block()
+        host.pack_input(hin, tens)
+        ins.append(hin)
+        outs.append(host.host_output_block())
+        ps = [t.to(DEV).requires_grad_(True) for t in tens]
+        img = G.rasterization(*ps, sc.W, sc.H, sc.bg)
+        img.backward(Gimg)
+        refs.append((float((img.detach() * Gimg).sum()), ps))
+    for hin, hout in zip(ins, outs):
+        host.submit(hin, hout)
+    host.wait()
+    host.check()
+    for hout, (loss, ps) in zip(outs, refs):
+        got = host.unpack_output(hout)
+        assert abs(float(got["loss"][0]) - loss) <= 1e-4 * abs(loss)
+        for name, p in zip(["xyz", "scale", "rotate", "opacity", "feature", "intr", "extr"], ps):
+            assert_close(got[name].reshape(p.grad.shape), p.grad, 1e-4, "host step grad " + name)
