@@ -141,15 +141,43 @@ def patch(trainer_module) -> None:
     cls._gflow_b200_native = True
 
 
+def try_patch_loaded(module_name: str = "trainer") -> bool:
+    """Patches `module_name` if it is in sys.modules and already defines SimpleGaussian.  True once patched."""
+    mod = sys.modules.get(module_name)
+    cls = getattr(mod, "SimpleGaussian", None) if mod is not None else None
+    if cls is None:
+        return False
+    patch(mod)
+    return True
+
+
 def install_import_hook(module_name: str = "trainer") -> None:
-    """Patches `module_name` right after it is imported (sys.meta_path wrapper), for zero-edit runs."""
+    """Patches `module_name` as soon as it defines SimpleGaussian, for zero-edit runs.
+
+    The real entry point imports in this order: fit_video.py -> `from trainer import SimpleGaussian` ->
+    trainer.py:7 `import msplat` -> (this hook is installed) -> rest of trainer.py.  So the target module is usually
+    ALREADY being executed when the hook arrives, and a finder that waits for its find_spec never fires (round-1 bug:
+    the switch was a silent no-op).  Three cases are handled:
+      * module already complete in sys.modules         -> patched at once;
+      * module not imported yet                        -> its loader's exec_module is wrapped (patched right after it runs);
+      * module in sys.modules but still executing      -> a watcher finder looks again at every later import statement
+        (fit_video.py:5 `from utils.traj_visualizer import ...` is the first one after trainer.py finishes) and the
+        drop-in operators look once more on their first call (gflow_b200/dropin/msplat).
+    """
     import importlib.abc
     import importlib.util
+
+    if try_patch_loaded(module_name):
+        return
 
     class _GflowTrainerPatchFinder(importlib.abc.MetaPathFinder):
         gflow_b200_target = module_name
 
         def find_spec(self, name, path, target=None):
+            if module_name in sys.modules:  # imported (maybe still executing) before or after we arrived: watch it
+                if try_patch_loaded(module_name) and self in sys.meta_path:
+                    sys.meta_path.remove(self)
+                return None
             if name != module_name:
                 return None
             sys.meta_path.remove(self)

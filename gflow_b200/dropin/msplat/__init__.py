@@ -30,3 +30,19 @@ if _os.environ.get("GFLOW_B200_NATIVE_TRAIN") == "1":
     from gflow_b200 import accelerate as _accelerate
 
     _accelerate.install_import_hook("trainer")
+
+    # `trainer` is normally half-way through its own import when it imports this module (trainer.py:7), so the hook
+    # cannot patch it yet; besides the import watcher, the operators look once more the first time one is called.
+    def _patch_on_first_call(fn):
+        def first(*a, **k):
+            _accelerate.try_patch_loaded("trainer")
+            for name, raw in _RAW.items():  # from now on the plain operators again
+                globals()[name] = raw
+            return fn(*a, **k)
+
+        first.__name__, first.__doc__ = fn.__name__, fn.__doc__
+        return first
+
+    _RAW = {n: globals()[n] for n in __all__}
+    for _n, _f in _RAW.items():
+        globals()[_n] = _patch_on_first_call(_f)

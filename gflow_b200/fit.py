@@ -15,9 +15,11 @@ Two execution modes with the same semantics:
     (csrc/fit.cu through gfb_fit_init / gfb_fit_iterate): activations + geometry + binning, one 4-channel
     blend for rgb and the depth map, fused losses, blend backward, geometry backward with the Adam update
     in the same kernel.
-Terms covered: mse [+ 1 - SSIM], depth, scale-variance and scale/depth regularisers, the camera-only /
-frozen-rgb / still-xyz gradient masks and the pixel mask (trainer.py:452-551).  Not rebuilt: flow / still
-position terms, densification, logging, checkpoints (SURVEY.md 8f "next" rows).
+Terms covered (both modes): mse [+ 1 - SSIM], depth, scale-variance and scale/depth regularisers, the still-position
+and flow-consistency terms, the camera-only / frozen-rgb / still-xyz gradient masks, the pixel mask and the moving
+subset's footprint (trainer.py:427-551), error-driven and occlusion densification (trainer.py:560-571, 878-951).
+Frame-state files and the wire format live in gflow_b200/checkpoint.py.  Not rebuilt: the concave-hull
+segmentation, logging and video dumps after a stage.
 """
 from __future__ import annotations
 
@@ -80,14 +82,31 @@ def pose_to_extr(pose: torch.Tensor) -> torch.Tensor:
 
 
 def extr_to_pose(extr: torch.Tensor) -> torch.Tensor:
-    """Inverse of pose_to_extr for a proper rotation (Shepperd's method, xyzw order)."""
+    """Inverse of pose_to_extr for a proper rotation: Shepperd's method with all four branches (xyzw order), valid for
+    every rotation including the 180-degree ones (axis flips such as an OpenGL <-> OpenCV extrinsic), like the
+    roma.rotmat_to_unitquat the reference uses (/root/reference/gflow/trainer.py:177).  The branch with the largest
+    pivot is taken, so no component is ever divided by a value near zero.  Returned with w >= 0."""
     R, t = extr[:, :3], extr[:, 3]
-    tr = R[0, 0] + R[1, 1] + R[2, 2]
-    w = torch.sqrt(torch.clamp(1.0 + tr, min=1e-12)) / 2.0
-    x = (R[2, 1] - R[1, 2]) / (4.0 * w)
-    y = (R[0, 2] - R[2, 0]) / (4.0 * w)
-    z = (R[1, 0] - R[0, 1]) / (4.0 * w)
-    return torch.cat([torch.stack([x, y, z, w]), t])
+    r = [[float(R[i, j]) for j in range(3)] for i in range(3)]
+    tr = r[0][0] + r[1][1] + r[2][2]
+    pivots = [tr, r[0][0], r[1][1], r[2][2]]
+    k = max(range(4), key=lambda i: pivots[i])
+    if k == 0:
+        s4 = 2.0 * (1.0 + tr) ** 0.5            # 4 w
+        w, x, y, z = 0.25 * s4, (r[2][1] - r[1][2]) / s4, (r[0][2] - r[2][0]) / s4, (r[1][0] - r[0][1]) / s4
+    elif k == 1:
+        s4 = 2.0 * (1.0 + r[0][0] - r[1][1] - r[2][2]) ** 0.5  # 4 x
+        w, x, y, z = (r[2][1] - r[1][2]) / s4, 0.25 * s4, (r[0][1] + r[1][0]) / s4, (r[0][2] + r[2][0]) / s4
+    elif k == 2:
+        s4 = 2.0 * (1.0 + r[1][1] - r[0][0] - r[2][2]) ** 0.5  # 4 y
+        w, x, y, z = (r[0][2] - r[2][0]) / s4, (r[0][1] + r[1][0]) / s4, 0.25 * s4, (r[1][2] + r[2][1]) / s4
+    else:
+        s4 = 2.0 * (1.0 + r[2][2] - r[0][0] - r[1][1]) ** 0.5  # 4 z
+        w, x, y, z = (r[1][0] - r[0][1]) / s4, (r[0][2] + r[2][0]) / s4, (r[1][2] + r[2][1]) / s4, 0.25 * s4
+    if w < 0.0:
+        w, x, y, z = -w, -x, -y, -z
+    q = torch.tensor([x, y, z, w], dtype=extr.dtype, device=extr.device)
+    return torch.cat([q, t])
 
 
 @dataclass
@@ -678,6 +697,11 @@ class NativeFitLoop:
             for k in ATTRS:
                 f.attrs[k] = torch.nn.Parameter(torch.cat([f.attrs[k].data, new[k]], dim=0))
             head = self.ws[: self.lay.adam_m].clone()  # status | loss sums | camera | loss history: N independent
+            # projected centres / depths of the last forward survive the re-allocation: a stage that ENDS with a
+            # densification hands them to the caller (still mask, last_uv, move_seg bookkeeping), and the fresh workspace
+            # would otherwise return uninitialised rows there
+            n_old = self.N
+            old_uv, old_depth = (self.last_uv(), self.last_depth()) if self.done > 0 else (None, None)
             self.N += count
             if self.scale_sel is not None:
                 self.scale_sel = torch.cat([self.scale_sel, torch.ones(count, dtype=torch.uint8, device=self.dev)])
@@ -690,6 +714,23 @@ class NativeFitLoop:
             capi.check(self.lib.gfb_fit_init(ctypes.addressof(self.problem), self.ws.data_ptr(), self.capacity, self.iters,
                                              self._stream()), "fit init after densify")
             self.ws[: self.lay.adam_m].copy_(head)
+            uv_new = self._view(self.lay.uv, 2 * self.N).reshape(self.N, 2)
+            d_new = self._view(self.lay.depth, self.N)
+            if old_uv is not None:
+                uv_new[:n_old] = old_uv
+                d_new[:n_old] = old_depth.reshape(-1)
+            else:
+                uv_new[:n_old] = 0.0
+                d_new[:n_old] = 0.0
+            # a new Gaussian is the back-projection of its pixel at the prior depth under the current camera
+            # (trainer.py:904-933), so it projects onto that pixel at that depth
+            # (geometry.py:104-116 back-projects with fx on both axes, so v lands on cy + (row - cy) fy / fx)
+            px = new["pixels"].long()
+            fx, fy, cy = f.intr[0], f.intr[1], f.intr[3]
+            row = torch.div(px, self.W, rounding_mode="floor").to(torch.float32)
+            uv_new[n_old:, 0] = (px % self.W).to(torch.float32)
+            uv_new[n_old:, 1] = cy + (row - cy) * (fy / fx)
+            d_new[n_old:] = self.gt_depth.reshape(-1)[px]
         return count
 
     def last_uv(self) -> torch.Tensor:

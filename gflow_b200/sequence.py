@@ -65,6 +65,7 @@ class FrameOutput:
     image: Optional[torch.Tensor] = None
     pose: Optional[torch.Tensor] = None
     num_points: int = 0
+    chunk_head: bool = False   # fit_video_sharded: first frame of a rank's chunk (its tracks / masks start afresh)
 
 
 class SequenceFitter:
@@ -141,6 +142,24 @@ class SequenceFitter:
         out = FrameOutput(losses={"first": self._stage("first", gt_image, gt_depth, fc, move_mask)})
         return self._finish(out)
 
+    def fit_chunk_head(self, gt_image, gt_depth, move_mask, have_camera_prior: bool) -> FrameOutput:
+        """First frame of a later chunk in fit_video_sharded: the broadcast Gaussians describe frame 0, the chunk's
+        first frame was taken from another viewpoint.  Without a camera prior the pose is first moved there by a
+        camera-only stage (frame 0's recipe keeps lr_camera at 0 in the shipped configuration and would leave the
+        chunk's camera at pose0), then the frame is fitted with the first-frame recipe."""
+        c = self.cfg
+        cam_losses = None
+        if not have_camera_prior and c.iterations_camera > 0:
+            move = torch.zeros(self.H, self.W, dtype=torch.bool, device=gt_image.device) if move_mask is None else move_mask
+            fc = self._fit_config(iterations=c.iterations_camera, lr=1e-2, lr_camera=c.lr_camera_after, lambda_var=0.0,
+                                  lambda_still=0.0, lambda_flow=0.0, camera_only=True)
+            cam_losses = self._stage("camera", gt_image, gt_depth, fc, move)
+        out = self.fit_first(gt_image, gt_depth, move_mask)
+        out.chunk_head = True
+        if cam_losses is not None:
+            out.losses["camera"] = cam_losses
+        return out
+
     def fit_next(self, gt_image, gt_depth, gt_flow, move_mask, occ_mask=None, extr: Optional[torch.Tensor] = None) -> FrameOutput:
         """fit_video.py:242-315.  `extr` (3,4): load_camera(extr=...) when camera priors are used (load_extr)."""
         c = self.cfg
@@ -180,9 +199,15 @@ def fit_video_sharded(state0: Optional[Dict[str, torch.Tensor]], intr: torch.Ten
     outputs (final render + pose) at the end.
 
     Rank r owns the contiguous chunk frames.shard_frames(num_frames, world, r) and runs it SEQUENTIALLY with the
-    reference's state carry-over inside the chunk (its first frame is fitted like fit_video's frame 0, starting from
-    the broadcast state; the following ones with camera-only + full stages, flow warp and still-mask bookkeeping).
-    Chunks do not see each other -- the reference itself is strictly sequential, so this is a throughput mode.
+    reference's state carry-over inside the chunk: the following frames get camera-only + full stages, flow warp and
+    still-mask bookkeeping; the chunk's FIRST frame starts from the broadcast frame-0 state -- its camera comes from the
+    `extr` prior when there is one, otherwise from a camera-only stage (SequenceFitter.fit_chunk_head) -- and is then
+    fitted with the first-frame recipe.
+
+    THROUGHPUT MODE, not the reference's semantics: the reference is strictly sequential, chunks here do not see each
+    other.  Gaussian identities, still masks, last_uv and therefore tracks / trajectories are continuous only INSIDE
+    a chunk, and poses of different chunks are only comparable when every chunk head got an `extr` prior or converged
+    in its camera stage.  Outputs of chunk heads carry `chunk_head=True` so a consumer can cut tracks there.
 
     frame_inputs(i) -> dict(image (H,W,3), depth (H,W,1), move_mask (H,W) bool[, flow (H,W,2), occ_mask (H,W,1), extr (3,4)]).
     Returns (outputs of the local frames keyed by frame index, list of (image, extr) per rank on rank 0 or None).
@@ -203,7 +228,11 @@ def fit_video_sharded(state0: Optional[Dict[str, torch.Tensor]], intr: torch.Ten
             seq = SequenceFitter(state, intr.to(device), pose0.to(device), W, H, cfg)
             if fi.get("extr") is not None:
                 seq.pose = _fit.extr_to_pose(fi["extr"].detach().float().cpu()).to(device)
-            outputs[i] = seq.fit_first(to(fi["image"]), to(fi["depth"]), to(fi["move_mask"]))
+            if i == 0:
+                outputs[i] = seq.fit_first(to(fi["image"]), to(fi["depth"]), to(fi["move_mask"]))
+            else:
+                outputs[i] = seq.fit_chunk_head(to(fi["image"]), to(fi["depth"]), to(fi["move_mask"]),
+                                                have_camera_prior=fi.get("extr") is not None)
         else:
             outputs[i] = seq.fit_next(to(fi["image"]), to(fi["depth"]), to(fi["flow"]), to(fi["move_mask"]),
                                       occ_mask=to(fi.get("occ_mask")), extr=fi.get("extr"))

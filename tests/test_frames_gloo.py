@@ -112,7 +112,11 @@ def _seq_worker(rank, world, port, q):
         outs, gathered = sequence.fit_video_sharded(raw if rank == 0 else None, sc.intr, pose, 4, frame_inputs, W, H, cfg,
                                                     torch.device("cpu"))
         ok = sorted(outs) == ([0, 1] if rank == 0 else [2, 3])
-        ok = ok and all(set(o.losses) == ({"first"} if i in (0, 2) else {"camera", "all"}) for i, o in outs.items())
+        # frame 0: first-frame recipe; frame 2 heads rank 1's chunk without a camera prior: camera-only stage, then the
+        # first-frame recipe, flagged as a chunk head; the others: camera-only + full stages
+        want = {0: {"first"}, 2: {"first", "camera"}, 1: {"camera", "all"}, 3: {"camera", "all"}}
+        ok = ok and all(set(o.losses) == want[i] for i, o in outs.items())
+        ok = ok and all(o.chunk_head == (i == 2) for i, o in outs.items())
         ok = ok and all(len(v) > 0 and all(x == x for x in v) for o in outs.values() for v in o.losses.values())
         if rank == 0:
             ok = ok and gathered is not None and len(gathered) == world

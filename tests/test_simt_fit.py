@@ -104,8 +104,14 @@ def test_densify_between_iterations_recreates_the_optimiser_like_the_reference()
     pose_before, ab_before = f.pose.data.clone(), loop.depth_ab.clone()
     hist_before = loop.loss_history().clone()
     old = {k: f.attrs[k].data.clone() for k in fit.ATTRS}
+    uv_before, depth_before = loop.last_uv(), loop.last_depth()
     added = loop.densify(error_threshold=1e-5, percent=0.5, seed=3)
     assert added > 10 and loop.N == N + added
+    # a stage may END with a densification (SimpleGaussian.train's defaults: iterations = densify_interval = 500): the
+    # caller then builds still masks / last_uv from last_uv() / last_depth(), which must not be fresh-workspace garbage
+    uv_after, depth_after = loop.last_uv(), loop.last_depth()
+    assert uv_after.shape == (N + added, 2) and torch.equal(uv_after[:N], uv_before) and torch.equal(depth_after[:N], depth_before)
+    assert bool(torch.isfinite(uv_after).all()) and bool((depth_after[N:] > 0).all())
     for k in fit.ATTRS:
         assert f.attrs[k].shape[0] == N + added and torch.equal(f.attrs[k].data[:N], old[k])
     assert torch.equal(loop.loss_history(), hist_before) and int(loop.status()[0]) == 2
@@ -122,6 +128,7 @@ def test_densify_between_iterations_recreates_the_optimiser_like_the_reference()
     fx, fy, cx, cy = (float(v) for v in sc.intr)
     assert torch.allclose(new_uv[seen, 0], col, atol=2e-3)
     assert torch.allclose(new_uv[seen, 1], cy + (row - cy) * fy / fx, atol=2e-3)
+    assert torch.allclose(uv_after[N:][seen], new_uv[seen], atol=2e-3), "the carried-over uv of the new rows = their projection"
     assert torch.allclose(depth[N:][seen, 0], gt_depth.reshape(-1)[pix], rtol=1e-4)
     # next iterations: fresh Adam (t restarts at 1), constant lr, camera frozen
     shadow = {k: f.attrs[k].data.clone().requires_grad_(True) for k in fit.ATTRS}
