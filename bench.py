@@ -273,6 +273,11 @@ def run_ours(args):
         big = torch.zeros(1 << 20, device=dev)
         dist.broadcast(big, src=0)
         dist.all_gather([torch.empty_like(big) for _ in range(world)], big)
+        from gflow_b200 import frames as _fr  # the same call pattern once on a tiny state (int64 count + float payload)
+
+        tiny = {k: torch.zeros(8, w, device=dev) for k, w in _fr.STATE_KEYS}
+        _fr.broadcast_state(tiny if rank == 0 else None, src=0, device=dev)
+        _fr.gather_frames(torch.zeros(3, 8, 8, device=dev), torch.zeros(3, 4, device=dev), dst=0)
         torch.cuda.synchronize()
         t_init = time.perf_counter() - t0
     lib = capi.load()
@@ -424,6 +429,9 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (alpha-blending backward), timed alone with CUDA events
     roof = kernel_roofline(G, lib, params, intr, extr, Gimg, sc.bg, N, W, H, T, P, flush_l2, dev, clocks,
                            cam_center if use_sh else None, args.profile)
+
+    if use_sh:
+        roof["compute_sh"] = sh_roofline(G, params[4].detach(), (params[0].detach() - cam_center), flush_l2)
 
     chain = iteration = sequence = None
     if not args.quick:
@@ -665,6 +673,49 @@ def eager_proxy_section(args):
         return {"error": (res.stderr or res.stdout)[-300:]}
     except Exception as e:  # noqa: BLE001
         return {"error": repr(e)[:300]}
+
+
+def sh_roofline(G, shs, dirs, flush_l2, reps=20):
+    """compute_sh forward / backward timed alone: the one purely streaming kernel of the path ((4CK + 12 + 4C) N bytes
+    forward, (8CK + 24 + 4C) N backward), against the measured HBM copy bandwidth."""
+    peak, _ = load_peaks()
+    N, C, K = shs.shape
+    s = shs.clone().requires_grad_(True)
+    d = dirs.clone().requires_grad_(True)
+    g = torch.randn(N, C, device=shs.device)
+
+    def timeit(fn):
+        ts = []
+        for _ in range(reps + 3):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts[3:])
+
+    with torch.no_grad():
+        ms_f = timeit(lambda: G.compute_sh(s, d))
+    out = G.compute_sh(s, d)
+
+    def bwd():
+        s.grad = d.grad = None
+        out.backward(g, retain_graph=True)
+
+    ms_b = timeit(bwd)  # includes the autograd engine's launch path; the kernel itself is the only GPU work
+    bf, bb = (4 * C * K + 12 + 4 * C) * N, (8 * C * K + 24 + 4 * C) * N
+    # what a plain device copy moving the SAME number of bytes takes under the same harness: at tens of MB the launch
+    # and DRAM ramp are a visible part of any kernel, so this is the practical ceiling next to the 2 GiB-copy peak
+    src_f, src_b = torch.empty(bf // 8, device=shs.device), torch.empty(bb // 8, device=shs.device)
+    dst_f, dst_b = torch.empty_like(src_f), torch.empty_like(src_b)
+    cp_f, cp_b = timeit(lambda: dst_f.copy_(src_f)), timeit(lambda: dst_b.copy_(src_b))
+    return {"forward": {"kernel_ms": ms_f, "algorithmic_bytes": bf, "achieved": bf / (ms_f * 1e-3) / 1e9, "frac": bf / (ms_f * 1e-3) / 1e9 / peak,
+                        "same_bytes_copy_ms": cp_f, "frac_of_same_bytes_copy": cp_f / ms_f},
+            "backward": {"kernel_ms": ms_b, "algorithmic_bytes": bb, "achieved": bb / (ms_b * 1e-3) / 1e9, "frac": bb / (ms_b * 1e-3) / 1e9 / peak,
+                         "same_bytes_copy_ms": cp_b, "frac_of_same_bytes_copy": cp_b / ms_b},
+            "unit": "GB/s", "what": f"compute_sh degree-{int(K ** 0.5) - 1} ({N} Gaussians x {C} x {K} coefficients), CUDA events around the op call, L2 flushed"}
 
 
 def ncu_constants(N, W, H, profile):

@@ -299,6 +299,188 @@ compute_sh_bwd_kernel(const float* __restrict__ shs, const float* __restrict__ d
     d_dirs[3 * i + 2] = dd[2];
 }
 
+// ---- coalesced variants for C == 3 (rgb): the (N, 3, K) coefficient block of a warp's 32 Gaussians is contiguous in
+// memory, so the warp streams it through shared memory with 128-bit loads / stores and every lane then works on its
+// own row there (odd pitch: conflict-free).  The per-thread walk above touches 32 different lines per load
+// instruction; at 200 000 Gaussians / degree 3 (38 MB in, 38 MB of gradients out) this kernel is the one purely
+// HBM-bound piece of the path, so the access pattern is the whole story.  Arithmetic and its order are
+// those of the kernels above.
+constexpr int kShWarps = 4;
+// row pitch of the tile in floats: for CK % 4 == 0 an ODD number of float4s, so that rows read / written with 128-bit
+// accesses by consecutive lanes fall into disjoint bank groups; otherwise an odd number of floats (scalar accesses)
+template <int CK>
+struct ShPitch {
+    static constexpr int value = (CK % 4 == 0) ? 4 * ((CK / 4) | 1) : (CK | 1);
+};
+
+template <int CK>
+__device__ __forceinline__ void sh_tile_load(const float* __restrict__ src, int total, float* tile, int lane) {
+    constexpr int PITCH = ShPitch<CK>::value;
+    if constexpr (CK % 4 == 0) {
+        // all CK / 4 loads of the lane are issued before the first one is consumed: one round trip to HBM per warp
+        // tile instead of CK / 4 dependent ones
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+        float4 v[CK / 4];
+#pragma unroll
+        for (int j = 0; j < CK / 4; ++j) {
+            const int q = lane + 32 * j;
+            v[j] = (q < total / 4) ? src4[q] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int j = 0; j < CK / 4; ++j) {
+            const int q = lane + 32 * j;
+            const int r = (4 * q) / CK, c = (4 * q) % CK;  // CK % 4 == 0: the four values stay in one row
+            *reinterpret_cast<float4*>(tile + r * PITCH + c) = v[j];
+        }
+    } else {
+        float v[CK];
+#pragma unroll
+        for (int j = 0; j < CK; ++j) {
+            const int idx = lane + 32 * j;
+            v[j] = (idx < total) ? src[idx] : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < CK; ++j) {
+            const int idx = lane + 32 * j;
+            tile[(idx / CK) * PITCH + idx % CK] = v[j];
+        }
+    }
+    __syncwarp();
+}
+
+template <int CK>
+__device__ __forceinline__ void sh_tile_store(float* __restrict__ dst, int total, const float* tile, int lane) {
+    constexpr int PITCH = ShPitch<CK>::value;
+    __syncwarp();
+    if constexpr (CK % 4 == 0) {
+        float4* dst4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+        for (int j = 0; j < CK / 4; ++j) {
+            const int q = lane + 32 * j;
+            const int r = (4 * q) / CK, c = (4 * q) % CK;
+            if (q < total / 4) dst4[q] = *reinterpret_cast<const float4*>(tile + r * PITCH + c);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CK; ++j) {
+            const int idx = lane + 32 * j;
+            if (idx < total) dst[idx] = tile[(idx / CK) * PITCH + idx % CK];
+        }
+    }
+}
+
+// the lane's row of the tile into registers / back (128-bit accesses when the pitch allows)
+template <int CK>
+__device__ __forceinline__ void sh_row_read(const float* src, float (&row)[CK]) {
+    if constexpr (CK % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < CK / 4; ++j) {
+            const float4 v = reinterpret_cast<const float4*>(src)[j];
+            row[4 * j] = v.x, row[4 * j + 1] = v.y, row[4 * j + 2] = v.z, row[4 * j + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CK; ++j) row[j] = src[j];
+    }
+}
+template <int CK>
+__device__ __forceinline__ void sh_row_write(float* dst, const float (&row)[CK]) {
+    if constexpr (CK % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < CK / 4; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(row[4 * j], row[4 * j + 1], row[4 * j + 2], row[4 * j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < CK; ++j) dst[j] = row[j];
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(32 * kShWarps)
+compute_sh3_fwd_kernel(const float* __restrict__ shs, const float* __restrict__ dirs, const uint8_t* __restrict__ visible,
+                       int N, float* __restrict__ out) {
+    constexpr int C = 3, CK = C * K, PITCH = ShPitch<CK>::value;
+    __shared__ __align__(16) float s_tile[kShWarps][32 * PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int base = (blockIdx.x * kShWarps + warp) * 32;
+    if (base >= N) return;
+    const int rows = min(32, N - base);
+    float* tile = s_tile[warp];
+    sh_tile_load<CK>(shs + (size_t)base * CK, rows * CK, tile, lane);
+    const int i = base + lane;
+    if (i >= N) return;
+    float* o = out + (size_t)i * C;
+    if (visible && !visible[i]) {
+        o[0] = o[1] = o[2] = 0.0f;
+        return;
+    }
+    const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
+    const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+    float Y[16];
+    sh_eval<false>(x * inv, y * inv, z * inv, K, Y, nullptr, nullptr, nullptr);
+    float row[CK];
+    sh_row_read<CK>(tile + lane * PITCH, row);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc += row[c * K + k] * Y[k];
+        o[c] = acc;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(32 * kShWarps)
+compute_sh3_bwd_kernel(const float* __restrict__ shs, const float* __restrict__ dirs, const uint8_t* __restrict__ visible,
+                       int N, const float* __restrict__ g_out, float* __restrict__ d_shs, float* __restrict__ d_dirs) {
+    constexpr int C = 3, CK = C * K, PITCH = ShPitch<CK>::value;
+    __shared__ __align__(16) float s_tile[kShWarps][32 * PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int base = (blockIdx.x * kShWarps + warp) * 32;
+    if (base >= N) return;
+    const int rows = min(32, N - base);
+    float* tile = s_tile[warp];
+    sh_tile_load<CK>(shs + (size_t)base * CK, rows * CK, tile, lane);
+    const int i = base + lane;
+    if (i < N) {
+        float dd[3] = {0.0f, 0.0f, 0.0f};
+        float row[CK];  // coefficients in, their gradients out (each lane owns its row of the tile)
+        if (visible && !visible[i]) {
+#pragma unroll
+            for (int k = 0; k < CK; ++k) row[k] = 0.0f;
+        } else {
+            sh_row_read<CK>(tile + lane * PITCH, row);
+            const float x = dirs[3 * i], y = dirs[3 * i + 1], z = dirs[3 * i + 2];
+            const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+            const float nx = x * inv, ny = y * inv, nz = z * inv;
+            float Y[16], Yx[16], Yy[16], Yz[16];
+            sh_eval<true>(nx, ny, nz, K, Y, Yx, Yy, Yz);
+            float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float g = g_out[(size_t)i * C + c];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float gs = g * row[c * K + k];
+                    row[c * K + k] = g * Y[k];
+                    gx += gs * Yx[k];
+                    gy += gs * Yy[k];
+                    gz += gs * Yz[k];
+                }
+            }
+            const float dot = gx * nx + gy * ny + gz * nz;
+            dd[0] = (gx - nx * dot) * inv;
+            dd[1] = (gy - ny * dot) * inv;
+            dd[2] = (gz - nz * dot) * inv;
+        }
+        sh_row_write<CK>(tile + lane * PITCH, row);
+        d_dirs[3 * i] = dd[0];
+        d_dirs[3 * i + 1] = dd[1];
+        d_dirs[3 * i + 2] = dd[2];
+    }
+    sh_tile_store<CK>(d_shs + (size_t)base * CK, rows * CK, tile, lane);
+}
+
 }  // namespace
 
 // ====================================================================== C ABI
@@ -384,8 +566,18 @@ int gfb_compute_sh_fwd(const float* shs, const float* dirs, const uint8_t* visib
     if (N < 0 || C <= 0 || !(K == 1 || K == 4 || K == 9 || K == 16)) return GFB_E_BADARG;
     if (N == 0) return 0;
     if (!shs || !dirs || !out) return GFB_E_BADARG;
-    compute_sh_fwd_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(shs, dirs, visible, N, C, K,
-                                                                                           out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 3 && ((uintptr_t)shs & 15u) == 0) {  // coalesced path (float4 tile loads need a 16-byte aligned base)
+        const int grid = gfb_div_up(N, 32 * kShWarps), block = 32 * kShWarps;
+        switch (K) {
+            case 1: compute_sh3_fwd_kernel<1><<<grid, block, 0, st>>>(shs, dirs, visible, N, out); break;
+            case 4: compute_sh3_fwd_kernel<4><<<grid, block, 0, st>>>(shs, dirs, visible, N, out); break;
+            case 9: compute_sh3_fwd_kernel<9><<<grid, block, 0, st>>>(shs, dirs, visible, N, out); break;
+            default: compute_sh3_fwd_kernel<16><<<grid, block, 0, st>>>(shs, dirs, visible, N, out); break;
+        }
+    } else {
+        compute_sh_fwd_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(shs, dirs, visible, N, C, K, out);
+    }
     GFB_CHECK_LAUNCH();
     return 0;
 }
@@ -395,8 +587,18 @@ int gfb_compute_sh_bwd(const float* shs, const float* dirs, const uint8_t* visib
     if (N < 0 || C <= 0 || !(K == 1 || K == 4 || K == 9 || K == 16)) return GFB_E_BADARG;
     if (N == 0) return 0;
     if (!shs || !dirs || !g_out || !d_shs || !d_dirs) return GFB_E_BADARG;
-    compute_sh_bwd_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(shs, dirs, visible, N, C, K,
-                                                                                           g_out, d_shs, d_dirs);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 3 && (((uintptr_t)shs | (uintptr_t)d_shs) & 15u) == 0) {
+        const int grid = gfb_div_up(N, 32 * kShWarps), block = 32 * kShWarps;
+        switch (K) {
+            case 1: compute_sh3_bwd_kernel<1><<<grid, block, 0, st>>>(shs, dirs, visible, N, g_out, d_shs, d_dirs); break;
+            case 4: compute_sh3_bwd_kernel<4><<<grid, block, 0, st>>>(shs, dirs, visible, N, g_out, d_shs, d_dirs); break;
+            case 9: compute_sh3_bwd_kernel<9><<<grid, block, 0, st>>>(shs, dirs, visible, N, g_out, d_shs, d_dirs); break;
+            default: compute_sh3_bwd_kernel<16><<<grid, block, 0, st>>>(shs, dirs, visible, N, g_out, d_shs, d_dirs); break;
+        }
+    } else {
+        compute_sh_bwd_kernel<<<gfb_div_up(N, kThreads), kThreads, 0, st>>>(shs, dirs, visible, N, C, K, g_out, d_shs, d_dirs);
+    }
     GFB_CHECK_LAUNCH();
     return 0;
 }
