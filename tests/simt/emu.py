@@ -22,6 +22,10 @@ def load():
     if _lib is None:
         from gflow_b200.capi import SIGNATURES
 
+        # The emulated suite pins the fused pipeline's ids / tile_range to the oracle's 3-sigma enumeration bit for
+        # bit, so it runs with tile culling off unless a test asks for it (tests/simt/tight_tiles_check.py runs the
+        # shipped default, GFB_TIGHT_TILES=1, in a process of its own; the switch is read once per process).
+        os.environ.setdefault("GFB_TIGHT_TILES", "0")
         # GFB_EMU_LIB: an alternative build of the same sources (the UBSan one, tests/test_simt_kernels.py)
         path = os.environ.get("GFB_EMU_LIB") or build_emu.build()
         lib = ctypes.CDLL(path)

@@ -630,10 +630,10 @@ def test_k_handoff_is_reentrant_across_streams_and_threads(G):
     want, refs = [], []
     for sc in scenes:
         args = cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb, sc.intr, sc.extr)
-        uv, depth = G.project_point(args[0], args[5], args[6], sc.W, sc.H)
-        vis = depth != 0
-        conic, radius, tiles = G.ewa_project(args[0], G.compute_cov3d(args[1], args[2], vis), args[5], args[6], uv, sc.W, sc.H, vis)
-        want.append(int(tiles.sum()))
+        out = torch.empty(3, sc.H, sc.W, device=DEV)  # K of the fused pipeline from a synchronous pass
+        want.append(ops._raster_forward(args[0], args[1], args[2], args[3].reshape(-1).contiguous(), args[4], args[5], args[6],
+                                        sc.xyz.shape[0], 3, sc.W, sc.H, 0.0, 0.2, 1.3, torch.device(DEV),
+                                        4 * sc.xyz.shape[0] + 4096, out, False)[4])
         refs.append(G.rasterization(*args, sc.W, sc.H, 0.0).clone())
     assert want[0] != want[1]
     # two streams, forwards enqueued back to back without waiting, K picked up in reverse order
@@ -770,7 +770,7 @@ def test_graphed_render_step_equals_the_eager_step(G):
     vis = depth != 0
     _, _, tiles = G.ewa_project(step.xyz, G.compute_cov3d(step.scale, step.rotate, vis), step.intr, step.extr, uv, sc.W, sc.H, vis)
     step()
-    assert step.k() == int(tiles.sum())
+    assert 0 < step.k() <= int(tiles.sum()), "the fused pipeline drops pairs that cannot reach alpha 1/255 (GFB_TIGHT_TILES)"
     step.check()
     small = G.GraphedRenderStep(*args, sc.W, sc.H, sc.bg, capacity=1000)
     small()

@@ -201,9 +201,9 @@ def test_full_size_config2_fused_pipeline():
     _check(r, o, "cfg2 fused pipeline")
 
 
-def test_experimental_tight_tile_culling_keeps_images_and_gradients():
-    """GFB_TIGHT_TILES=1 (off by default; fused pipeline + native fit loop only): tests/simt/tight_tiles_check.py in a
-    process of its own."""
+def test_tight_tile_culling_keeps_images_and_gradients():
+    """GFB_TIGHT_TILES=1 (the shipped default; fused pipeline + native fit loop only): tests/simt/tight_tiles_check.py in
+    a process of its own (the rest of the emulated suite runs with the 3-sigma rule to compare ids bit for bit)."""
     import subprocess
 
     here = os.path.dirname(os.path.abspath(__file__))
