@@ -76,12 +76,18 @@ class GraphedRenderStep:
                 "extr": self._grad_ws[12 * N:12 * N + 12].view(3, 4), "intr": self._grad_ws[12 * N + 12:12 * N + 16]}
             k_off = 8 * T + self.lib.gfb_render_control_k_offset(self.W, self.H)
             self._k_word = self._tbuf[k_off:k_off + 4].view(torch.int32)
-            self.graph = None
+            self.graph = self.graph_fwd = self.graph_bwd = None
             if capture:
                 self.warm_up()
-                self.graph = torch.cuda.CUDAGraph()
+                self.graph = torch.cuda.CUDAGraph()  # forward + backward in one launch (g_image known beforehand)
                 with torch.cuda.graph(self.graph):
                     self.enqueue()
+                if self.with_backward:  # and as two graphs, for a loss computed from the image in between
+                    self.graph_fwd, self.graph_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph_fwd):
+                        self.enqueue(backward=False)
+                    with torch.cuda.graph(self.graph_bwd):
+                        self.enqueue(forward=False)
 
     def warm_up(self, extra=None) -> None:
         """Two eager passes on a side stream: the first launches load modules, which cannot happen inside a capture."""
@@ -96,18 +102,14 @@ class GraphedRenderStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
 
-    def enqueue(self) -> None:
-        """Enqueues forward (+ backward) on the current stream -- eagerly, or into the CUDA graph being captured."""
+    def enqueue(self, forward: bool = True, backward: bool = True) -> None:
+        """Enqueues forward and / or backward on the current stream -- eagerly, or into the CUDA graph being captured."""
         N, C, W, H, cap, T = self.N, self.C, self.W, self.H, self.capacity, self.T
         gp, tp, kp = self._gbuf.data_ptr(), self._tbuf.data_ptr(), self._kbuf.data_ptr()
         st = ops._stream()
-        capi.check(self.lib.gfb_render_forward(
-            self.xyz.data_ptr(), self.scale.data_ptr(), self.rotate.data_ptr(), self.opacity.data_ptr(),
-            self.feature.data_ptr(), C, self.intr.data_ptr(), self.extr.data_ptr(), N, W, H, self.bg, self.nearest, self.extent,
-            gp, gp + 16 * N, gp + 20 * N, gp + 32 * N, gp + 8 * N, tp + 8 * T, tp, cap, kp + 48 * cap, kp + 56 * cap,
-            kp, kp + 32 * cap, self.image.data_ptr(), self._aux.data_ptr(), self._aux.data_ptr() + 4 * H * W, None, st),
-            "graphed rasterization forward")
-        if not self.with_backward:
+        if forward:
+            self._enqueue_forward(gp, tp, kp, st)
+        if not (backward and self.with_backward):
             return
         dp = self._dbuf.data_ptr()
         capi.check(self.lib.gfb_render_backward(
@@ -115,6 +117,15 @@ class GraphedRenderStep:
             N, W, H, C, self.bg, self.nearest, self.extent, kp + 56 * cap, tp, cap, kp, kp + 32 * cap, self._aux.data_ptr(),
             self._aux.data_ptr() + 4 * H * W, self.g_image.data_ptr(), self._grad_ws.data_ptr(), dp + 16 * N, dp + 28 * N, dp,
             dp + 40 * N, dp + 44 * N, st), "graphed rasterization backward")
+
+    def _enqueue_forward(self, gp, tp, kp, st) -> None:
+        N, C, W, H, cap, T = self.N, self.C, self.W, self.H, self.capacity, self.T
+        capi.check(self.lib.gfb_render_forward(
+            self.xyz.data_ptr(), self.scale.data_ptr(), self.rotate.data_ptr(), self.opacity.data_ptr(),
+            self.feature.data_ptr(), C, self.intr.data_ptr(), self.extr.data_ptr(), N, W, H, self.bg, self.nearest, self.extent,
+            gp, gp + 16 * N, gp + 20 * N, gp + 32 * N, gp + 8 * N, tp + 8 * T, tp, cap, kp + 48 * cap, kp + 56 * cap,
+            kp, kp + 32 * cap, self.image.data_ptr(), self._aux.data_ptr(), self._aux.data_ptr() + 4 * H * W, None, st),
+            "graphed rasterization forward")
 
     def parameters(self):
         """The static input tensors (update them in place between replays)."""
@@ -126,6 +137,20 @@ class GraphedRenderStep:
             raise RuntimeError("gflow_b200: this GraphedRenderStep was built with capture=False; replay the owner's graph")
         self.graph.replay()
         return self.image
+
+    def forward(self) -> torch.Tensor:
+        """Forward only (its own graph): compute dL/d(image) from the returned image, write it into g_image, then backward()."""
+        if self.graph_fwd is None:
+            raise RuntimeError("gflow_b200: no separate forward graph (capture=False or backward=False)")
+        self.graph_fwd.replay()
+        return self.image
+
+    def backward(self) -> Dict[str, torch.Tensor]:
+        """Backward only, against the current contents of g_image and the last forward's buffers."""
+        if self.graph_bwd is None:
+            raise RuntimeError("gflow_b200: no separate backward graph (capture=False or backward=False)")
+        self.graph_bwd.replay()
+        return self.grads
 
     def k(self) -> int:
         """Intersection count of the last replay (synchronises)."""

@@ -766,6 +766,15 @@ def test_graphed_render_step_equals_the_eager_step(G):
         with torch.no_grad():  # in-place update of the static parameters: the next replay must see it
             step.xyz.add_(0.01 * torch.randn_like(step.xyz))
             step.feature.mul_(0.9)
+    # forward and backward as two graphs, with dL/d(image) computed from the image in between
+    img = step.forward()
+    step.g_image.copy_(2.0 * img)
+    grads = step.backward()
+    ps = [t.clone().requires_grad_(True) for t in (step.xyz, step.scale, step.rotate, step.opacity.reshape(-1, 1), step.feature)]
+    (G.rasterization(*ps, step.intr, step.extr, sc.W, sc.H, sc.bg) ** 2).sum().backward()
+    for name, p in zip(["xyz", "scale", "rotate", "opacity", "feature"], ps):
+        assert_close(grads[name].reshape(p.grad.shape), p.grad, 1e-4, "split graphed grad " + name)
+    step.g_image.copy_(Gimg)
     uv, depth = G.project_point(step.xyz, step.intr, step.extr, sc.W, sc.H)
     vis = depth != 0
     _, _, tiles = G.ewa_project(step.xyz, G.compute_cov3d(step.scale, step.rotate, vis), step.intr, step.extr, uv, sc.W, sc.H, vis)
