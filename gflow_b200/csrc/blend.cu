@@ -31,6 +31,8 @@
 //  No tensor cores: this is a gather / scatter bounded by issue rate and L2 atomics.
 #include <cstdlib>
 
+#include "records.cuh"
+#include "sort_network.cuh"
 #include "splat_math.cuh"
 
 namespace {
@@ -85,6 +87,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders this thread's earlier generic-proxy writes (ordinary stores) before later async-proxy accesses (bulk copies)
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -308,18 +314,14 @@ __device__ __forceinline__ void fwd_records(const Stage& st, const int (&jj)[NR]
     }
 }
 
+// The forward blend of one tile by the calling CTA (kBlendThreads threads): records [range.x, range.y) of the streams.
 template <int CG>
-__global__ void __launch_bounds__(kBlendThreads, kBlendMinCtas)
-blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, const float4* __restrict__ gF,
-                 const int2* __restrict__ tile_range, int gx, int c0, float bg, int W, int H,
-                 float* __restrict__ out, float* __restrict__ final_T, int32_t* __restrict__ n_contrib) {
-    __shared__ __align__(128) Stage s_stage[2];
-    __shared__ __align__(8) uint64_t s_bar[2];
-
-    gfb_pdl_wait();  // fused pipeline: tile_sort_pack may still be draining
-    const int tile = blockIdx.x;
+__device__ __forceinline__ void blend_forward_tile(const float4* __restrict__ gA, const float4* __restrict__ gB,
+                                                   const float4* __restrict__ gF, int tile, int2 range, int gx, int c0,
+                                                   float bg, int W, int H, float* __restrict__ out,
+                                                   float* __restrict__ final_T, int32_t* __restrict__ n_contrib,
+                                                   Stage* s_stage, uint64_t* s_bar) {
     const int tx = tile % gx, ty = tile / gx;
-    const int2 range = tile_range[tile];
     const int n = range.y - range.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const LanePixels lp(tx, ty, tid >> 5, lane, W, H);
@@ -397,6 +399,50 @@ blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
         final_T[pix] = fabsf(px.T.y);
         n_contrib[pix] = px.last1;
     }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kBlendThreads, kBlendMinCtas)
+blend_fwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, const float4* __restrict__ gF,
+                 const int2* __restrict__ tile_range, int gx, int c0, float bg, int W, int H,
+                 float* __restrict__ out, float* __restrict__ final_T, int32_t* __restrict__ n_contrib) {
+    __shared__ __align__(128) Stage s_stage[2];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    gfb_pdl_wait();  // fused pipeline: tile_sort_pack may still be draining
+    blend_forward_tile<CG>(gA, gB, gF, blockIdx.x, tile_range[blockIdx.x], gx, c0, bg, W, H, out, final_T, n_contrib, s_stage,
+                           s_bar);
+}
+
+// Fused pipeline: per-tile sort + record packing + forward blend in ONE kernel.  A tile's blend only needs that
+// tile's records, so there is no reason to wait for every other tile's sort (a kernel boundary is a grid-wide
+// barrier): the CTA sorts its segment, writes ids and the A / B / F records (the backward reads them later), and
+// blends from them straight away.  Sorting is a dependent-latency chain with half-empty issue slots, blending is
+// issue bound -- with both in one kernel, tiles in different phases share an SM and fill each other's gaps, and one
+// launch + ramp + drain disappears.  The records written by this CTA with ordinary stores are read back by its own
+// bulk copies: fence.proxy.async orders the two proxies.
+static_assert(kSortThreads == kBlendThreads, "the fused kernel sorts and blends with the same CTA");
+template <int CG>
+__global__ void __launch_bounds__(kBlendThreads, kBlendMinCtas)
+tile_sort_blend_fwd_kernel(const int32_t* __restrict__ offsets, int R, unsigned long long* __restrict__ keys,
+                           int2* __restrict__ tile_range, long long capacity, GfbPackArgs pa, int gx, float bg, int W, int H,
+                           float* __restrict__ out, float* __restrict__ final_T, int32_t* __restrict__ n_contrib) {
+    // the sort's exchange buffer and the blend's stages are never live at the same time
+    __shared__ __align__(128) unsigned char s_raw[sizeof(Stage) * 2 > sizeof(unsigned long long) * kSortSmemSmall
+                                                     ? sizeof(Stage) * 2 : sizeof(unsigned long long) * kSortSmemSmall];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    gfb_pdl_launch_dependents();
+    gfb_pdl_wait();  // keys come from scatter
+    sort_tile_cta(offsets, R, keys, capacity, reinterpret_cast<unsigned long long*>(s_raw), tile_range,
+                  [pa](long long pos, unsigned long long key) { gfb_write_record(pa, pos, (int)(unsigned int)key); });
+    const int tile = blockIdx.x;
+    const int start = offsets[tile * R];
+    long long end = offsets[(tile + 1) * R];
+    if (end > capacity) end = max((long long)start, capacity);
+    const int2 range = (end > start) ? make_int2(start, (int)end) : make_int2(0, 0);
+    fence_proxy_async();
+    __syncthreads();
+    blend_forward_tile<CG>(pa.sA, pa.sB, pa.sF, tile, range, gx, 0, bg, W, H, out, final_T, n_contrib,
+                           reinterpret_cast<Stage*>(s_raw), s_bar);
 }
 
 // ------------------------------------------------------------------ backward
@@ -759,6 +805,36 @@ int gfb_internal_blend_fwd(const void* geom_stream, const void* feat_stream, int
 
 int gfb_internal_blend_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int, float, int, int,
                            const float*, const int32_t*, const float*, float*, void*, bool no_rgb);
+
+// Fused pipeline / native loop: per-tile sort + pack + forward blend of all C <= 4 channels in one kernel
+// (tile_sort_blend_fwd_kernel).  tile_offsets / R: the scanned (tile, replica) counters of the control block;
+// keys_ws: the keys scatter wrote.  Writes ids, both record streams, tile_range, out, final_T, n_contrib.
+int gfb_internal_sort_pack_blend_fwd(const int32_t* tile_offsets, int R, void* keys_ws, int32_t* tile_range, int64_t capacity,
+                                     const float* uv, const float* conic, const float* opacity, const float* feature, int C,
+                                     int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, float bg, int W,
+                                     int H, float* out, float* final_T, int32_t* n_contrib, void* stream, bool pdl) {
+    if (W <= 0 || H <= 0 || capacity < 0 || C < 1 || C > 4) return GFB_E_BADARG;
+    if (!tile_offsets || !tile_range || !out || !final_T || !n_contrib) return GFB_E_BADARG;
+    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
+    float4* sA = reinterpret_cast<float4*>(geom_stream);
+    GfbPackArgs pa{reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, sA, sA + capacity,
+                   reinterpret_cast<float4*>(feat_stream), gaussian_ids_sorted};
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(keys_ws);
+    int2* tr = reinterpret_cast<int2*>(tile_range);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(gx * gy), block(kBlendThreads);
+    const long long cap = (long long)capacity;
+    cudaError_t le;
+    switch (C) {
+        case 1: le = gfb_launch_pdl(tile_sort_blend_fwd_kernel<1>, grid, block, st, pdl, tile_offsets, R, keys, tr, cap, pa, gx, bg, W, H, out, final_T, n_contrib); break;
+        case 2: le = gfb_launch_pdl(tile_sort_blend_fwd_kernel<2>, grid, block, st, pdl, tile_offsets, R, keys, tr, cap, pa, gx, bg, W, H, out, final_T, n_contrib); break;
+        case 3: le = gfb_launch_pdl(tile_sort_blend_fwd_kernel<3>, grid, block, st, pdl, tile_offsets, R, keys, tr, cap, pa, gx, bg, W, H, out, final_T, n_contrib); break;
+        default: le = gfb_launch_pdl(tile_sort_blend_fwd_kernel<4>, grid, block, st, pdl, tile_offsets, R, keys, tr, cap, pa, gx, bg, W, H, out, final_T, n_contrib); break;
+    }
+    if (le != cudaSuccess) return (int)le;
+    GFB_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" {
 

@@ -31,6 +31,9 @@
 
 // pipeline.cu / blend.cu
 bool gfb_tight_tiles();
+int gfb_internal_scatter_sort_pack_blend(const void*, const float*, int, int, int, void*, int64_t, void*, int32_t*, const float*,
+                                         const float*, const float*, const float*, int, int32_t*, void*, void*, float, float*,
+                                         float*, int32_t*, void*, bool pdl);
 int gfb_internal_scatter_sort_pack(const void*, const float*, int, int, int, void*, int64_t, void*, int32_t*,
                                    const float*, const float*, const float*, const float*, int, int32_t*, void*, void*,
                                    void*, bool);
@@ -880,11 +883,8 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
             p->extent, C, reinterpret_cast<float2*>(uv), depth, conic, radius, reinterpret_cast<ushort4*>(rect), op_act,
             feat, counts, offsets, ctrl, T, R, rg, loss_acc, p->dbg_act, tight);
         GFB_CHECK_LAUNCH();
-        rc = gfb_internal_scatter_sort_pack(rect, depth, N, W, H, counts, capacity, keys, tile_range, uv, conic, op_act,
-                                            feat, C, ids, geom, fstream, stream, pdl);
-        if (rc) return rc;
-        rc = gfb_internal_blend_fwd(geom, fstream, capacity, tile_range, C, 0, C, p->bg, W, H, out, final_T, n_contrib,
-                                    stream, pdl);
+        rc = gfb_internal_scatter_sort_pack_blend(rect, depth, N, W, H, counts, capacity, keys, tile_range, uv, conic, op_act,
+                                                  feat, C, ids, geom, fstream, p->bg, out, final_T, n_contrib, stream, pdl);
         if (rc) return rc;
         if (use_sub) {
             int32_t* s_counts = (int32_t*)(sw + S.control);
@@ -897,14 +897,12 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                 (float*)(sw + S.op_act), (float*)(sw + S.feat), s_counts, s_ctrl + GFB_CTRL_WORDS, s_ctrl, T, R, no_regs,
                 loss_acc, nullptr, tight);
             GFB_CHECK_LAUNCH();
-            rc = gfb_internal_scatter_sort_pack(sw + S.rect, (float*)(sw + S.depth), p->sub_N, W, H, s_counts, p->sub_capacity,
-                                                sw + S.keys, (int32_t*)(sw + S.tile_range), (float*)(sw + S.uv),
-                                                (float*)(sw + S.conic), (float*)(sw + S.op_act), (float*)(sw + S.feat), 3,
-                                                (int32_t*)(sw + S.ids), sw + S.geom, sw + S.fstream, stream, pdl);
-            if (rc) return rc;
-            rc = gfb_internal_blend_fwd(sw + S.geom, sw + S.fstream, p->sub_capacity, (int32_t*)(sw + S.tile_range), 3, 0, 3,
-                                        p->bg, W, H, (float*)(sw + S.out), (float*)(sw + S.final_T),
-                                        (int32_t*)(sw + S.n_contrib), stream, pdl);
+            rc = gfb_internal_scatter_sort_pack_blend(sw + S.rect, (float*)(sw + S.depth), p->sub_N, W, H, s_counts,
+                                                      p->sub_capacity, sw + S.keys, (int32_t*)(sw + S.tile_range),
+                                                      (float*)(sw + S.uv), (float*)(sw + S.conic), (float*)(sw + S.op_act),
+                                                      (float*)(sw + S.feat), 3, (int32_t*)(sw + S.ids), sw + S.geom,
+                                                      sw + S.fstream, p->bg, (float*)(sw + S.out), (float*)(sw + S.final_T),
+                                                      (int32_t*)(sw + S.n_contrib), stream, pdl);
             if (rc) return rc;
             fit_move_mask_kernel<<<gfb_div_up(P, 256), 256, 0, st>>>((float*)(sw + S.out), P, p->dyn_mask, s_ctrl, status);
             GFB_CHECK_LAUNCH();

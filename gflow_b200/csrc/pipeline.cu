@@ -23,6 +23,7 @@
 // GFB_E_CAPACITY so the caller can retry with a larger buffer.
 #include <cstdlib>
 
+#include "records.cuh"
 #include "sort_network.cuh"
 #include "splat_math.cuh"
 
@@ -31,6 +32,9 @@ bool gfb_tight_tiles();
 // blend.cu
 int gfb_internal_blend_fwd(const void*, const void*, int64_t, const int32_t*, int, int, int, float, int, int, float*,
                            float*, int32_t*, void*, bool pdl);
+int gfb_internal_sort_pack_blend_fwd(const int32_t*, int, void*, int32_t*, int64_t, const float*, const float*, const float*,
+                                     const float*, int, int32_t*, void*, void*, float, int, int, float*, float*, int32_t*,
+                                     void*, bool pdl);
 extern "C" int gfb_alpha_blending_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int,
                                       float, int, int, const float*, const int32_t*, const float*, float*, void*);
 
@@ -150,35 +154,8 @@ scatter_kernel(const ushort4* __restrict__ rect, const float* __restrict__ depth
     }
 }
 
-// record writers -------------------------------------------------------------
-struct PackArgs {
-    const float2* uv;
-    const float* conic;
-    const float* opacity;
-    const float* feature;
-    int C;
-    float4* sA;
-    float4* sB;
-    float4* sF;
-    int32_t* ids;
-};
-
-__device__ __forceinline__ void write_record(const PackArgs& a, long long k, int id) {
-    const float2 p = a.uv[id];
-    const float ca = a.conic[3 * id], cb = a.conic[3 * id + 1], cc = a.conic[3 * id + 2];
-    const float o = a.opacity[id];
-    float hx, hy;
-    splat_bbox(ca, cb, cc, o, hx, hy);
-    const float* f = a.feature + (size_t)id * a.C;
-    float4 fr = make_float4(f[0], 0.0f, 0.0f, 0.0f);
-    if (a.C > 1) fr.y = f[1];
-    if (a.C > 2) fr.z = f[2];
-    if (a.C > 3) fr.w = f[3];
-    a.ids[k] = id;
-    a.sA[k] = gfb_pack_record_a(p.x, p.y, hx, hy, id);
-    a.sB[k] = make_float4(ca, cb, cc, o);
-    a.sF[k] = fr;
-}
+// record writers: records.cuh
+using PackArgs = GfbPackArgs;
 
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_pack_kernel(const int32_t* __restrict__ offsets, int R, unsigned long long* __restrict__ keys,
@@ -187,7 +164,7 @@ tile_sort_pack_kernel(const int32_t* __restrict__ offsets, int R, unsigned long 
     gfb_pdl_launch_dependents();
     gfb_pdl_wait();  // keys come from scatter
     sort_tile_cta(offsets, R, keys, capacity, s_keys, tile_range,
-                   [pa](long long pos, unsigned long long key) { write_record(pa, pos, (int)(unsigned int)key); });
+                   [pa](long long pos, unsigned long long key) { gfb_write_record(pa, pos, (int)(unsigned int)key); });
 }
 
 // Fused geometry backward: grad_pack (from blend_bwd) -> parameter gradients.
@@ -261,6 +238,32 @@ bool gfb_tight_tiles() {
     return on;
 }
 
+// GFB_FUSE_SORT_BLEND=0: run the per-tile sort + pack and the forward blend as two kernels (the round-1 structure)
+// instead of tile_sort_blend_fwd_kernel (blend.cu).
+bool gfb_fuse_sort_blend() {
+    static const bool on = [] {
+        const char* e = getenv("GFB_FUSE_SORT_BLEND");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+static int launch_scatter(const void* rect_ws, const float* depth, int N, int W, int H, void* control_ws, int64_t capacity,
+                          void* keys_ws, void* stream, bool pdl) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
+    const int R = gfb_tile_replicas(T);
+    int32_t* counts = (int32_t*)control_ws;
+    int32_t* tile_offsets = counts + (size_t)T * R + CTRL_WORDS;
+    if (N > 0 && capacity > 0) {
+        GFB_TRY(gfb_launch_pdl(scatter_kernel, dim3(gfb_div_up(N, kThreads)), dim3(kThreads), st, pdl,
+                               reinterpret_cast<const ushort4*>(rect_ws), depth, N, gx, R, tile_offsets, counts,
+                               reinterpret_cast<unsigned long long*>(keys_ws), (long long)capacity));
+        GFB_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
 // Second and third forward kernels for a caller that has run its own preprocess (gfb_render_forward
 // above, the native fit iteration in fit.cu): claim slots + write keys, then per-tile sort + pack.
 // control_ws is laid out as gfb_render_control_bytes() describes and holds the scanned offsets.
@@ -275,12 +278,8 @@ int gfb_internal_scatter_sort_pack(const void* rect_ws, const float* depth, int 
     int32_t* counts = (int32_t*)control_ws;
     int32_t* tile_offsets = counts + (size_t)T * R + CTRL_WORDS;
     float4* sA = reinterpret_cast<float4*>(geom_stream);
-    if (N > 0 && capacity > 0) {
-        GFB_TRY(gfb_launch_pdl(scatter_kernel, dim3(gfb_div_up(N, kThreads)), dim3(kThreads), st, pdl,
-                               reinterpret_cast<const ushort4*>(rect_ws), depth, N, gx, R, tile_offsets, counts,
-                               reinterpret_cast<unsigned long long*>(keys_ws), (long long)capacity));
-        GFB_CHECK_LAUNCH();
-    }
+    int rc = launch_scatter(rect_ws, depth, N, W, H, control_ws, capacity, keys_ws, stream, pdl);
+    if (rc) return rc;
     PackArgs pa{reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, sA, sA + capacity,
                 reinterpret_cast<float4*>(feat_stream), gaussian_ids_sorted};
     GFB_TRY(gfb_launch_pdl(tile_sort_pack_kernel, dim3(T), dim3(kSortThreads), st, pdl, tile_offsets, R,
@@ -288,6 +287,30 @@ int gfb_internal_scatter_sort_pack(const void* rect_ws, const float* depth, int 
                            (long long)capacity, pa));
     GFB_CHECK_LAUNCH();
     return 0;
+}
+
+// The same plus the forward blend of all C <= 4 channels: scatter, then ONE kernel that sorts, packs and blends each
+// tile (or, with GFB_FUSE_SORT_BLEND=0, tile_sort_pack followed by blend_fwd).
+int gfb_internal_scatter_sort_pack_blend(const void* rect_ws, const float* depth, int N, int W, int H, void* control_ws,
+                                         int64_t capacity, void* keys_ws, int32_t* tile_range, const float* uv,
+                                         const float* conic, const float* opacity, const float* feature, int C,
+                                         int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, float bg,
+                                         float* out, float* final_T, int32_t* n_contrib, void* stream, bool pdl) {
+    if (!gfb_fuse_sort_blend() || C < 1 || C > 4) {
+        int rc = gfb_internal_scatter_sort_pack(rect_ws, depth, N, W, H, control_ws, capacity, keys_ws, tile_range, uv, conic,
+                                                opacity, feature, C, gaussian_ids_sorted, geom_stream, feat_stream, stream, pdl);
+        if (rc) return rc;
+        return gfb_internal_blend_fwd(geom_stream, feat_stream, capacity, tile_range, C, 0, C, bg, W, H, out, final_T,
+                                      n_contrib, stream, pdl);
+    }
+    const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE, T = gx * gy;
+    const int R = gfb_tile_replicas(T);
+    const int32_t* tile_offsets = (const int32_t*)control_ws + (size_t)T * R + CTRL_WORDS;
+    int rc = launch_scatter(rect_ws, depth, N, W, H, control_ws, capacity, keys_ws, stream, pdl);
+    if (rc) return rc;
+    return gfb_internal_sort_pack_blend_fwd(tile_offsets, R, keys_ws, tile_range, capacity, uv, conic, opacity, feature, C,
+                                            gaussian_ids_sorted, geom_stream, feat_stream, bg, W, H, out, final_T, n_contrib,
+                                            stream, pdl);
 }
 
 extern "C" {
@@ -354,12 +377,9 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     GFB_CHECK_LAUNCH();
     if (!capturing) GFB_TRY(cudaEventRecord(ev, st));
     // speculative part: enqueued before K is known on the host
-    rc = gfb_internal_scatter_sort_pack(rect_ws, depth, N, W, H, control_ws, capacity, keys_ws, tile_range, uv, conic,
-                                        opacity, feature, C, gaussian_ids_sorted, geom_stream, feat_stream, stream,
-                                        true);
-    if (rc) return rc;
-    rc = gfb_internal_blend_fwd(geom_stream, feat_stream, capacity, tile_range, C, 0, C, bg, W, H, out, final_T,
-                                n_contrib, stream, true);
+    rc = gfb_internal_scatter_sort_pack_blend(rect_ws, depth, N, W, H, control_ws, capacity, keys_ws, tile_range, uv, conic,
+                                              opacity, feature, C, gaussian_ids_sorted, geom_stream, feat_stream, bg, out,
+                                              final_T, n_contrib, stream, true);
     if (rc) return rc;
     if (!K_host) return 0;  // the caller overlaps host work, then calls gfb_wait_k()
     GFB_TRY(cudaEventSynchronize(ev));  // waits for `preprocess` only

@@ -33,6 +33,7 @@ PTX_WRAPPERS = {
     "smem_u32": "return 0u;",
     "mbar_init": "gfb_emu::mbar_init(bar, count);",
     "fence_mbar_init": "",
+    "fence_proxy_async": "",
     "mbar_expect_tx": "gfb_emu::mbar_expect_tx(bar, bytes);",
     "mbar_arrive": "gfb_emu::mbar_arrive(bar);",
     "bulk_g2s": "gfb_emu::bulk_g2s(dst, src, bytes, bar);",
