@@ -40,8 +40,11 @@ SIGNATURES = {
     "gfb_query_k_ticket": (I, [L, P]),
     "gfb_render_forward": (I, [P, P, P, P, P, I, P, P, I, I, I, F, F, F, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P,
                                P, P]),
+    "gfb_render_forward_keep": (I, [P, P, P, P, P, I, P, P, I, I, I, F, F, F, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P,
+                                    P, P]),
     "gfb_render_grad_bytes": (c_size_t, [I]),
     "gfb_render_backward": (I, [P, P, P, P, P, I, I, I, I, F, F, F, P, P, L, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "gfb_render_backward_keep": (I, [P, P, P, P, P, I, I, I, I, F, F, F, P, P, L, P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "gfb_blend_geometry_stream_bytes": (c_size_t, [L]),
     "gfb_blend_feature_stream_bytes": (c_size_t, [L]),
     "gfb_blend_grad_pack_bytes": (c_size_t, [I]),

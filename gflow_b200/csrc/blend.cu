@@ -599,12 +599,14 @@ __global__ void __launch_bounds__(kBlendThreads, kBlendMinCtas)
 blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, const float4* __restrict__ gF,
                  const int2* __restrict__ tile_range, int gx, int c0, float bg, int W, int H,
                  const float* __restrict__ final_T, const int32_t* __restrict__ n_contrib,
-                 const float* __restrict__ g_out, float* __restrict__ grad_pack) {
+                 const float* __restrict__ g_out, float* __restrict__ grad_pack, float* __restrict__ zero16) {
     __shared__ __align__(128) Stage s_stage[2];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_max_last;
 
     gfb_pdl_launch_dependents();  // fused pipeline: geometry_bwd may queue behind the last wave
+    // the camera-gradient block geometry_bwd accumulates into afterwards (saves the caller a memset launch)
+    if (zero16 != nullptr && blockIdx.x == 0 && threadIdx.x < 16) zero16[threadIdx.x] = 0.0f;
 #ifdef GFB_BLEND_TRACE
     TraceScope trace_scope;
 #endif
@@ -804,7 +806,7 @@ int gfb_internal_blend_fwd(const void* geom_stream, const void* feat_stream, int
 }
 
 int gfb_internal_blend_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int, float, int, int,
-                           const float*, const int32_t*, const float*, float*, void*, bool no_rgb);
+                           const float*, const int32_t*, const float*, float*, void*, bool no_rgb, float* zero16);
 
 // Fused pipeline / native loop: per-tile sort + pack + forward blend of all C <= 4 channels in one kernel
 // (tile_sort_blend_fwd_kernel).  tile_offsets / R: the scanned (tile, replica) counters of the control block;
@@ -850,16 +852,17 @@ int gfb_alpha_blending_bwd(const void* geom_stream, const void* feat_stream, int
                            float bg, int W, int H, const float* final_T, const int32_t* n_contrib, const float* g_out,
                            float* grad_pack, void* stream) {
     return gfb_internal_blend_bwd(geom_stream, feat_stream, K, gaussian_ids_sorted, tile_range, C, c0, Cg, bg, W, H, final_T,
-                                  n_contrib, g_out, grad_pack, stream, false);
+                                  n_contrib, g_out, grad_pack, stream, false, nullptr);
 }
 
 }  // extern "C"
 
 // no_rgb: only with Cg == 4 and c0 == 0 (rgb + depth in one blend): skip the colour channels' own gradient
+// zero16: optional 16 floats cleared by the kernel before anything else (the camera gradients of geometry_bwd)
 int gfb_internal_blend_bwd(const void* geom_stream, const void* feat_stream, int64_t K,
                            const int32_t* gaussian_ids_sorted, const int32_t* tile_range, int C, int c0, int Cg,
                            float bg, int W, int H, const float* final_T, const int32_t* n_contrib, const float* g_out,
-                           float* grad_pack, void* stream, bool no_rgb) {
+                           float* grad_pack, void* stream, bool no_rgb, float* zero16) {
     if (no_rgb && (Cg != 4 || c0 != 0)) return GFB_E_BADARG;
     if (W <= 0 || H <= 0 || K < 0 || C <= 0 || c0 < 0 || Cg < 1 || Cg > 4 || c0 + Cg > C) return GFB_E_BADARG;
     if (K == 0) return 0;
@@ -876,7 +879,7 @@ int gfb_internal_blend_bwd(const void* geom_stream, const void* feat_stream, int
     (void)gaussian_ids_sorted;  // the record stream carries the Gaussian id (gfb_pack_record_a)
 #define GFB_BWD_LAUNCH(CGV, NORGB)                                                                                    \
     blend_bwd_kernel<CGV, NORGB><<<grid, block, 0, st>>>(gA, gB, gF, tr, gx, c0, bg, W, H, final_T, n_contrib, g_out, \
-                                                         grad_pack)
+                                                         grad_pack, zero16)
     if (no_rgb) {
         GFB_BWD_LAUNCH(4, true);
     } else {

@@ -40,7 +40,7 @@ int gfb_internal_scatter_sort_pack(const void*, const float*, int, int, int, voi
 int gfb_internal_blend_fwd(const void*, const void*, int64_t, const int32_t*, int, int, int, float, int, int, float*,
                            float*, int32_t*, void*, bool pdl);
 int gfb_internal_blend_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int, float, int, int,
-                           const float*, const int32_t*, const float*, float*, void*, bool no_rgb);
+                           const float*, const int32_t*, const float*, float*, void*, bool no_rgb, float* zero16);
 
 namespace {
 
@@ -922,7 +922,7 @@ int gfb_fit_iterate(const gfb_fit_problem* p, void* workspace, int64_t capacity,
                                                                      (size_t)T * R + GFB_CTRL_K);
         GFB_CHECK_LAUNCH();
         rc = gfb_internal_blend_bwd(geom, fstream, capacity, ids, tile_range, C, 0, C, p->bg, W, H, final_T, n_contrib,
-                                    g_out, grad_ws, stream, no_rgb);
+                                    g_out, grad_ws, stream, no_rgb, nullptr);
         if (rc) return rc;
         GFB_TRY(gfb_launch_pdl(fit_geometry_bwd_adam_kernel, dim3(nblk), dim3(kThreads), st, pdl, p->xyz, p->scale,
                                reinterpret_cast<float4*>(p->rotate), p->opacity, p->rgb, cam, N, W, H, p->nearest, p->extent,

@@ -35,8 +35,8 @@ int gfb_internal_blend_fwd(const void*, const void*, int64_t, const int32_t*, in
 int gfb_internal_sort_pack_blend_fwd(const int32_t*, int, void*, int32_t*, int64_t, const float*, const float*, const float*,
                                      const float*, int, int32_t*, void*, void*, float, int, int, float*, float*, int32_t*,
                                      void*, bool pdl);
-extern "C" int gfb_alpha_blending_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int,
-                                      float, int, int, const float*, const int32_t*, const float*, float*, void*);
+int gfb_internal_blend_bwd(const void*, const void*, int64_t, const int32_t*, const int32_t*, int, int, int, float, int, int,
+                           const float*, const int32_t*, const float*, float*, void*, bool no_rgb, float* zero16);
 
 namespace {
 
@@ -121,6 +121,7 @@ preprocess_kernel(const float* __restrict__ xyz, const float* __restrict__ scale
     const int total = cta_exclusive_scan(counts, T * R, offsets, s_buf, s_scan);
     if (threadIdx.x == 0) {
         ctrl[CTRL_K] = total;
+        ctrl[CTRL_DONE] = 0;  // the ticket is back at zero; scatter hands the counters back: the block cleans itself
         if (k_mapped) *k_mapped = total;  // mapped pinned host word: no D2H copy in the stream
         __threadfence_system();
     }
@@ -171,7 +172,7 @@ tile_sort_pack_kernel(const int32_t* __restrict__ offsets, int R, unsigned long 
 __global__ void __launch_bounds__(kThreads)
 geometry_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ scale, const float4* __restrict__ rotate,
                     const float* __restrict__ intr, const float* __restrict__ extr, int N, int W, int H, float nearest,
-                    float extent, int C, const float4* __restrict__ grad_pack, float* __restrict__ d_xyz,
+                    float extent, int C, float4* __restrict__ grad_pack, int clear_pack, float* __restrict__ d_xyz,
                     float* __restrict__ d_scale, float4* __restrict__ d_rotate, float* __restrict__ d_opacity,
                     float* __restrict__ d_feature, float* __restrict__ d_cam) {
     __shared__ float s_cam[16];
@@ -186,6 +187,12 @@ geometry_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ sca
     for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
     if (i < N) {
         const float4 g0 = grad_pack[3 * (size_t)i], g1 = grad_pack[3 * (size_t)i + 1], g2 = grad_pack[3 * (size_t)i + 2];
+        if (clear_pack) {  // a kept pack is handed back zeroed: the next backward accumulates into it without a memset
+            const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            grad_pack[3 * (size_t)i] = z;
+            grad_pack[3 * (size_t)i + 1] = z;
+            grad_pack[3 * (size_t)i + 2] = z;
+        }
         float dp[3] = {0.0f, 0.0f, 0.0f}, ds[3] = {0.0f, 0.0f, 0.0f};
         float4 dq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         const float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
@@ -329,12 +336,12 @@ size_t gfb_render_control_bytes(int W, int H) {
     return (2 * T * R + 1 + CTRL_WORDS) * sizeof(int32_t);
 }
 
-int gfb_render_forward(const float* xyz, const float* scale, const float* rotate, const float* opacity,
-                       const float* feature, int C, const float* intr, const float* extr, int N, int W, int H,
-                       float bg, float nearest, float extent, float* uv, float* depth, float* conic, int32_t* radius,
-                       void* rect_ws, void* control_ws, int32_t* tile_range, int64_t capacity,
-                       void* keys_ws, int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, float* out,
-                       float* final_T, int32_t* n_contrib, int64_t* K_host, void* stream) {
+static int render_forward_impl(const float* xyz, const float* scale, const float* rotate, const float* opacity,
+                               const float* feature, int C, const float* intr, const float* extr, int N, int W, int H,
+                               float bg, float nearest, float extent, float* uv, float* depth, float* conic, int32_t* radius,
+                               void* rect_ws, void* control_ws, int32_t* tile_range, int64_t capacity,
+                               void* keys_ws, int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, float* out,
+                               float* final_T, int32_t* n_contrib, int64_t* K_host, void* stream, bool keep) {
     if (N < 0 || W <= 0 || H <= 0 || C < 1 || C > 4 || capacity < 0) return GFB_E_BADARG;
     if (!intr || !extr || !control_ws || !tile_range || !out || !final_T || !n_contrib)
         return GFB_E_BADARG;
@@ -362,7 +369,10 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
         rc = gfb_internal_host_sync(&pinned, &mapped, &ev);
         if (rc) return rc;
     }
-    GFB_TRY(cudaMemsetAsync(control_ws, 0, ((size_t)T * R + CTRL_WORDS) * sizeof(int32_t), st));
+    // keep: the caller's control block persists across calls and cleans itself (scatter returns every counter to zero,
+    // the scan resets its ticket); scatter is skipped for N == 0 or capacity == 0, so those calls clear it here
+    if (!keep || N == 0 || capacity == 0)
+        GFB_TRY(cudaMemsetAsync(control_ws, 0, ((size_t)T * R + CTRL_WORDS) * sizeof(int32_t), st));
     // N == 0 still runs one CTA so the scan zeroes the offsets
     if (gfb_tight_tiles())
         preprocess_kernel<true><<<max(1, gfb_div_up(N, kThreads)), kThreads, 0, st>>>(
@@ -387,7 +397,61 @@ int gfb_render_forward(const float* xyz, const float* scale, const float* rotate
     return (*K_host > capacity) ? GFB_E_CAPACITY : 0;
 }
 
+int gfb_render_forward(const float* xyz, const float* scale, const float* rotate, const float* opacity,
+                       const float* feature, int C, const float* intr, const float* extr, int N, int W, int H,
+                       float bg, float nearest, float extent, float* uv, float* depth, float* conic, int32_t* radius,
+                       void* rect_ws, void* control_ws, int32_t* tile_range, int64_t capacity,
+                       void* keys_ws, int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, float* out,
+                       float* final_T, int32_t* n_contrib, int64_t* K_host, void* stream) {
+    return render_forward_impl(xyz, scale, rotate, opacity, feature, C, intr, extr, N, W, H, bg, nearest, extent, uv, depth,
+                               conic, radius, rect_ws, control_ws, tile_range, capacity, keys_ws, gaussian_ids_sorted,
+                               geom_stream, feat_stream, out, final_T, n_contrib, K_host, stream, false);
+}
+
+int gfb_render_forward_keep(const float* xyz, const float* scale, const float* rotate, const float* opacity,
+                            const float* feature, int C, const float* intr, const float* extr, int N, int W, int H,
+                            float bg, float nearest, float extent, float* uv, float* depth, float* conic, int32_t* radius,
+                            void* rect_ws, void* control_ws, int32_t* tile_range, int64_t capacity,
+                            void* keys_ws, int32_t* gaussian_ids_sorted, void* geom_stream, void* feat_stream, float* out,
+                            float* final_T, int32_t* n_contrib, int64_t* K_host, void* stream) {
+    return render_forward_impl(xyz, scale, rotate, opacity, feature, C, intr, extr, N, W, H, bg, nearest, extent, uv, depth,
+                               conic, radius, rect_ws, control_ws, tile_range, capacity, keys_ws, gaussian_ids_sorted,
+                               geom_stream, feat_stream, out, final_T, n_contrib, K_host, stream, true);
+}
+
 size_t gfb_render_grad_bytes(int N) { return N < 0 ? 0 : ((size_t)N * 12 + 16) * sizeof(float); }
+
+static int render_backward_impl(const float* xyz, const float* scale, const float* rotate, const float* intr,
+                                const float* extr, int N, int W, int H, int C, float bg, float nearest, float extent,
+                                const int32_t* gaussian_ids_sorted, const int32_t* tile_range, int64_t capacity,
+                                const void* geom_stream, const void* feat_stream, const float* final_T,
+                                const int32_t* n_contrib, const float* g_out, float* grad_pack, float* d_cam, bool keep,
+                                float* d_xyz, float* d_scale, float* d_rotate, float* d_opacity, float* d_feature,
+                                void* stream) {
+    if (N < 0 || W <= 0 || H <= 0 || C < 1 || C > 4 || capacity < 0 || !grad_pack || !d_cam) return GFB_E_BADARG;
+    const GfbRange nvtx_range("gfb_render_backward");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!keep) {
+        GFB_TRY(cudaMemsetAsync(grad_pack, 0, gfb_render_grad_bytes(N), st));  // pack and d_cam are one block here
+    } else if (N == 0 || capacity == 0) {
+        GFB_TRY(cudaMemsetAsync(d_cam, 0, 16 * sizeof(float), st));  // no blend backward will run to clear it
+    }
+    if (N == 0) return 0;
+    if (!xyz || !scale || !rotate || !intr || !extr || !tile_range || !final_T || !n_contrib || !g_out || !d_xyz ||
+        !d_scale || !d_rotate || !d_opacity || !d_feature)
+        return GFB_E_BADARG;
+    if (capacity > 0) {
+        int rc = gfb_internal_blend_bwd(geom_stream, feat_stream, capacity, gaussian_ids_sorted, tile_range, C, 0, C, bg, W,
+                                        H, final_T, n_contrib, g_out, grad_pack, stream, false, keep ? d_cam : nullptr);
+        if (rc) return rc;
+    }
+    GFB_TRY(gfb_launch_pdl(geometry_bwd_kernel, dim3(gfb_div_up(N, kThreads)), dim3(kThreads), st, capacity > 0, xyz,
+                           scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent, C,
+                           reinterpret_cast<float4*>(grad_pack), keep ? 1 : 0, d_xyz, d_scale,
+                           reinterpret_cast<float4*>(d_rotate), d_opacity, d_feature, d_cam));
+    GFB_CHECK_LAUNCH();
+    return 0;
+}
 
 int gfb_render_backward(const float* xyz, const float* scale, const float* rotate, const float* intr,
                         const float* extr, int N, int W, int H, int C, float bg, float nearest, float extent,
@@ -395,27 +459,22 @@ int gfb_render_backward(const float* xyz, const float* scale, const float* rotat
                         const void* geom_stream, const void* feat_stream, const float* final_T,
                         const int32_t* n_contrib, const float* g_out, void* grad_ws, float* d_xyz, float* d_scale,
                         float* d_rotate, float* d_opacity, float* d_feature, void* stream) {
-    if (N < 0 || W <= 0 || H <= 0 || C < 1 || C > 4 || capacity < 0 || !grad_ws) return GFB_E_BADARG;
-    const GfbRange nvtx_range("gfb_render_backward");
-    cudaStream_t st = (cudaStream_t)stream;
+    if (N < 0 || !grad_ws) return GFB_E_BADARG;
     float* grad_pack = (float*)grad_ws;
-    float* d_cam = grad_pack + (size_t)N * 12;
-    GFB_TRY(cudaMemsetAsync(grad_ws, 0, gfb_render_grad_bytes(N), st));
-    if (N == 0) return 0;
-    if (!xyz || !scale || !rotate || !intr || !extr || !tile_range || !final_T || !n_contrib || !g_out || !d_xyz ||
-        !d_scale || !d_rotate || !d_opacity || !d_feature)
-        return GFB_E_BADARG;
-    if (capacity > 0) {
-        int rc = gfb_alpha_blending_bwd(geom_stream, feat_stream, capacity, gaussian_ids_sorted, tile_range, C, 0, C,
-                                        bg, W, H, final_T, n_contrib, g_out, grad_pack, stream);
-        if (rc) return rc;
-    }
-    GFB_TRY(gfb_launch_pdl(geometry_bwd_kernel, dim3(gfb_div_up(N, kThreads)), dim3(kThreads), st, capacity > 0, xyz,
-                           scale, reinterpret_cast<const float4*>(rotate), intr, extr, N, W, H, nearest, extent, C,
-                           reinterpret_cast<const float4*>(grad_pack), d_xyz, d_scale,
-                           reinterpret_cast<float4*>(d_rotate), d_opacity, d_feature, d_cam));
-    GFB_CHECK_LAUNCH();
-    return 0;
+    return render_backward_impl(xyz, scale, rotate, intr, extr, N, W, H, C, bg, nearest, extent, gaussian_ids_sorted,
+                                tile_range, capacity, geom_stream, feat_stream, final_T, n_contrib, g_out, grad_pack,
+                                grad_pack + (size_t)N * 12, false, d_xyz, d_scale, d_rotate, d_opacity, d_feature, stream);
+}
+
+int gfb_render_backward_keep(const float* xyz, const float* scale, const float* rotate, const float* intr,
+                             const float* extr, int N, int W, int H, int C, float bg, float nearest, float extent,
+                             const int32_t* gaussian_ids_sorted, const int32_t* tile_range, int64_t capacity,
+                             const void* geom_stream, const void* feat_stream, const float* final_T,
+                             const int32_t* n_contrib, const float* g_out, void* grad_pack_keep, float* d_cam, float* d_xyz,
+                             float* d_scale, float* d_rotate, float* d_opacity, float* d_feature, void* stream) {
+    return render_backward_impl(xyz, scale, rotate, intr, extr, N, W, H, C, bg, nearest, extent, gaussian_ids_sorted,
+                                tile_range, capacity, geom_stream, feat_stream, final_T, n_contrib, g_out,
+                                (float*)grad_pack_keep, d_cam, true, d_xyz, d_scale, d_rotate, d_opacity, d_feature, stream);
 }
 
 }  // extern "C"

@@ -403,19 +403,37 @@ bool lazy_k_enabled() {
     return on;
 }
 
-// Buffers of one gfb_render_forward call.  scratch (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N |
-// final_T 4HW | n_contrib 4HW | tile_range 8T | control;  kbuf (bytes): geom 32c | feat 16c | keys 8c | ids 4c.
+// Self-cleaning workspaces kept alive per (device, stream) -- the forward's control block, the backward's gradient
+// pack -- so that a render step launches no memset (gfb_render_forward_keep / gfb_render_backward_keep).  A failed
+// call drops them: they may be dirty.
+std::map<std::tuple<int, int, void*, int64_t>, Tensor> g_kept;
+Tensor kept_block(int kind, const Tensor& like, void* st, int64_t size_key, int64_t nbytes) {
+    std::lock_guard<std::mutex> lock(g_hint_mutex);
+    auto key = std::make_tuple(kind, (int)like.device().index(), st, size_key);
+    auto it = g_kept.find(key);
+    if (it != g_kept.end()) return it->second;
+    Tensor t = at::zeros({nbytes}, like.options().dtype(at::kByte));
+    g_kept[key] = t;
+    return t;
+}
+void drop_kept(int kind, const Tensor& like, void* st, int64_t size_key) {
+    std::lock_guard<std::mutex> lock(g_hint_mutex);
+    g_kept.erase(std::make_tuple(kind, (int)like.device().index(), st, size_key));
+}
+
+// Buffers of one forward call.  scratch (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N |
+// final_T 4HW | n_contrib 4HW | tile_range 8T;  kbuf (bytes): geom 32c | feat 16c | keys 8c | ids 4c.
 struct RasterForward {
     Tensor scratch, kbuf;
     int64_t cap = 0, K = -1, ticket = -1;
 };
 struct RasterLayout {
-    int64_t o_rect, o_depth, o_conic, o_radius, o_ft, o_nc, o_rng, o_ctl, ctl;
+    int64_t o_rect, o_depth, o_conic, o_radius, o_ft, o_nc, o_rng, o_end, ctl;
     RasterLayout(int64_t N, int64_t W, int64_t H) {
         const int64_t T = ((W + 15) / 16) * ((H + 15) / 16), HW = H * W;
         ctl = (int64_t)gfb_render_control_bytes((int)W, (int)H);
         o_rect = 8 * N, o_depth = 16 * N, o_conic = 20 * N, o_radius = 32 * N, o_ft = 36 * N;
-        o_nc = o_ft + 4 * HW, o_rng = ((o_nc + 4 * HW + 7) / 8) * 8, o_ctl = o_rng + 8 * T;
+        o_nc = o_ft + 4 * HW, o_rng = ((o_nc + 4 * HW + 7) / 8) * 8, o_end = o_rng + 8 * T;
     }
 };
 
@@ -427,18 +445,21 @@ RasterForward raster_forward(const Tensor& xyz, const Tensor& scale, const Tenso
     const int64_t N = xyz.size(0), C = feature.size(1);
     const RasterLayout L(N, W, H);
     RasterForward r;
-    r.scratch = at::empty({L.o_ctl + L.ctl + 16}, xyz.options().dtype(at::kByte));
+    r.scratch = at::empty({L.o_end + 16}, xyz.options().dtype(at::kByte));
     char* sp = (char*)r.scratch.data_ptr();
+    void* st = stream();
+    const int64_t ctl_key = W * 65536 + H;
+    Tensor ctl = kept_block(0, xyz, st, ctl_key, L.ctl);
     for (;;) {
         r.kbuf = at::empty({15 * std::max<int64_t>(cap, 1)}, f32(xyz));
         char* kp = (char*)r.kbuf.data_ptr();
-        check_rc(gfb_render_forward(fp(xyz), fp(scale), fp(rotate), fp(opacity), fp(feature), (int)C, fp(intr), fp(extr),
-                                    (int)N, (int)W, (int)H, (float)bg, (float)nearest, (float)extent, (float*)sp,
-                                    (float*)(sp + L.o_depth), (float*)(sp + L.o_conic), (int32_t*)(sp + L.o_radius),
-                                    sp + L.o_rect, sp + L.o_ctl, (int32_t*)(sp + L.o_rng), cap, kp + 48 * cap,
-                                    (int32_t*)(kp + 56 * cap), kp, kp + 32 * cap, fp(out), (float*)(sp + L.o_ft),
-                                    (int32_t*)(sp + L.o_nc), nullptr, stream()),
-                 "rasterization forward");
+        const int rc = gfb_render_forward_keep(
+            fp(xyz), fp(scale), fp(rotate), fp(opacity), fp(feature), (int)C, fp(intr), fp(extr), (int)N, (int)W, (int)H,
+            (float)bg, (float)nearest, (float)extent, (float*)sp, (float*)(sp + L.o_depth), (float*)(sp + L.o_conic),
+            (int32_t*)(sp + L.o_radius), sp + L.o_rect, ctl.data_ptr(), (int32_t*)(sp + L.o_rng), cap, kp + 48 * cap,
+            (int32_t*)(kp + 56 * cap), kp, kp + 32 * cap, fp(out), (float*)(sp + L.o_ft), (int32_t*)(sp + L.o_nc), nullptr, st);
+        if (rc != 0) drop_kept(0, xyz, st, ctl_key);
+        check_rc(rc, "rasterization forward");
         r.cap = cap;
         r.ticket = gfb_k_ticket();
         if (lazy) return r;
@@ -478,7 +499,7 @@ struct Rasterize : public torch::autograd::Function<Rasterize> {
         Tensor out = at::empty({C, H, W}, f32(xyz));
         RasterForward f = raster_forward(xyz, scale, rotate, opacity, feature, intr, extr, W, H, bg, nearest, extent,
                                          capacity_for(dev, N, W, H), out, lazy);
-        Tensor grad_ws = at::empty({12 * N + 16}, f32(xyz));
+        Tensor grad_ws = at::empty({16}, f32(xyz));  // d_cam; the per-Gaussian gradient pack is a kept, self-cleaning block
         Tensor dbuf = at::empty({(11 + C) * std::max<int64_t>(N, 1)}, f32(xyz));
         if (!lazy) remember_k(dev, N, W, H, f.K);
         if (lazy)
@@ -540,18 +561,21 @@ struct Rasterize : public torch::autograd::Function<Rasterize> {
         char* sp = (char*)scratch.data_ptr();
         char* kp = (char*)kbuf.data_ptr();
         float* dp = fp(dbuf);
-        check_rc(gfb_render_backward(fp(xyz), fp(scale), fp(rotate), fp(intr), fp(extr), (int)N, (int)W, (int)H, (int)C,
-                                     (float)bg, (float)nearest, (float)extent, (int32_t*)(kp + 56 * cap),
-                                     (int32_t*)(sp + L.o_rng), cap, kp, kp + 32 * cap, (float*)(sp + L.o_ft),
-                                     (int32_t*)(sp + L.o_nc), fp(g_out), grad_ws.data_ptr(), dp + 4 * N, dp + 7 * N, dp,
-                                     dp + 10 * N, dp + 11 * N, stream()),
-                 "rasterization backward");
+        void* st = stream();
+        Tensor pack = kept_block(1, xyz, st, N, 48 * std::max<int64_t>(N, 1));
+        const int rc_b = gfb_render_backward_keep(
+            fp(xyz), fp(scale), fp(rotate), fp(intr), fp(extr), (int)N, (int)W, (int)H, (int)C, (float)bg, (float)nearest,
+            (float)extent, (int32_t*)(kp + 56 * cap), (int32_t*)(sp + L.o_rng), cap, kp, kp + 32 * cap, (float*)(sp + L.o_ft),
+            (int32_t*)(sp + L.o_nc), fp(g_out), pack.data_ptr(), fp(grad_ws), dp + 4 * N, dp + 7 * N, dp, dp + 10 * N,
+            dp + 11 * N, st);
+        if (rc_b != 0) drop_kept(1, xyz, st, N);
+        check_rc(rc_b, "rasterization backward");
         Tensor d_rotate = dbuf.narrow(0, 0, 4 * N).view({N, 4});
         Tensor d_xyz = dbuf.narrow(0, 4 * N, 3 * N).view({N, 3});
         Tensor d_scale = dbuf.narrow(0, 7 * N, 3 * N).view({N, 3});
         Tensor d_opacity = dbuf.narrow(0, 10 * N, N).view({N, 1});
         Tensor d_feature = dbuf.narrow(0, 11 * N, C * N).view({N, C});
-        Tensor d_cam = grad_ws.narrow(0, 12 * N, 16);
+        Tensor d_cam = grad_ws;
         return {d_xyz, d_scale, d_rotate, d_opacity, d_feature, d_cam.narrow(0, 12, 4), d_cam.narrow(0, 0, 12).view({3, 4}),
                 Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
     }

@@ -57,12 +57,13 @@ class GraphedRenderStep:
                 capacity = k + k // 4 + 4096
             cap = self.capacity = int(capacity)
             self._gbuf = torch.empty(9 * max(N, 1), device=dev, dtype=f32)
-            self._tbuf = torch.empty(8 * T + self.lib.gfb_render_control_bytes(self.W, self.H), device=dev, dtype=torch.uint8)
+            # tile_range (8T bytes) | control block: zero once, self-cleaning afterwards (gfb_render_forward_keep)
+            self._tbuf = torch.zeros(8 * T + self.lib.gfb_render_control_bytes(self.W, self.H), device=dev, dtype=torch.uint8)
             self._kbuf = torch.empty(15 * max(cap, 1), device=dev, dtype=f32)
             self._aux = torch.empty(2, self.H, self.W, device=dev, dtype=f32)
             self.image = torch.empty(C, self.H, self.W, device=dev, dtype=f32)
             self.g_image = torch.zeros(C, self.H, self.W, device=dev, dtype=f32)
-            self._grad_ws = torch.empty(12 * N + 16, device=dev, dtype=f32)
+            self._grad_ws = torch.zeros(12 * N + 16, device=dev, dtype=f32)  # kept gradient pack (self-cleaning) | d_cam
             if grad_buffer is not None:
                 if grad_buffer.numel() != (11 + C) * N or grad_buffer.dtype != f32 or not grad_buffer.is_contiguous():
                     raise RuntimeError("gflow_b200: grad_buffer must be a contiguous float32 tensor of (11 + C) N elements")
@@ -112,15 +113,16 @@ class GraphedRenderStep:
         if not (backward and self.with_backward):
             return
         dp = self._dbuf.data_ptr()
-        capi.check(self.lib.gfb_render_backward(
+        gw = self._grad_ws.data_ptr()
+        capi.check(self.lib.gfb_render_backward_keep(
             self.xyz.data_ptr(), self.scale.data_ptr(), self.rotate.data_ptr(), self.intr.data_ptr(), self.extr.data_ptr(),
             N, W, H, C, self.bg, self.nearest, self.extent, kp + 56 * cap, tp, cap, kp, kp + 32 * cap, self._aux.data_ptr(),
-            self._aux.data_ptr() + 4 * H * W, self.g_image.data_ptr(), self._grad_ws.data_ptr(), dp + 16 * N, dp + 28 * N, dp,
+            self._aux.data_ptr() + 4 * H * W, self.g_image.data_ptr(), gw, gw + 48 * N, dp + 16 * N, dp + 28 * N, dp,
             dp + 40 * N, dp + 44 * N, st), "graphed rasterization backward")
 
     def _enqueue_forward(self, gp, tp, kp, st) -> None:
         N, C, W, H, cap, T = self.N, self.C, self.W, self.H, self.capacity, self.T
-        capi.check(self.lib.gfb_render_forward(
+        capi.check(self.lib.gfb_render_forward_keep(
             self.xyz.data_ptr(), self.scale.data_ptr(), self.rotate.data_ptr(), self.opacity.data_ptr(),
             self.feature.data_ptr(), C, self.intr.data_ptr(), self.extr.data_ptr(), N, W, H, self.bg, self.nearest, self.extent,
             gp, gp + 16 * N, gp + 20 * N, gp + 32 * N, gp + 8 * N, tp + 8 * T, tp, cap, kp + 48 * cap, kp + 56 * cap,

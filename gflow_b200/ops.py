@@ -494,32 +494,48 @@ _CLIPPED_WARNING = ("gflow_b200.rasterization: the intersection count grew by mo
                     "recomputed from a corrected pass).  Set GFLOW_B200_LAZY_K=0 to validate K inside every forward.")
 
 
+# Self-cleaning workspaces kept alive per (device, stream): the control block of the forward and the gradient pack of
+# the backward return to all-zero by themselves (gfb_render_forward_keep / gfb_render_backward_keep), so a render step
+# launches no memset.  A failed call drops them (they may be dirty).
+_KEPT = {}
+
+
+def _kept(kind, dev, stream, size_key, nbytes):
+    key = (kind, dev.index, stream, size_key)
+    t = _KEPT.get(key)
+    if t is None:
+        t = torch.zeros(nbytes, device=dev, dtype=torch.uint8)
+        _KEPT[key] = t
+    return key, t
+
+
 def _raster_forward(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr_c, N, C, W, H, bg, nearest, extent, dev,
                     cap, out, lazy):
-    """Enqueues gfb_render_forward with capacity `cap`.  Returns (kbuf, tbuf, aux, cap, K, ticket): K is None and
+    """Enqueues the fused forward with capacity `cap`.  Returns (kbuf, tbuf, aux, cap, K, ticket): K is None and
     ticket names the pending hand-off when `lazy`, otherwise K is final (the call retried until it fitted)."""
     gx, gy = _grid(W, H)
     T = gx * gy
     k_host = _ctypes.c_int64(0)
+    st = _stream()
     # per-Gaussian buffer (bytes): uv 8N | rect 8N | depth 4N | conic 12N | radius 4N
     gbuf = torch.empty(9 * max(N, 1), device=dev, dtype=torch.float32)
     gp = gbuf.data_ptr()
     p_uv, p_rect, p_depth, p_conic, p_radius = gp, gp + 8 * N, gp + 16 * N, gp + 20 * N, gp + 32 * N
-    # tile buffer: range 2T int32 (8-byte aligned) | control workspace
-    tbuf = torch.empty(8 * T + _lib.gfb_render_control_bytes(W, H), device=dev, dtype=torch.uint8)
-    tp = tbuf.data_ptr()
-    p_rng, p_ctl = tp, tp + 8 * T
+    tbuf = torch.empty(8 * T, device=dev, dtype=torch.uint8)  # tile_range (T,2) int32: the backward reads it
+    ckey, ctl = _kept("control", dev, st, (W, H), _lib.gfb_render_control_bytes(W, H))
     aux = torch.empty(2, H, W, device=dev, dtype=torch.float32)  # final_T | n_contrib (int32 bits)
     while True:
         # K-sized buffer (bytes): geom 32c | feat 16c | keys 8c | ids 4c
         kbuf = torch.empty(15 * max(cap, 1), device=dev, dtype=torch.float32)
         kp = kbuf.data_ptr()
-        rc = _lib.gfb_render_forward(
+        rc = _lib.gfb_render_forward_keep(
             xyz_c.data_ptr(), scale_c.data_ptr(), rotate_c.data_ptr(), opacity_c.data_ptr(),
             feature_c.data_ptr(), C, intr_c.data_ptr(), extr_c.data_ptr(), N, W, H, bg, nearest, extent,
-            p_uv, p_depth, p_conic, p_radius, p_rect, p_ctl, p_rng, cap, kp + 48 * cap, kp + 56 * cap,
+            p_uv, p_depth, p_conic, p_radius, p_rect, ctl.data_ptr(), tbuf.data_ptr(), cap, kp + 48 * cap, kp + 56 * cap,
             kp, kp + 32 * cap, out.data_ptr(), aux.data_ptr(), aux.data_ptr() + 4 * H * W,
-            None, _stream())
+            None, st)
+        if rc != 0:
+            _KEPT.pop(ckey, None)
         capi.check(rc, "rasterization forward")
         ticket = int(_lib.gfb_k_ticket())
         if lazy:
@@ -558,8 +574,9 @@ class _Rasterize(torch.autograd.Function):
             kbuf, tbuf, aux, cap, K, ticket = _raster_forward(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr_c,
                                                               N, C, W, H, bg, nearest, extent, dev, _capacity_for(key, N), out,
                                                               lazy)
-            # backward buffers: grad pack 12N+16 | d_rotate 4N | d_xyz 3N | d_scale 3N | d_opacity N | d_feature CN
-            bufs = (torch.empty(12 * N + 16, device=dev, dtype=torch.float32),
+            # backward buffers: d_cam 16 | d_rotate 4N | d_xyz 3N | d_scale 3N | d_opacity N | d_feature CN (the packed
+            # per-Gaussian gradients live in a kept, self-cleaning block)
+            bufs = (torch.empty(16, device=dev, dtype=torch.float32),
                     torch.empty((11 + C) * max(N, 1), device=dev, dtype=torch.float32))
         if lazy:  # validated when the backward starts; opacity / feature are kept for a corrective pass
             ctx.save_for_backward(xyz_c, scale_c, rotate_c, intr_c, extr_c, opacity_c, feature_c)
@@ -575,7 +592,7 @@ class _Rasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         xyz, scale, rotate, intr, extr = ctx.saved_tensors[:5]
-        kbuf, tbuf, aux, grad_ws, dbuf = ctx.bufs
+        kbuf, tbuf, aux, d_cam, dbuf = ctx.bufs
         N, C, T, cap, W, H, bg, nearest, extent = ctx.meta
         dev = xyz.device
         with _on_device(dev):
@@ -598,25 +615,29 @@ class _Rasterize(torch.autograd.Function):
                     kbuf, tbuf, aux, cap, K, _ = _raster_forward(xyz, scale, rotate, opacity_c, feature_c, intr, extr, N, C, W, H,
                                                                  bg, nearest, extent, dev, cap2, scratch, False)
                     _K_HINT[key] = max(K, 1)
-                    ctx.bufs = (kbuf, tbuf, aux, grad_ws, dbuf)
+                    ctx.bufs = (kbuf, tbuf, aux, d_cam, dbuf)
                     ctx.meta = (N, C, T, cap, W, H, bg, nearest, extent)
             if getattr(ctx, "bwd_done", False):  # retain_graph: earlier gradients alias the first buffers
-                grad_ws, dbuf = torch.empty_like(grad_ws), torch.empty_like(dbuf)
+                d_cam, dbuf = torch.empty_like(d_cam), torch.empty_like(dbuf)
             ctx.bwd_done = True
             g_out = _prep(g_out, "grad feature_map", shape=(C, H, W))
             dp = dbuf.data_ptr()
             kp, tp = kbuf.data_ptr(), tbuf.data_ptr()
-            capi.check(_lib.gfb_render_backward(
+            st = _stream()
+            pkey, pack = _kept("grad_pack", dev, st, N, 48 * max(N, 1))
+            rc = _lib.gfb_render_backward_keep(
                 xyz.data_ptr(), scale.data_ptr(), rotate.data_ptr(), intr.data_ptr(), extr.data_ptr(), N, W, H, C, bg,
                 nearest, extent, kp + 56 * cap, tp, cap, kp, kp + 32 * cap, aux.data_ptr(),
-                aux.data_ptr() + 4 * H * W, g_out.data_ptr(), grad_ws.data_ptr(), dp + 16 * N, dp + 28 * N, dp,
-                dp + 40 * N, dp + 44 * N, _stream()), "rasterization backward")
+                aux.data_ptr() + 4 * H * W, g_out.data_ptr(), pack.data_ptr(), d_cam.data_ptr(), dp + 16 * N, dp + 28 * N, dp,
+                dp + 40 * N, dp + 44 * N, st)
+            if rc != 0:
+                _KEPT.pop(pkey, None)
+            capi.check(rc, "rasterization backward")
         d_rotate = dbuf[:4 * N].view(N, 4)
         d_xyz = dbuf[4 * N:7 * N].view(N, 3)
         d_scale = dbuf[7 * N:10 * N].view(N, 3)
         d_opacity = dbuf[10 * N:11 * N].view(N, 1)
         d_feature = dbuf[11 * N:(11 + C) * N].view(N, C)
-        d_cam = grad_ws[12 * N:]
         return (d_xyz, d_scale, d_rotate, d_opacity, d_feature, d_cam[12:16], d_cam[:12].view(3, 4), None, None, None,
                 None, None, None)
 

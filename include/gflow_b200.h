@@ -178,6 +178,27 @@ int gfb_render_backward(const float *xyz, const float *scale, const float *rotat
                         const int32_t *n_contrib, const float *g_out, void *grad_ws, float *d_xyz, float *d_scale,
                         float *d_rotate, float *d_opacity, float *d_feature, void *stream);
 
+/* Variants for callers that keep their workspaces ALIVE across calls on one stream, which saves the two memset
+ * launches of a render step (the blocks clean themselves):
+ *   control_ws      zero before the first call; every call leaves it zero again (scatter hands the tile counters
+ *                   back, the scan resets its ticket; only the K word keeps its value)
+ *   grad_pack_keep  N x 12 floats, zero before the first call; geometry_bwd clears each row after reading it
+ *   d_cam           16 floats (d_extr 3x4, d_intr 4), any contents: cleared by the blend backward before use
+ * After a call that returned an error the caller must zero the kept blocks again before reusing them.  Everything
+ * else as gfb_render_forward / gfb_render_backward. */
+int gfb_render_forward_keep(const float *xyz, const float *scale, const float *rotate, const float *opacity,
+                            const float *feature, int C, const float *intr, const float *extr, int N, int W, int H,
+                            float bg, float nearest, float extent, float *uv, float *depth, float *conic, int32_t *radius,
+                            void *rect_ws, void *control_ws, int32_t *tile_range, int64_t capacity,
+                            void *keys_ws, int32_t *gaussian_ids_sorted, void *geom_stream, void *feat_stream, float *out,
+                            float *final_T, int32_t *n_contrib, int64_t *K_host, void *stream);
+int gfb_render_backward_keep(const float *xyz, const float *scale, const float *rotate, const float *intr,
+                             const float *extr, int N, int W, int H, int C, float bg, float nearest, float extent,
+                             const int32_t *gaussian_ids_sorted, const int32_t *tile_range, int64_t capacity,
+                             const void *geom_stream, const void *feat_stream, const float *final_T,
+                             const int32_t *n_contrib, const float *g_out, void *grad_pack_keep, float *d_cam, float *d_xyz,
+                             float *d_scale, float *d_rotate, float *d_opacity, float *d_feature, void *stream);
+
 /* ------------------------------------------------------------------ native per-frame optimisation loop
  * The inner loop GFlow runs per frame, /root/reference/gflow/trainer.py:387-558 (driven by
  * /root/reference/gflow/fit_video.py:119-142,256-315), as ONE stream of kernels per iteration with no host

@@ -118,8 +118,9 @@ def operator_chain(sc, Gimg, C=3, feature=None):
                            extr=d_cam[:12].reshape(3, 4), intr=d_cam[12:]))
 
 
-def fused_pipeline(sc, Gimg, feature=None, capacity=None):
-    """gfb_render_forward / gfb_render_backward (msplat.rasterization)."""
+def fused_pipeline(sc, Gimg, feature=None, capacity=None, kept=None):
+    """gfb_render_forward / gfb_render_backward (msplat.rasterization).  kept: dict holding the caller-kept,
+    self-cleaning workspaces across calls ("control", "pack"): the *_keep entry points are used then."""
     L = load()
     N, W, H = sc.xyz.shape[0], sc.W, sc.H
     gx, gy = (W + 15) // 16, (H + 15) // 16
@@ -130,7 +131,10 @@ def fused_pipeline(sc, Gimg, feature=None, capacity=None):
     intr, extr = sc.intr.contiguous(), sc.extr.contiguous()
     uv, depth, conic, radius = f32(N, 2), f32(N, 1), f32(N, 3), i32(N, 1)
     rect = torch.zeros(max(N, 1) * 8, dtype=torch.uint8)
-    ctrl = torch.full((L.gfb_render_control_bytes(W, H),), 0x5A, dtype=torch.uint8)
+    if kept is not None:
+        ctrl = kept.setdefault("control", torch.zeros(L.gfb_render_control_bytes(W, H), dtype=torch.uint8))
+    else:
+        ctrl = torch.full((L.gfb_render_control_bytes(W, H),), 0x5A, dtype=torch.uint8)
     rng = i32(T, 2)
     cap = int(capacity) if capacity is not None else 64 * max(N, 1)
     keys = torch.zeros(max(cap, 1) * 8, dtype=torch.uint8)
@@ -139,18 +143,26 @@ def fused_pipeline(sc, Gimg, feature=None, capacity=None):
     feat = torch.zeros(max(cap, 1) * 4, dtype=torch.float32)
     out, fT, nc = f32(C, H, W), f32(H, W), i32(H, W)
     K = ctypes.c_int64(-1)
-    rc = L.gfb_render_forward(p(xyz), p(scale), p(rot), p(op), p(feature), C, p(intr), p(extr), N, W, H, sc.bg, 0.2, 1.3,
+    fwd = L.gfb_render_forward_keep if kept is not None else L.gfb_render_forward
+    rc = fwd(p(xyz), p(scale), p(rot), p(op), p(feature), C, p(intr), p(extr), N, W, H, sc.bg, 0.2, 1.3,
                               p(uv), p(depth), p(conic), p(radius), p(rect), p(ctrl), p(rng), cap, p(keys), p(ids),
                               p(geom), p(feat), p(out), p(fT), p(nc), ctypes.addressof(K), None)
     K = int(K.value)
     if rc != 0:
         return dict(rc=rc, K=K)
-    gws = torch.full((L.gfb_render_grad_bytes(N) // 4,), float("nan"), dtype=torch.float32)
     d_xyz, d_scale, d_rot, d_op, d_feat = f32(N, 3), f32(N, 3), f32(N, 4), f32(N, 1), f32(N, C)
-    ok(L.gfb_render_backward(p(xyz), p(scale), p(rot), p(intr), p(extr), N, W, H, C, sc.bg, 0.2, 1.3, p(ids), p(rng), cap,
-                             p(geom), p(feat), p(fT), p(nc), p(Gimg.contiguous()), p(gws), p(d_xyz), p(d_scale), p(d_rot),
-                             p(d_op), p(d_feat), None), "render backward")
-    d_cam = gws[N * 12:N * 12 + 16]
+    if kept is not None:
+        pack = kept.setdefault("pack", torch.zeros(max(N, 1) * 12, dtype=torch.float32))
+        d_cam = torch.full((16,), float("nan"), dtype=torch.float32)
+        ok(L.gfb_render_backward_keep(p(xyz), p(scale), p(rot), p(intr), p(extr), N, W, H, C, sc.bg, 0.2, 1.3, p(ids), p(rng),
+                                      cap, p(geom), p(feat), p(fT), p(nc), p(Gimg.contiguous()), p(pack), p(d_cam), p(d_xyz),
+                                      p(d_scale), p(d_rot), p(d_op), p(d_feat), None), "render backward (kept workspaces)")
+    else:
+        gws = torch.full((L.gfb_render_grad_bytes(N) // 4,), float("nan"), dtype=torch.float32)
+        ok(L.gfb_render_backward(p(xyz), p(scale), p(rot), p(intr), p(extr), N, W, H, C, sc.bg, 0.2, 1.3, p(ids), p(rng), cap,
+                                 p(geom), p(feat), p(fT), p(nc), p(Gimg.contiguous()), p(gws), p(d_xyz), p(d_scale), p(d_rot),
+                                 p(d_op), p(d_feat), None), "render backward")
+        d_cam = gws[N * 12:N * 12 + 16]
     return dict(rc=0, uv=uv, depth=depth, conic=conic, radius=radius, ids=ids[:K].clone(), tile_range=rng, K=K, image=out,
                 final_T=fT, n_contrib=nc,
                 grads=dict(xyz=d_xyz, scale=d_scale, rotate=d_rot, opacity=d_op, feature=d_feat,

@@ -190,6 +190,32 @@ def test_randomised_edge_cases():
             emu.set_schedule(0)
 
 
+def test_kept_workspaces_clean_themselves():
+    """gfb_render_forward_keep / gfb_render_backward_keep: the caller's control block and gradient pack are zero
+    before the first call and return to zero by themselves (scatter hands the tile counters back, the scan resets its
+    ticket, geometry_bwd clears each pack row after reading it, the blend backward clears d_cam) -- no memset launch
+    per step.  Three calls over the same kept blocks, different scenes and a capacity overflow in between, give the
+    results of the self-contained entry points."""
+    kept = {}
+    for i, (N, W, H, seed, cap) in enumerate([(900, 64, 48, 3, None), (900, 64, 48, 4, 50), (900, 64, 48, 5, None)]):
+        sc = make_scene(N, W, H, seed=seed, bg=0.2)
+        Gimg = make_grad_image(3, W, H, seed=seed)
+        a = emu.fused_pipeline(sc, Gimg, capacity=cap, kept=kept)
+        b = emu.fused_pipeline(sc, Gimg, capacity=cap)
+        assert a["rc"] == b["rc"] and a["K"] == b["K"]
+        ctl = kept["control"].view(torch.int32).clone()
+        k_word = emu.load().gfb_render_control_k_offset(W, H) // 4
+        ctl[k_word] = 0  # the K word keeps its value (it is overwritten, never accumulated)
+        n_counts = k_word + 3  # counters + control words; the scanned offsets behind them are rewritten every call
+        assert int(ctl[:n_counts].abs().sum()) == 0, f"call {i}: the kept control block must be back at zero"
+        if a["rc"] != 0:  # GFB_E_CAPACITY: the caller retries larger; the kept block is already clean for that
+            continue
+        assert torch.equal(a["image"], b["image"]) and torch.equal(a["ids"], b["ids"])
+        for k in a["grads"]:
+            assert_close(a["grads"][k], b["grads"][k], 1e-5, f"kept-workspace grad {k}")
+        assert int((kept["pack"] != 0).sum()) == 0, f"call {i}: the kept gradient pack must be back at zero"
+
+
 def test_full_size_config2_fused_pipeline():
     """BASELINE config 2 at full size (60 000 Gaussians, 854x480, K = 197 461) through the shim: ids / tile_range /
     per-Gaussian geometry bit-exact, image 1e-4, gradients 1e-3 against the C oracle (about 20 s)."""
