@@ -97,7 +97,9 @@ def load():
         _build.build()
     if not os.path.exists(_build.LIB_PATH):
         raise ImportError(f"gflow_b200: CUDA library missing at {_build.LIB_PATH}; run __graft_entry__.build()")
-    lib = ctypes.CDLL(_build.LIB_PATH)
+    # GFLOW_B200_LIB: another build of the same C ABI (A/B of whole-library variants, tools/build_variants.py); use it
+    # together with GFLOW_B200_NO_EXT=1, the C++ binding is linked against the default library
+    lib = ctypes.CDLL(os.environ.get("GFLOW_B200_LIB") or _build.LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
         fn.restype = res

@@ -316,8 +316,11 @@ struct WarpTileWalk {
 
 // Tile counters are replicated R ways (replica = CTA index mod R): atomics on one address serialise
 // in the L2 at roughly one per 50 cycles, and a 60k-Gaussian frame puts >100 of them on every tile.
+#ifndef GFB_TILE_REPLICAS_MAX
+#define GFB_TILE_REPLICAS_MAX 4
+#endif
 __host__ __device__ __forceinline__ int gfb_tile_replicas(int T) {
-    int r = 8;
+    int r = GFB_TILE_REPLICAS_MAX;
     while (r > 1 && (long long)T * r > 16384) r >>= 1;
     return r;
 }
