@@ -260,24 +260,12 @@ def run_ours(args):
     distributed = world > 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    t_init = t_bcast = t_bcast_frame = 0.0
+    t_init = t_bcast = t_bcast_first = t_bcast_frame = 0.0
     if distributed:
         t0 = time.perf_counter()
         dist.init_process_group("nccl", device_id=dev)
         # communicator bring-up (hundreds of ms) happens here, not inside the first payload collective
-        dist.barrier()
-        warm = torch.ones(1, device=dev)
-        dist.all_reduce(warm)
-        dist.broadcast(warm, src=0)
-        # a payload-sized broadcast / all_gather once, so the timed ones below do not pay for channel set-up
-        big = torch.zeros(1 << 20, device=dev)
-        dist.broadcast(big, src=0)
-        dist.all_gather([torch.empty_like(big) for _ in range(world)], big)
-        from gflow_b200 import frames as _fr  # the same call pattern once on a tiny state (int64 count + float payload)
-
-        tiny = {k: torch.zeros(8, w, device=dev) for k, w in _fr.STATE_KEYS}
-        _fr.broadcast_state(tiny if rank == 0 else None, src=0, device=dev)
-        _fr.gather_frames(torch.zeros(3, 8, 8, device=dev), torch.zeros(3, 4, device=dev), dst=0)
+        frames.warm_up(dev)
         torch.cuda.synchronize()
         t_init = time.perf_counter() - t0
     lib = capi.load()
@@ -291,6 +279,11 @@ def run_ours(args):
     state = {k: getattr(sc, k).to(dev) for k in ("xyz", "scale", "rotate", "opacity", "rgb")}
     if distributed:
         torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        state = frames.broadcast_state(state if rank == 0 else None, src=0, device=dev)
+        torch.cuda.synchronize()
+        t_bcast_first = time.perf_counter() - t0  # first call at this size: includes the allocator growing on every rank
         dist.barrier()
         t0 = time.perf_counter()
         state = frames.broadcast_state(state if rank == 0 else None, src=0, device=dev)
@@ -515,6 +508,7 @@ def run_ours(args):
                 line[k] = v
         if distributed:
             line["collectives_ms"] = {"nccl_init_and_warmup": 1e3 * t_init, "broadcast_state": 1e3 * t_bcast,
+                                      "broadcast_state_first_call": 1e3 * t_bcast_first,
                                       "gather_frames": 1e3 * t_gather, "broadcast_frame_state": 1e3 * t_bcast_frame}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()

@@ -31,6 +31,24 @@ def shard_frames(num_frames: int, world: int, rank: int) -> range:
     return range(lo, hi)
 
 
+def warm_up(device, payload_floats: int = 1 << 20) -> None:
+    """Bring the communicator up before the first payload collective: NCCL connects channels lazily, per collective
+    and per message-size class, and the first frames.* call of a job otherwise pays for that (hundreds of ms at 8
+    ranks).  One barrier, one small and one payload-sized broadcast / all_gather, then the call patterns below once."""
+    dist.barrier()
+    small = torch.ones(1, device=device)
+    dist.all_reduce(small)
+    dist.broadcast(small, src=0)
+    big = torch.zeros(int(payload_floats), device=device)
+    dist.broadcast(big, src=0)
+    dist.all_gather([torch.empty_like(big) for _ in range(dist.get_world_size())], big)
+    tiny = {k: torch.zeros(8, w, device=device) for k, w in STATE_KEYS}
+    broadcast_state(tiny if dist.get_rank() == 0 else None, src=0, device=device)
+    gather_frames(torch.zeros(3, 8, 8, device=device), torch.zeros(3, 4, device=device), dst=0)
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
+
+
 def pack_state(state: Dict[str, torch.Tensor]) -> torch.Tensor:
     """(N,14) float32: xyz | scale | rotate | opacity | rgb (checkpoint attribute order of
     /root/reference/gflow/trainer.py:81-88)."""
