@@ -32,6 +32,7 @@ SIGNATURES = {
     "gfb_sort_workspace_bytes": (c_size_t, [L]),
     "gfb_sort_tile_workspace_bytes": (c_size_t, [I, I]),
     "gfb_sort_gaussian": (I, [P, P, P, P, I, I, I, P, L, P, P, P, P, P]),
+    "gfb_sort_gaussian_keep": (I, [P, P, P, P, I, I, I, P, L, P, P, P, P, P]),
     "gfb_render_control_bytes": (c_size_t, [I, I]),
     "gfb_render_control_k_offset": (c_size_t, [I, I]),
     "gfb_wait_k": (I, [P]),
@@ -50,6 +51,7 @@ SIGNATURES = {
     "gfb_blend_grad_pack_bytes": (c_size_t, [I]),
     "gfb_blend_pack_geometry": (I, [P, P, P, P, L, P, P]),
     "gfb_blend_pack_feature": (I, [P, I, I, I, P, L, P, P]),
+    "gfb_blend_pack_geometry_feature": (I, [P, P, P, P, I, I, I, P, L, P, P, P]),
     "gfb_alpha_blending_fwd": (I, [P, P, L, P, I, I, I, F, I, I, P, P, P, P]),
     "gfb_alpha_blending_bwd": (I, [P, P, L, P, P, I, I, I, F, I, I, P, P, P, P, P]),
     "gfb_blend_unpack_grads": (I, [P, I, I, I, I, P, P, P, P, I, P]),

@@ -199,6 +199,32 @@ pack_geometry_kernel(const float2* __restrict__ uv, const float* __restrict__ co
     sB[k] = make_float4(a, b, c, o);
 }
 
+// both streams in one launch: the first blend of a geometry (the later blends of render_multiple reuse the geometry
+// stream and pack only their own features)
+__global__ void __launch_bounds__(256)
+pack_geometry_feature_kernel(const float2* __restrict__ uv, const float* __restrict__ conic,
+                             const float* __restrict__ opacity, const float* __restrict__ feature, int C, int c0, int Cg,
+                             const int32_t* __restrict__ ids, long long K, float4* __restrict__ sA,
+                             float4* __restrict__ sB, float4* __restrict__ sF) {
+    const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (k >= K) return;
+    const int id = ids[k];
+    const float2 p = uv[id];
+    const float a = conic[3 * id], b = conic[3 * id + 1], c = conic[3 * id + 2];
+    const float o = opacity[id];
+    float hx, hy;
+    gfbm::splat_bbox(a, b, c, o, hx, hy);
+    sA[k] = gfb_pack_record_a(p.x, p.y, hx, hy, id);
+    sB[k] = make_float4(a, b, c, o);
+    const float* f = feature + (size_t)id * C + c0;
+    float4 r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    r.x = f[0];
+    if (Cg > 1) r.y = f[1];
+    if (Cg > 2) r.z = f[2];
+    if (Cg > 3) r.w = f[3];
+    sF[k] = r;
+}
+
 __global__ void __launch_bounds__(256)
 pack_feature_kernel(const float* __restrict__ feature, int C, int c0, int Cg, const int32_t* __restrict__ ids,
                     long long K, float4* __restrict__ sF) {
@@ -716,13 +742,17 @@ blend_bwd_kernel(const float4* __restrict__ gA, const float4* __restrict__ gB, c
 }
 
 __global__ void __launch_bounds__(256)
-unpack_grads_kernel(const float4* __restrict__ grad_pack, int N, int C, int c0, int Cg, float2* __restrict__ d_uv,
+unpack_grads_kernel(float4* __restrict__ grad_pack, int N, int C, int c0, int Cg, float2* __restrict__ d_uv,
                     float* __restrict__ d_conic, float* __restrict__ d_opacity, float* __restrict__ d_feature,
-                    int accumulate) {
+                    int flags) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
     const float4 g0 = grad_pack[3 * (size_t)i], g1 = grad_pack[3 * (size_t)i + 1], g2 = grad_pack[3 * (size_t)i + 2];
-    if (accumulate) {
+    if (flags & GFB_UNPACK_CLEAR) {  // a pack the caller keeps between calls goes back to zero here: no memset per call
+        const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        grad_pack[3 * (size_t)i] = z, grad_pack[3 * (size_t)i + 1] = z, grad_pack[3 * (size_t)i + 2] = z;
+    }
+    if (flags & GFB_UNPACK_ACCUMULATE) {
         float2 p = d_uv[i];
         p.x += g0.x;
         p.y += g0.y;
@@ -763,6 +793,20 @@ int gfb_blend_pack_geometry(const float* uv, const float* conic, const float* op
     float4* sB = sA + K;
     pack_geometry_kernel<<<gfb_div_up(K, 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float2*>(uv), conic, opacity, gaussian_ids_sorted, (long long)K, sA, sB);
+    GFB_CHECK_LAUNCH();
+    return 0;
+}
+
+int gfb_blend_pack_geometry_feature(const float* uv, const float* conic, const float* opacity, const float* feature,
+                                    int C, int c0, int Cg, const int32_t* gaussian_ids_sorted, int64_t K,
+                                    void* geom_stream, void* feat_stream, void* stream) {
+    if (K < 0 || C <= 0 || c0 < 0 || Cg < 1 || Cg > 4 || c0 + Cg > C) return GFB_E_BADARG;
+    if (K == 0) return 0;
+    if (!uv || !conic || !opacity || !feature || !gaussian_ids_sorted || !geom_stream || !feat_stream) return GFB_E_BADARG;
+    float4* sA = reinterpret_cast<float4*>(geom_stream);
+    pack_geometry_feature_kernel<<<gfb_div_up(K, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(uv), conic, opacity, feature, C, c0, Cg, gaussian_ids_sorted, (long long)K, sA,
+        sA + K, reinterpret_cast<float4*>(feat_stream));
     GFB_CHECK_LAUNCH();
     return 0;
 }
@@ -897,14 +941,14 @@ int gfb_internal_blend_bwd(const void* geom_stream, const void* feat_stream, int
 
 extern "C" {
 
-int gfb_blend_unpack_grads(const float* grad_pack, int N, int C, int c0, int Cg, float* d_uv, float* d_conic,
-                           float* d_opacity, float* d_feature, int accumulate, void* stream) {
+int gfb_blend_unpack_grads(float* grad_pack, int N, int C, int c0, int Cg, float* d_uv, float* d_conic,
+                           float* d_opacity, float* d_feature, int flags, void* stream) {
     if (N < 0 || C <= 0 || c0 < 0 || Cg < 1 || Cg > 4 || c0 + Cg > C) return GFB_E_BADARG;
     if (N == 0) return 0;
     if (!grad_pack || !d_uv || !d_conic || !d_opacity || !d_feature) return GFB_E_BADARG;
     unpack_grads_kernel<<<gfb_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(grad_pack), N, C, c0, Cg, reinterpret_cast<float2*>(d_uv), d_conic, d_opacity,
-        d_feature, accumulate);
+        reinterpret_cast<float4*>(grad_pack), N, C, c0, Cg, reinterpret_cast<float2*>(d_uv), d_conic, d_opacity,
+        d_feature, flags);
     GFB_CHECK_LAUNCH();
     return 0;
 }

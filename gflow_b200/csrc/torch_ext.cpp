@@ -83,6 +83,7 @@ struct ProjectPoint : public torch::autograd::Function<ProjectPoint> {
                                        (float)extent, fp(uv), fp(depth), stream()),
                  "project_point forward");
         ctx->save_for_backward({xyz, intr, extr});
+        ctx->set_materialize_grads(false);  // depth usually carries no gradient: no zero tensor is made up for it
         ctx->saved_data["W"] = W;
         ctx->saved_data["H"] = H;
         ctx->saved_data["nearest"] = nearest;
@@ -92,6 +93,7 @@ struct ProjectPoint : public torch::autograd::Function<ProjectPoint> {
     static variable_list backward(AutogradContext* ctx, variable_list g) {
         auto saved = ctx->get_saved_variables();
         const Tensor &xyz = saved[0], &intr = saved[1], &extr = saved[2];
+        if (!g[0].defined() && !g[1].defined()) return variable_list(7);
         c10::cuda::CUDAGuard guard(xyz.device());
         const int64_t N = xyz.size(0);
         Tensor g_uv = g[0].defined() ? prep(g[0], "grad uv") : at::zeros({N, 2}, f32(xyz));
@@ -120,11 +122,13 @@ struct ComputeCov3D : public torch::autograd::Function<ComputeCov3D> {
         check_rc(gfb_compute_cov3d_fwd(fp(scale), fp(rotate), vis_ptr(vis), (int)N, fp(cov), stream()),
                  "compute_cov3d forward");
         ctx->save_for_backward({scale, rotate, vis});
+        ctx->set_materialize_grads(false);
         return cov;
     }
     static variable_list backward(AutogradContext* ctx, variable_list g) {
         auto saved = ctx->get_saved_variables();
         const Tensor &scale = saved[0], &rotate = saved[1], &vis = saved[2];
+        if (!g[0].defined()) return variable_list(3);
         c10::cuda::CUDAGuard guard(scale.device());
         const int64_t N = scale.size(0);
         Tensor g_cov = prep(g[0], "grad cov3d");
@@ -160,11 +164,13 @@ struct EwaProject : public torch::autograd::Function<EwaProject> {
         ctx->saved_data["W"] = W;
         ctx->saved_data["H"] = H;
         ctx->mark_non_differentiable({radius, tiles});
+        ctx->set_materialize_grads(false);  // else the engine zero-fills int32 "gradients" for radius and tiles every step
         return {conic, radius, tiles};
     }
     static variable_list backward(AutogradContext* ctx, variable_list g) {
         auto s = ctx->get_saved_variables();
         const Tensor& xyz = s[0];
+        if (!g[0].defined()) return variable_list(8);
         c10::cuda::CUDAGuard guard(xyz.device());
         const int64_t N = xyz.size(0);
         Tensor g_conic = prep(g[0], "grad conic");
@@ -202,6 +208,12 @@ void clear_k_hints() {
     g_hint.clear();
 }
 
+Tensor kept_block(int kind, const Tensor& like, void* st, int64_t size_key, int64_t nbytes);
+void drop_kept(int kind, const Tensor& like, void* st, int64_t size_key);
+// A kept block is shared by every call on its (device, stream): the kernels of one call must reach the stream as
+// one uninterrupted run, also when several host threads issue work on that stream.
+std::mutex g_keep_enqueue;
+
 // ------------------------------------------------------------------ sort_gaussian
 std::tuple<Tensor, Tensor> sort_gaussian(const Tensor& uv_, const Tensor& depth_, int64_t W, int64_t H,
                                          const Tensor& radius_, const Tensor& tiles_) {
@@ -217,15 +229,21 @@ std::tuple<Tensor, Tensor> sort_gaussian(const Tensor& uv_, const Tensor& depth_
     c10::cuda::CUDAGuard guard(uv.device());
     const int dev = uv.device().index();
     const int64_t T = ((W + 15) / 16) * ((H + 15) / 16);
-    Tensor tile_ws = at::empty({(int64_t)gfb_sort_tile_workspace_bytes((int)W, (int)H)}, uv.options().dtype(at::kByte));
     Tensor tile_range = at::empty({T, 2}, i32(uv));
     int64_t cap = capacity_for(dev, N, W, H), K = 0;
     Tensor ids;
+    void* st = stream();
+    // tile counters: a block kept per (device, stream, W x H), zeroed once; the kernels hand it back clean
+    const int64_t ws_key = W * 65536 + H;
+    Tensor tile_ws = kept_block(3, uv, st, ws_key, (int64_t)gfb_sort_tile_workspace_bytes((int)W, (int)H));
     for (;;) {
         Tensor keys = at::empty({std::max<int64_t>(cap, 1)}, uv.options().dtype(at::kLong));
         ids = at::empty({std::max<int64_t>(cap, 1)}, i32(uv));
-        int rc = gfb_sort_gaussian(fp(uv), fp(depth), ip(radius), ip(tiles), (int)N, (int)W, (int)H, tile_ws.data_ptr(), cap,
-                                   keys.data_ptr(), ip(ids), ip(tile_range), &K, stream());
+        std::unique_lock<std::mutex> run(g_keep_enqueue);
+        int rc = gfb_sort_gaussian_keep(fp(uv), fp(depth), ip(radius), ip(tiles), (int)N, (int)W, (int)H, tile_ws.data_ptr(),
+                                        cap, keys.data_ptr(), ip(ids), ip(tile_range), &K, st);
+        if (rc != 0 && rc != GFB_E_CAPACITY) drop_kept(3, uv, st, ws_key);
+        run.unlock();
         if (rc == GFB_E_CAPACITY) {
             cap = K + K / 8 + 1024;
             continue;
@@ -248,8 +266,10 @@ struct GeomCache {
 } g_geom;
 std::mutex g_geom_mutex;
 
+// feat0 != nullptr: on a miss the first channel group's feature stream is packed by the same launch (*packed0 = true)
 Tensor geometry_stream(const Tensor& uv_in, const Tensor& conic_in, const Tensor& op_in, const Tensor& ids_in,
-                       const Tensor& uv, const Tensor& conic, const Tensor& op, const Tensor& ids, int64_t K) {
+                       const Tensor& uv, const Tensor& conic, const Tensor& op, const Tensor& ids, int64_t K,
+                       const Tensor& feature, float* feat0, bool* packed0) {
     std::lock_guard<std::mutex> lock(g_geom_mutex);
     const Tensor* in[4] = {&uv_in, &conic_in, &op_in, &ids_in};
     bool hit = g_geom.stream_buf.defined();
@@ -257,8 +277,16 @@ Tensor geometry_stream(const Tensor& uv_in, const Tensor& conic_in, const Tensor
         hit = g_geom.impl[i] == in[i]->unsafeGetTensorImpl() && g_geom.ver[i] == in[i]->_version();
     if (hit) return g_geom.stream_buf;
     Tensor buf = at::empty({std::max<int64_t>(K, 1) * 8}, f32(uv));
-    check_rc(gfb_blend_pack_geometry(fp(uv), fp(conic), fp(op), ip(ids), K, buf.data_ptr(), stream()),
-             "blend pack geometry");
+    if (feat0) {
+        const int C = (int)feature.size(1);
+        check_rc(gfb_blend_pack_geometry_feature(fp(uv), fp(conic), fp(op), fp(feature), C, 0, std::min(4, C), ip(ids), K,
+                                                 buf.data_ptr(), feat0, stream()),
+                 "blend pack geometry + feature");
+        *packed0 = true;
+    } else {
+        check_rc(gfb_blend_pack_geometry(fp(uv), fp(conic), fp(op), ip(ids), K, buf.data_ptr(), stream()),
+                 "blend pack geometry");
+    }
     for (int i = 0; i < 4; ++i) {
         g_geom.impl[i] = in[i]->unsafeGetTensorImpl();
         g_geom.ver[i] = in[i]->_version();
@@ -289,22 +317,25 @@ struct AlphaBlending : public torch::autograd::Function<AlphaBlending> {
         check_shape(range, "tile_range", {T, 2});
         c10::cuda::CUDAGuard guard(uv.device());
         const int64_t K = ids.numel();
-        Tensor geom = geometry_stream(uv_, conic_, opacity_, ids_, uv, conic, opacity, ids, K);
+        const int64_t groups = (C + 3) / 4;
+        Tensor feats = at::empty({groups, std::max<int64_t>(K, 1) * 4}, f32(uv));
+        bool packed0 = false;
+        Tensor geom = geometry_stream(uv_, conic_, opacity_, ids_, uv, conic, opacity, ids, K, feature, fp(feats), &packed0);
         Tensor out = at::empty({C, H, W}, f32(uv));
         Tensor aux = at::empty({2, H, W}, f32(uv));  // final_T | n_contrib (int32 bits)
         float* final_T = fp(aux);
         int32_t* n_contrib = reinterpret_cast<int32_t*>(final_T + H * W);
-        const int64_t groups = (C + 3) / 4;
-        Tensor feats = at::empty({groups, std::max<int64_t>(K, 1) * 4}, f32(uv));
         for (int64_t gi = 0; gi < groups; ++gi) {
             const int c0 = (int)(gi * 4), cg = (int)std::min<int64_t>(4, C - c0);
             float* fs = fp(feats) + gi * feats.size(1);
-            check_rc(gfb_blend_pack_feature(fp(feature), (int)C, c0, cg, ip(ids), K, fs, stream()), "blend pack feature");
+            if (gi > 0 || !packed0)
+                check_rc(gfb_blend_pack_feature(fp(feature), (int)C, c0, cg, ip(ids), K, fs, stream()), "blend pack feature");
             check_rc(gfb_alpha_blending_fwd(geom.data_ptr(), fs, K, ip(range), (int)C, c0, cg, (float)bg, (int)W, (int)H,
                                             fp(out), final_T, n_contrib, stream()),
                      "alpha_blending forward");
         }
         ctx->save_for_backward({geom, feats, ids, range, aux});
+        ctx->set_materialize_grads(false);
         ctx->saved_data["N"] = N;
         ctx->saved_data["C"] = C;
         ctx->saved_data["bg"] = bg;
@@ -319,25 +350,32 @@ struct AlphaBlending : public torch::autograd::Function<AlphaBlending> {
         const int64_t N = ctx->saved_data["N"].toInt(), C = ctx->saved_data["C"].toInt();
         const int64_t W = ctx->saved_data["W"].toInt(), H = ctx->saved_data["H"].toInt();
         const float bg = (float)ctx->saved_data["bg"].toDouble();
+        if (!g[0].defined()) return variable_list(10);
         c10::cuda::CUDAGuard guard(geom.device());
         Tensor g_out = prep(g[0], "grad feature_map");
         check_shape(g_out, "grad feature_map", {C, H, W});
         const int64_t K = ids.numel();
-        Tensor d_uv = at::empty({N, 2}, f32(geom)), d_conic = at::empty({N, 3}, f32(geom)),
-               d_opacity = at::empty({N, 1}, f32(geom)), d_feature = at::empty({N, C}, f32(geom));
+        Tensor dall = at::empty({(6 + C) * N}, f32(geom));  // one allocation: d_uv | d_conic | d_opacity | d_feature
+        Tensor d_uv = dall.narrow(0, 0, 2 * N).view({N, 2}), d_conic = dall.narrow(0, 2 * N, 3 * N).view({N, 3}),
+               d_opacity = dall.narrow(0, 5 * N, N).view({N, 1}), d_feature = dall.narrow(0, 6 * N, C * N).view({N, C});
         const float* final_T = fp(aux);
         const int32_t* n_contrib = reinterpret_cast<const int32_t*>(final_T + H * W);
         const int64_t groups = (C + 3) / 4;
+        // the gradient pack is a block kept per (device, stream, N): zeroed once, the unpack kernel hands it back clean
+        void* st = stream();
+        Tensor pack = kept_block(2, geom, st, N, 48 * std::max<int64_t>(N, 1));
+        std::lock_guard<std::mutex> run(g_keep_enqueue);
         for (int64_t gi = 0; gi < groups; ++gi) {
             const int c0 = (int)(gi * 4), cg = (int)std::min<int64_t>(4, C - c0);
-            Tensor pack = at::zeros({std::max<int64_t>(N, 1) * 12}, f32(geom));
             const float* fs = fp(feats) + gi * feats.size(1);
-            check_rc(gfb_alpha_blending_bwd(geom.data_ptr(), fs, K, ip(ids), ip(range), (int)C, c0, cg, bg, (int)W, (int)H,
-                                            final_T, n_contrib, fp(g_out), fp(pack), stream()),
-                     "alpha_blending backward");
-            check_rc(gfb_blend_unpack_grads(fp(pack), (int)N, (int)C, c0, cg, fp(d_uv), fp(d_conic), fp(d_opacity),
-                                            fp(d_feature), gi > 0 ? 1 : 0, stream()),
-                     "alpha_blending unpack grads");
+            int rc = gfb_alpha_blending_bwd(geom.data_ptr(), fs, K, ip(ids), ip(range), (int)C, c0, cg, bg, (int)W, (int)H,
+                                            final_T, n_contrib, fp(g_out), (float*)pack.data_ptr(), st);
+            if (rc == 0)
+                rc = gfb_blend_unpack_grads((float*)pack.data_ptr(), (int)N, (int)C, c0, cg, fp(d_uv), fp(d_conic),
+                                            fp(d_opacity), fp(d_feature),
+                                            GFB_UNPACK_CLEAR | (gi > 0 ? GFB_UNPACK_ACCUMULATE : 0), st);
+            if (rc != 0) drop_kept(2, geom, st, N);  // may be dirty
+            check_rc(rc, "alpha_blending backward");
         }
         Tensor d_ndc = ctx->saved_data["ndc"].toBool() ? d_uv.clone() : Tensor();
         return {d_uv, d_conic, d_opacity, d_feature, Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), d_ndc};
@@ -453,12 +491,14 @@ RasterForward raster_forward(const Tensor& xyz, const Tensor& scale, const Tenso
     for (;;) {
         r.kbuf = at::empty({15 * std::max<int64_t>(cap, 1)}, f32(xyz));
         char* kp = (char*)r.kbuf.data_ptr();
+        std::unique_lock<std::mutex> run(g_keep_enqueue);
         const int rc = gfb_render_forward_keep(
             fp(xyz), fp(scale), fp(rotate), fp(opacity), fp(feature), (int)C, fp(intr), fp(extr), (int)N, (int)W, (int)H,
             (float)bg, (float)nearest, (float)extent, (float*)sp, (float*)(sp + L.o_depth), (float*)(sp + L.o_conic),
             (int32_t*)(sp + L.o_radius), sp + L.o_rect, ctl.data_ptr(), (int32_t*)(sp + L.o_rng), cap, kp + 48 * cap,
             (int32_t*)(kp + 56 * cap), kp, kp + 32 * cap, fp(out), (float*)(sp + L.o_ft), (int32_t*)(sp + L.o_nc), nullptr, st);
         if (rc != 0) drop_kept(0, xyz, st, ctl_key);
+        run.unlock();
         check_rc(rc, "rasterization forward");
         r.cap = cap;
         r.ticket = gfb_k_ticket();
@@ -563,12 +603,14 @@ struct Rasterize : public torch::autograd::Function<Rasterize> {
         float* dp = fp(dbuf);
         void* st = stream();
         Tensor pack = kept_block(1, xyz, st, N, 48 * std::max<int64_t>(N, 1));
+        std::unique_lock<std::mutex> run(g_keep_enqueue);
         const int rc_b = gfb_render_backward_keep(
             fp(xyz), fp(scale), fp(rotate), fp(intr), fp(extr), (int)N, (int)W, (int)H, (int)C, (float)bg, (float)nearest,
             (float)extent, (int32_t*)(kp + 56 * cap), (int32_t*)(sp + L.o_rng), cap, kp, kp + 32 * cap, (float*)(sp + L.o_ft),
             (int32_t*)(sp + L.o_nc), fp(g_out), pack.data_ptr(), fp(grad_ws), dp + 4 * N, dp + 7 * N, dp, dp + 10 * N,
             dp + 11 * N, st);
         if (rc_b != 0) drop_kept(1, xyz, st, N);
+        run.unlock();
         check_rc(rc_b, "rasterization backward");
         Tensor d_rotate = dbuf.narrow(0, 0, 4 * N).view({N, 4});
         Tensor d_xyz = dbuf.narrow(0, 4 * N, 3 * N).view({N, 3});

@@ -19,6 +19,8 @@ memory, streams, autograd graph).  There is no CPU path: CPU tensors raise Runti
 """
 from __future__ import annotations
 
+import threading
+
 import torch
 
 from . import capi
@@ -498,6 +500,8 @@ _CLIPPED_WARNING = ("gflow_b200.rasterization: the intersection count grew by mo
 # the backward return to all-zero by themselves (gfb_render_forward_keep / gfb_render_backward_keep), so a render step
 # launches no memset.  A failed call drops them (they may be dirty).
 _KEPT = {}
+# ctypes releases the GIL inside a call: the kernels of one call on a kept block must reach the stream as one run
+_KEEP_LOCK = threading.Lock()
 
 
 def _kept(kind, dev, stream, size_key, nbytes):
@@ -528,14 +532,15 @@ def _raster_forward(xyz_c, scale_c, rotate_c, opacity_c, feature_c, intr_c, extr
         # K-sized buffer (bytes): geom 32c | feat 16c | keys 8c | ids 4c
         kbuf = torch.empty(15 * max(cap, 1), device=dev, dtype=torch.float32)
         kp = kbuf.data_ptr()
-        rc = _lib.gfb_render_forward_keep(
-            xyz_c.data_ptr(), scale_c.data_ptr(), rotate_c.data_ptr(), opacity_c.data_ptr(),
-            feature_c.data_ptr(), C, intr_c.data_ptr(), extr_c.data_ptr(), N, W, H, bg, nearest, extent,
-            p_uv, p_depth, p_conic, p_radius, p_rect, ctl.data_ptr(), tbuf.data_ptr(), cap, kp + 48 * cap, kp + 56 * cap,
-            kp, kp + 32 * cap, out.data_ptr(), aux.data_ptr(), aux.data_ptr() + 4 * H * W,
-            None, st)
-        if rc != 0:
-            _KEPT.pop(ckey, None)
+        with _KEEP_LOCK:
+            rc = _lib.gfb_render_forward_keep(
+                xyz_c.data_ptr(), scale_c.data_ptr(), rotate_c.data_ptr(), opacity_c.data_ptr(),
+                feature_c.data_ptr(), C, intr_c.data_ptr(), extr_c.data_ptr(), N, W, H, bg, nearest, extent,
+                p_uv, p_depth, p_conic, p_radius, p_rect, ctl.data_ptr(), tbuf.data_ptr(), cap, kp + 48 * cap, kp + 56 * cap,
+                kp, kp + 32 * cap, out.data_ptr(), aux.data_ptr(), aux.data_ptr() + 4 * H * W,
+                None, st)
+            if rc != 0:
+                _KEPT.pop(ckey, None)
         capi.check(rc, "rasterization forward")
         ticket = int(_lib.gfb_k_ticket())
         if lazy:
@@ -625,13 +630,14 @@ class _Rasterize(torch.autograd.Function):
             kp, tp = kbuf.data_ptr(), tbuf.data_ptr()
             st = _stream()
             pkey, pack = _kept("grad_pack", dev, st, N, 48 * max(N, 1))
-            rc = _lib.gfb_render_backward_keep(
-                xyz.data_ptr(), scale.data_ptr(), rotate.data_ptr(), intr.data_ptr(), extr.data_ptr(), N, W, H, C, bg,
-                nearest, extent, kp + 56 * cap, tp, cap, kp, kp + 32 * cap, aux.data_ptr(),
-                aux.data_ptr() + 4 * H * W, g_out.data_ptr(), pack.data_ptr(), d_cam.data_ptr(), dp + 16 * N, dp + 28 * N, dp,
-                dp + 40 * N, dp + 44 * N, st)
-            if rc != 0:
-                _KEPT.pop(pkey, None)
+            with _KEEP_LOCK:
+                rc = _lib.gfb_render_backward_keep(
+                    xyz.data_ptr(), scale.data_ptr(), rotate.data_ptr(), intr.data_ptr(), extr.data_ptr(), N, W, H, C, bg,
+                    nearest, extent, kp + 56 * cap, tp, cap, kp, kp + 32 * cap, aux.data_ptr(),
+                    aux.data_ptr() + 4 * H * W, g_out.data_ptr(), pack.data_ptr(), d_cam.data_ptr(), dp + 16 * N, dp + 28 * N,
+                    dp, dp + 40 * N, dp + 44 * N, st)
+                if rc != 0:
+                    _KEPT.pop(pkey, None)
             capi.check(rc, "rasterization backward")
         d_rotate = dbuf[:4 * N].view(N, 4)
         d_xyz = dbuf[4 * N:7 * N].view(N, 3)

@@ -94,6 +94,12 @@ size_t gfb_sort_tile_workspace_bytes(int W, int H);
 int gfb_sort_gaussian(const float *uv, const float *depth, const int32_t *radius, const int32_t *tiles_touched, int N,
                       int W, int H, void *tile_ws, int64_t capacity, void *keys_ws, int32_t *gaussian_ids_sorted,
                       int32_t *tile_range, int64_t *K_host, void *stream);
+/* Same, for a caller that keeps tile_ws between calls on one stream: zero the block once; the part the kernels rely
+ * on (tile counters + ticket) is zero again when the call's kernels have run, so no memset is enqueued per call.
+ * After a failed call (other than GFB_E_CAPACITY) the block may be dirty: zero it again. */
+int gfb_sort_gaussian_keep(const float *uv, const float *depth, const int32_t *radius, const int32_t *tiles_touched,
+                           int N, int W, int H, void *tile_ws_keep, int64_t capacity, void *keys_ws,
+                           int32_t *gaussian_ids_sorted, int32_t *tile_range, int64_t *K_host, void *stream);
 
 /* ------------------------------------------------------------------ msplat.alpha_blending
  * call sites: render.py:58-64,68-74,84-90,99-105,148-154; backward via trainer.py:533.
@@ -112,6 +118,10 @@ int gfb_blend_pack_geometry(const float *uv, const float *conic, const float *op
                             const int32_t *gaussian_ids_sorted, int64_t K, void *geom_stream, void *stream);
 int gfb_blend_pack_feature(const float *feature, int C, int c0, int Cg, const int32_t *gaussian_ids_sorted, int64_t K,
                            void *feat_stream, void *stream);
+/* Both streams in one launch (the first blend of a geometry; bit-identical to the two calls above). */
+int gfb_blend_pack_geometry_feature(const float *uv, const float *conic, const float *opacity, const float *feature,
+                                    int C, int c0, int Cg, const int32_t *gaussian_ids_sorted, int64_t K,
+                                    void *geom_stream, void *feat_stream, void *stream);
 /* out is (C,H,W); this call writes channels [c0, c0+Cg).  final_T (H,W) float and
  * n_contrib (H,W) int32 are saved for the backward pass. */
 int gfb_alpha_blending_fwd(const void *geom_stream, const void *feat_stream, int64_t K, const int32_t *tile_range,
@@ -126,10 +136,14 @@ int gfb_alpha_blending_bwd(const void *geom_stream, const void *feat_stream, int
                            const float *final_T, const int32_t *n_contrib, const float *g_out, float *grad_pack,
                            void *stream);
 /* Scatter grad_pack into msplat-shaped gradients.  Feature slots go to
- * d_feature[:, c0:c0+Cg] (row stride C).  accumulate == 0 overwrites d_uv / d_conic /
- * d_opacity, != 0 adds to them (second and later channel groups). */
-int gfb_blend_unpack_grads(const float *grad_pack, int N, int C, int c0, int Cg, float *d_uv, float *d_conic,
-                           float *d_opacity, float *d_feature, int accumulate, void *stream);
+ * d_feature[:, c0:c0+Cg] (row stride C).  flags: GFB_UNPACK_ACCUMULATE adds to d_uv / d_conic /
+ * d_opacity instead of overwriting them (second and later channel groups); GFB_UNPACK_CLEAR writes
+ * zeros back into grad_pack after reading it, so a pack the caller keeps between calls needs no
+ * memset of its own. */
+#define GFB_UNPACK_ACCUMULATE 1
+#define GFB_UNPACK_CLEAR 2
+int gfb_blend_unpack_grads(float *grad_pack, int N, int C, int c0, int Cg, float *d_uv, float *d_conic,
+                           float *d_opacity, float *d_feature, int flags, void *stream);
 
 /* ------------------------------------------------------------------ msplat.rasterization (fused)
  * The whole chain of render.py:21-64 for callers that only need the image: 4 forward kernels

@@ -87,22 +87,36 @@ def operator_chain(sc, Gimg, C=3, feature=None):
     ok(L.gfb_sort_gaussian(p(uv), p(depth), p(radius), p(tiles), N, W, H, p(tile_ws), cap, p(keys), p(ids), p(rng),
                            ctypes.addressof(K), None), "sort")
     K = int(K.value)
+    # the kept-workspace variant: zero block in, same result, zero block out
+    tile_ws.zero_()
+    ids_k, rng_k, K_k = i32(cap), i32(T, 2), ctypes.c_int64(-1)
+    ok(L.gfb_sort_gaussian_keep(p(uv), p(depth), p(radius), p(tiles), N, W, H, p(tile_ws), cap, p(keys), p(ids_k),
+                                p(rng_k), ctypes.addressof(K_k), None), "sort (kept workspace)")
+    assert int(K_k.value) == K and torch.equal(ids_k[:K], ids[:K]) and torch.equal(rng_k, rng)
+    n_clean = (tile_ws.numel() // 4 - 2) // 2 + 1  # counters[T R] | ticket; the offsets behind them are plain outputs
+    assert not tile_ws.view(torch.int32)[:n_clean].any(), "gfb_sort_gaussian_keep left its counters dirty"
     ids = ids[:K].contiguous()
     geom = torch.zeros(max(K, 1) * 8, dtype=torch.float32)
     out, fT, nc = f32(C, H, W), f32(H, W), i32(H, W)
     ok(L.gfb_blend_pack_geometry(p(uv), p(conic), p(op), p(ids), K, p(geom), None), "pack geometry")
     d_uv, d_conic, d_op, d_feat = f32(N, 2), f32(N, 3), f32(N, 1), f32(N, C)
+    gp = torch.zeros(N * 12, dtype=torch.float32)  # kept over the channel groups: GFB_UNPACK_CLEAR (2) hands it back zeroed
     for gi, c0 in enumerate(range(0, C, 4)):
         cg = min(4, C - c0)
         feat = torch.zeros(max(K, 1) * 4, dtype=torch.float32)
         ok(L.gfb_blend_pack_feature(p(feature.contiguous()), C, c0, cg, p(ids), K, p(feat), None), "pack feature")
+        if gi == 0:  # the one-launch variant writes the same two streams
+            geom2, feat2 = torch.zeros_like(geom), torch.zeros_like(feat)
+            ok(L.gfb_blend_pack_geometry_feature(p(uv), p(conic), p(op), p(feature.contiguous()), C, 0, cg, p(ids), K,
+                                                 p(geom2), p(feat2), None), "pack geometry + feature")
+            assert torch.equal(geom2.view(torch.int32), geom.view(torch.int32)) and torch.equal(feat2, feat)
         ok(L.gfb_alpha_blending_fwd(p(geom), p(feat), K, p(rng), C, c0, cg, sc.bg, W, H, p(out), p(fT), p(nc), None),
            "blend fwd")
-        gp = torch.zeros(N * 12, dtype=torch.float32)
         ok(L.gfb_alpha_blending_bwd(p(geom), p(feat), K, p(ids), p(rng), C, c0, cg, sc.bg, W, H, p(fT), p(nc),
                                     p(Gimg.contiguous()), p(gp), None), "blend bwd")
-        ok(L.gfb_blend_unpack_grads(p(gp), N, C, c0, cg, p(d_uv), p(d_conic), p(d_op), p(d_feat), int(gi > 0), None),
+        ok(L.gfb_blend_unpack_grads(p(gp), N, C, c0, cg, p(d_uv), p(d_conic), p(d_op), p(d_feat), 2 | int(gi > 0), None),
            "unpack")
+        assert not gp.any(), "gfb_blend_unpack_grads(GFB_UNPACK_CLEAR) left the gradient pack dirty"
     d_xyz_e, d_cov, d_cam_e = f32(N, 3), f32(N, 6), f32(16)
     ok(L.gfb_ewa_project_bwd(p(xyz), p(cov), p(intr), p(extr), p(uv), N, W, H, p(vis), p(d_conic), p(d_xyz_e), p(d_cov),
                              p(d_cam_e), None), "ewa bwd")

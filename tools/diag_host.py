@@ -50,3 +50,25 @@ class Nop(torch.autograd.Function):
         return tuple(torch.empty_like(p) for p in ps) + (None, torch.empty_like(extr))
 def nop(*a): return Nop.apply(*a[:7])
 measure("python no-op Function (autograd floor)", lambda *a: nop(*a))
+
+# ---- per-operator host time of the chain's forward (queue kept shallow)
+def per_op(reps=200):
+    names = ["project_point", "depth != 0", "compute_cov3d", "ewa_project", "sort_gaussian", "alpha_blending"]
+    acc = {n: [] for n in names}
+    xyz, scale, rot, op, rgb = ps
+    for i in range(reps + 20):
+        t = [time.perf_counter()]
+        uv, depth = G.project_point(xyz, intr, extr, W, H); t.append(time.perf_counter())
+        vis = depth != 0; t.append(time.perf_counter())
+        cov = G.compute_cov3d(scale, rot, vis); t.append(time.perf_counter())
+        conic, radius, tiles = G.ewa_project(xyz, cov, intr, extr, uv, W, H, vis); t.append(time.perf_counter())
+        ids, rng = G.sort_gaussian(uv, depth, W, H, radius, tiles); t.append(time.perf_counter())
+        img = G.alpha_blending(uv, conic, op, rgb, ids, rng, 0.0, W, H); t.append(time.perf_counter())
+        if i % 4 == 3: torch.cuda.synchronize()
+        if i >= 20:
+            for n, a, b in zip(names, t[:-1], t[1:]): acc[n].append(b - a)
+    print("chain forward, host us per operator: " + "  ".join(f"{n} {statistics.median(v)*1e6:.1f}" for n, v in acc.items()))
+per_op()
+with torch.no_grad():
+    print("(no_grad)", end=" ")
+    per_op()
