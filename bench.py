@@ -55,6 +55,7 @@ UNIT = "iters/s"
 WORKLOADS = {"cfg1": (1_000, 256, 256), "cfg2": (60_000, 854, 480), "cfg5": (200_000, 1280, 720)}
 BLOCKS = 10
 SEQ_FRAMES, SEQ_ITERS = 48, 300
+SEQ_CONCURRENT = 3  # independent frames a rank fits side by side (one stream each): 48 / N frames per rank divide evenly
 
 
 def parse_args():
@@ -72,6 +73,7 @@ def parse_args():
     ap.add_argument("--no-sequence", action="store_true", help="skip the config-4 frame-sharded sequence section")
     ap.add_argument("--no-proxy", action="store_true", help="skip the eager-PyTorch-on-CUDA proxy baseline")
     ap.add_argument("--quick", action="store_true", help="value / e2e / roofline only")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="steps in flight in the e2e leg (HostRenderStep depth)")
     return ap.parse_args()
 
 
@@ -391,12 +393,13 @@ def run_ours(args):
     for t in [p.detach() for p in params] + [intr, extr]:
         host_in[o:o + t.numel()].copy_(t.reshape(-1).cpu())
         o += t.numel()
-    host = hostapi.HostRenderStep(N, W, H, tuple(params[4].shape[1:]), Gimg, sc.bg, dev, depth=2,
+    host = hostapi.HostRenderStep(N, W, H, tuple(params[4].shape[1:]), Gimg, sc.bg, dev, depth=args.e2e_depth,
                                   colour=sh_colour if use_sh else None, sample_input=host_in)
-    host_outs = [host.host_output_block() for _ in range(2)]
+    n_slot = max(1, args.e2e_depth)
+    host_outs = [host.host_output_block() for _ in range(n_slot)]
     n_e2e = max(5, min(args.steps, 50))
     for i in range(3):
-        host.submit(host_in, host_outs[i % 2])
+        host.submit(host_in, host_outs[i % n_slot])
     host.wait()
     e2e_blocks = []
     for _ in range(max(1, min(args.blocks, 5))):
@@ -405,7 +408,7 @@ def run_ours(args):
         flush_l2()
         a.record()
         for i in range(n_e2e):
-            host.submit(host_in, host_outs[i % 2])
+            host.submit(host_in, host_outs[i % n_slot])
         host.wait()          # every D2H has landed
         b.record()
         barrier()
@@ -417,7 +420,27 @@ def run_ours(args):
         e2e_blocks.append(t)
     host.check()
     e2e_value = world * n_e2e / (statistics.median(e2e_blocks) / 1e3)
-    e2e_loss = float(host.unpack_output(host_outs[(n_e2e - 1) % 2])["loss"][0])
+    # the same copies with no kernels between them (both directions at once, as in the step): the link's own ceiling
+    cur = torch.cuda.current_stream(dev)
+    link_ms = []
+    for _ in range(3):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        host.h2d_stream.wait_stream(cur)
+        host.d2h_stream.wait_stream(cur)
+        for i in range(n_e2e):
+            with torch.cuda.stream(host.h2d_stream):
+                host.slots[i % n_slot]["dev_in"].copy_(host_in, non_blocking=True)
+            with torch.cuda.stream(host.d2h_stream):
+                host_outs[i % n_slot].copy_(host.slots[i % n_slot]["dev_out"], non_blocking=True)
+        cur.wait_stream(host.h2d_stream)
+        cur.wait_stream(host.d2h_stream)
+        b.record()
+        barrier()
+        link_ms.append(a.elapsed_time(b) / n_e2e)
+    link_ms = statistics.median(link_ms)
+    e2e_loss = float(host.unpack_output(host_outs[(n_e2e - 1) % n_slot])["loss"][0])
 
     # ---- roofline of the dominant kernel (alpha-blending backward), timed alone with CUDA events
     roof = kernel_roofline(G, lib, params, intr, extr, Gimg, sc.bg, N, W, H, T, P, flush_l2, dev, clocks,
@@ -490,8 +513,13 @@ def run_ours(args):
                        "api": f"msplat.rasterization (gflow_b200.ops, fused pipeline, {G.BACKEND} binding) -> C ABI",
                        "timing": f"median of {max(1, args.blocks)} blocks of {args.steps} steps, max over ranks per block"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
-                    "steps": n_e2e, "api": "gflow_b200.hostapi.HostRenderStep (pinned host blocks, copy stream, 2 steps in flight, compute as "
-                           + ("one CUDA graph per slot)" if host.graphed else "eager autograd: SH colour)"),
+                    "steps": n_e2e, "copies_alone_ms_per_step": link_ms,
+                    "copies_alone_GBps_per_direction": max(host.h2d_bytes, host.d2h_bytes) / (link_ms * 1e6),
+                    "steps_in_flight": n_slot,
+                    "api": f"gflow_b200.hostapi.HostRenderStep (pinned host blocks, one copy stream per direction, {n_slot} "
+                           "independent steps in flight, compute as "
+                           + ("one CUDA graph per slot on the slot's own stream, one library call per step)" if host.graphed
+                              else "eager autograd: SH colour)"),
                     "loss_read_back": e2e_loss},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
@@ -606,7 +634,8 @@ def sequence_section(dist, world, rank, dev):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    results, gathered = fit.fit_sequence_sharded(raw_dev if rank == 0 or dist is None else None, sc.intr, targets, W, H, cfg, dev)
+    results, gathered = fit.fit_sequence_sharded(raw_dev if rank == 0 or dist is None else None, sc.intr, targets, W, H, cfg, dev,
+                                                 concurrent_frames=SEQ_CONCURRENT)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if dist is not None:
@@ -616,10 +645,12 @@ def sequence_section(dist, world, rank, dev):
     first = results[min(results)]
     per_rank = (SEQ_FRAMES + world - 1) // world
     return {"what": f"BASELINE config 4: {SEQ_FRAMES} synthetic frames x {SEQ_ITERS} native Adam iterations (60k Gaussians, "
-                    "854x480, mse + depth loss), frames sharded across the ranks; wall clock incl. the state broadcast "
-                    "and the gather of per-frame outputs, max over ranks",
+                    "854x480, mse + depth loss), frames sharded across the ranks, each rank working on "
+                    f"{SEQ_CONCURRENT} of its (independent) frames at a time on separate streams; wall clock incl. the state "
+                    "broadcast and the gather of per-frame outputs, max over ranks",
             "value": SEQ_FRAMES * SEQ_ITERS / dt, "unit": "frame-iterations/s", "seconds": dt, "frames": SEQ_FRAMES,
             "iterations_per_frame": SEQ_ITERS, "frames_per_rank": per_rank, "n_gpus": world,
+            "concurrent_frames_per_gpu": SEQ_CONCURRENT,
             "loss_first": first.losses[0], "loss_last": first.losses[-1]}
 
 

@@ -23,7 +23,7 @@ COMMON_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxa
 # geometry.cu must not fuse multiply-adds: its float32 results are bit-compared with the oracle
 PER_FILE_FLAGS = {"geometry.cu": ["-fmad=false"], "binning.cu": ["-fmad=false"], "pipeline.cu": ["-fmad=false"],
                   "fit.cu": ["-fmad=false"], "densify.cu": ["-fmad=false"]}
-SOURCES = ["capi.cu", "geometry.cu", "binning.cu", "blend.cu", "pipeline.cu", "fit.cu", "densify.cu"]
+SOURCES = ["capi.cu", "geometry.cu", "binning.cu", "blend.cu", "pipeline.cu", "fit.cu", "densify.cu", "hostpipe.cu"]
 
 
 def _nvcc() -> str:

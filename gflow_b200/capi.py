@@ -63,6 +63,10 @@ SIGNATURES = {
     "gfb_densify_workspace_bytes": (c_size_t, [I, I]),
     "gfb_densify_prepare": (I, [P, P, I, I, F, P, P]),
     "gfb_densify_sample": (I, [P, P, P, P, P, I, I, I, I, ctypes.c_uint64, P, P, P, P, P, P, P]),
+    "gfb_hostpipe_create": (I, [I, P]),
+    "gfb_hostpipe_submit": (I, [P, I, P, P, c_size_t, P, P, P, P, c_size_t]),
+    "gfb_hostpipe_wait": (I, [P]),
+    "gfb_hostpipe_destroy": (I, [P]),
 }
 
 

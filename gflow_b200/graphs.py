@@ -24,11 +24,13 @@ from . import capi, ops
 class GraphedRenderStep:
     def __init__(self, xyz, scale, rotate, opacity, feature, intr, extr, W: int, H: int, bg: float = 0.0,
                  capacity: Optional[int] = None, nearest: float = 0.2, extent: float = 1.3, backward: bool = True,
-                 adopt_inputs: bool = False, capture: bool = True, grad_buffer: Optional[torch.Tensor] = None):
+                 adopt_inputs: bool = False, capture: bool = True, grad_buffer: Optional[torch.Tensor] = None,
+                 cam_buffer: Optional[torch.Tensor] = None):
         """adopt_inputs: use the given tensors themselves as the static inputs (they must be contiguous float32 CUDA
         tensors that stay alive) instead of cloning them.  capture=False: build the buffers only; the caller captures
         `enqueue()` inside a larger graph of its own.  grad_buffer: caller-provided flat float32 buffer of
-        (11 + C) N elements that receives d_rotate | d_xyz | d_scale | d_opacity | d_feature."""
+        (11 + C) N elements that receives d_rotate | d_xyz | d_scale | d_opacity | d_feature; cam_buffer: likewise 16
+        floats for d_extr (12) | d_intr (4)."""
         self.lib = capi.load()
         f32 = torch.float32
         own = (lambda t: t) if adopt_inputs else (lambda t: t.clone())
@@ -64,6 +66,12 @@ class GraphedRenderStep:
             self.image = torch.empty(C, self.H, self.W, device=dev, dtype=f32)
             self.g_image = torch.zeros(C, self.H, self.W, device=dev, dtype=f32)
             self._grad_ws = torch.zeros(12 * N + 16, device=dev, dtype=f32)  # kept gradient pack (self-cleaning) | d_cam
+            if cam_buffer is not None:
+                if cam_buffer.numel() != 16 or cam_buffer.dtype != f32 or not cam_buffer.is_contiguous():
+                    raise RuntimeError("gflow_b200: cam_buffer must be a contiguous float32 tensor of 16 elements")
+                self._cam = cam_buffer
+            else:
+                self._cam = self._grad_ws[12 * N:12 * N + 16]
             if grad_buffer is not None:
                 if grad_buffer.numel() != (11 + C) * N or grad_buffer.dtype != f32 or not grad_buffer.is_contiguous():
                     raise RuntimeError("gflow_b200: grad_buffer must be a contiguous float32 tensor of (11 + C) N elements")
@@ -74,7 +82,7 @@ class GraphedRenderStep:
             self.grads: Dict[str, torch.Tensor] = {
                 "rotate": d[:4 * N].view(N, 4), "xyz": d[4 * N:7 * N].view(N, 3), "scale": d[7 * N:10 * N].view(N, 3),
                 "opacity": d[10 * N:11 * N].view(N, 1), "feature": d[11 * N:(11 + C) * N].view(N, C),
-                "extr": self._grad_ws[12 * N:12 * N + 12].view(3, 4), "intr": self._grad_ws[12 * N + 12:12 * N + 16]}
+                "extr": self._cam[:12].view(3, 4), "intr": self._cam[12:16]}
             k_off = 8 * T + self.lib.gfb_render_control_k_offset(self.W, self.H)
             self._k_word = self._tbuf[k_off:k_off + 4].view(torch.int32)
             self.graph = self.graph_fwd = self.graph_bwd = None
@@ -117,7 +125,7 @@ class GraphedRenderStep:
         capi.check(self.lib.gfb_render_backward_keep(
             self.xyz.data_ptr(), self.scale.data_ptr(), self.rotate.data_ptr(), self.intr.data_ptr(), self.extr.data_ptr(),
             N, W, H, C, self.bg, self.nearest, self.extent, kp + 56 * cap, tp, cap, kp, kp + 32 * cap, self._aux.data_ptr(),
-            self._aux.data_ptr() + 4 * H * W, self.g_image.data_ptr(), gw, gw + 48 * N, dp + 16 * N, dp + 28 * N, dp,
+            self._aux.data_ptr() + 4 * H * W, self.g_image.data_ptr(), gw, self._cam.data_ptr(), dp + 16 * N, dp + 28 * N, dp,
             dp + 40 * N, dp + 44 * N, st), "graphed rasterization backward")
 
     def _enqueue_forward(self, gp, tp, kp, st) -> None:

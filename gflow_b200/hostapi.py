@@ -8,8 +8,10 @@ The copies run on two streams of their own (one per direction: PCIe is full dupl
 each) and the device buffers are double buffered, so the H2D copy of step i+1 and the D2H copy of step i-1 overlap
 the kernels of step i (round 1 ran copy -> compute -> copy serially on one
 stream and lost 47 % against the device-resident step).  With plain per-Gaussian colours the compute part of a slot
-is ONE CUDA graph (gflow_b200.graphs.GraphedRenderStep over the slot's buffers + the loss), so a step costs the host
-two copies and one graph launch; with a `colour` callback (e.g. spherical harmonics through autograd) it runs eagerly.
+is ONE CUDA graph (gflow_b200.graphs.GraphedRenderStep over the slot's buffers + the loss) and the whole step -- both
+copies, the graph launch and the events between them -- is ONE call into the library (gfb_hostpipe_submit,
+csrc/hostpipe.cu): issued from Python, those ten calls cost the host more than the kernels take.  With a `colour`
+callback (e.g. spherical harmonics through autograd) the step runs eagerly on torch streams.
 Nothing here is a CPU fallback: the work is done by the CUDA kernels behind gflow_b200.ops.
 
 Host block layouts (float32):
@@ -18,21 +20,24 @@ Host block layouts (float32):
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
-from . import ops
+from . import capi, ops
 
 
 class HostRenderStep:
     def __init__(self, N: int, W: int, H: int, feature_shape: Tuple[int, ...], g_image: torch.Tensor, bg: float = 0.0,
                  device=None, depth: int = 2, colour: Optional[Callable[[torch.Tensor, torch.Tensor], torch.Tensor]] = None,
-                 capacity: Optional[int] = None, sample_input: Optional[torch.Tensor] = None):
+                 capacity: Optional[int] = None, sample_input: Optional[torch.Tensor] = None, concurrent: bool = True):
         """feature_shape: per-Gaussian shape of the colour input, (3,) for rgb or (3, 16) for degree-3 SH coefficients
         (then `colour(feature, xyz)` maps it to (N, C<=4) colours on the device).  g_image: dL/d(image) (C,H,W) on the
         device.  depth: number of in-flight steps (2 = double buffering).  sample_input: a representative host input
-        block; needed by the graph path to size the intersection capacity (or pass `capacity`)."""
+        block; needed by the graph path to size the intersection capacity (or pass `capacity`).  concurrent (graph path):
+        every slot computes on a stream of its own, so neighbouring steps overlap; g_image must then not be modified
+        while steps are in flight (wait() first)."""
         self.N, self.W, self.H, self.bg = int(N), int(W), int(H), float(bg)
         self.dev = torch.device(device) if device is not None else g_image.device
         if self.dev.type != "cuda":
@@ -68,10 +73,31 @@ class HostRenderStep:
                 capacity = slot["step"].capacity  # the other slots reuse the first one's capacity
             self.slots.append(slot)
         self._next = 0
+        self._pipe = None
+        if self.graphed:
+            self._lib = capi.load()
+            pipe = ctypes.c_void_p()
+            with torch.cuda.device(self.dev):
+                capi.check(self._lib.gfb_hostpipe_create(len(self.slots), ctypes.byref(pipe)), "host pipe")
+            self._pipe = pipe
+            for slot in self.slots:
+                slot["exec"] = int(slot["graph"].raw_cuda_graph_exec())
+                # own compute stream per slot: the kernels of step i+1 fill the SMs the last wave of step i leaves idle
+                slot["stream"] = torch.cuda.Stream(device=self.dev) if concurrent else None
+            torch.cuda.synchronize(self.dev)
+
+    def __del__(self):
+        pipe, self._pipe = getattr(self, "_pipe", None), None
+        if pipe is not None:
+            try:
+                self._lib.gfb_hostpipe_wait(pipe)
+                self._lib.gfb_hostpipe_destroy(pipe)
+            except Exception:  # interpreter shutdown
+                pass
 
     def _capture(self, slot, capacity) -> None:
-        """The slot's compute as one CUDA graph: render step over the slot's input views, gradients straight into the
-        slot's output block, camera gradients + loss appended by two tiny captured kernels."""
+        """The slot's compute as one CUDA graph: render step over the slot's input views, all gradients (per-Gaussian
+        and camera) straight into the slot's output block, the loss appended by one captured dot product."""
         from .graphs import GraphedRenderStep
 
         N = self.N
@@ -79,13 +105,13 @@ class HostRenderStep:
         out = slot["dev_out"]
         n_grad = self.out_offs[5]
         step = GraphedRenderStep(dv[0], dv[1], dv[2], dv[3], dv[4], dv[5], dv[6], self.W, self.H, self.bg, capacity=capacity,
-                                 adopt_inputs=True, capture=False, grad_buffer=out[:n_grad])
+                                 adopt_inputs=True, capture=False, grad_buffer=out[:n_grad],
+                                 cam_buffer=out[n_grad:n_grad + 16])  # the kernels write straight into the output block
         step.g_image = self.g_image  # dL/d(image) is shared by the slots (read only)
-        cam = step._grad_ws[12 * N:12 * N + 16]
+        loss = out[n_grad + 16]      # 0-dim view of the block's last word
 
-        def tail():
-            out[n_grad:n_grad + 16].copy_(cam)
-            out[n_grad + 16:n_grad + 17].copy_((step.image * self.g_image).sum().reshape(1))
+        def tail():  # loss = sum(image * G) as one dot product, no temporary
+            torch.dot(step.image.view(-1), self.g_image.reshape(-1), out=loss)
 
         step.warm_up(tail)
         graph = torch.cuda.CUDAGraph()
@@ -119,9 +145,17 @@ class HostRenderStep:
         """Enqueue one step.  host_in / host_out must be pinned; host_out is valid after wait()."""
         if not (host_in.is_pinned() and host_out.is_pinned()):
             raise RuntimeError("gflow_b200: HostRenderStep.submit needs pinned host blocks (host_input_block / host_output_block)")
-        slot = self.slots[self._next]
+        index = self._next
+        slot = self.slots[index]
         self._next = (self._next + 1) % len(self.slots)
         compute = torch.cuda.current_stream(self.dev)
+        if self._pipe is not None:  # graph path: the whole step is one library call
+            capi.check(self._lib.gfb_hostpipe_submit(self._pipe, index, slot["dev_in"].data_ptr(), host_in.data_ptr(),
+                                                     self.h2d_bytes, slot["exec"],
+                                                     (slot["stream"] or compute).cuda_stream, host_out.data_ptr(),
+                                                     slot["dev_out"].data_ptr(), self.d2h_bytes), "host pipe submit")
+            slot["busy"] = True
+            return
         with torch.cuda.stream(self.h2d_stream):
             if slot["busy"]:
                 self.h2d_stream.wait_event(slot["done"])  # dev_in is still read by the slot's previous compute
@@ -164,6 +198,9 @@ class HostRenderStep:
 
     def wait(self) -> None:
         """Blocks until every submitted step's results have landed in their host blocks."""
+        if self._pipe is not None:
+            capi.check(self._lib.gfb_hostpipe_wait(self._pipe), "host pipe wait")
+            return
         for slot in self.slots:
             if slot["busy"]:
                 slot["d2h"].synchronize()

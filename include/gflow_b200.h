@@ -322,6 +322,24 @@ int gfb_densify_sample(const void *workspace, const float *gt_image, const float
                        float *new_scale, float *new_rotate, float *new_opacity, float *new_rgb,
                        int32_t *sampled_pixels, void *stream);
 
+/* ------------------------------------------------------------------ host pipe
+ * Stream plumbing of a render step whose inputs and results live in HOST memory (what a caller of the reference
+ * pays around msplat when its Gaussians are numpy / CPU tensors: .cuda() before, .cpu() after).  A pipe owns two copy
+ * streams and `depth` slots; gfb_hostpipe_submit enqueues, for one slot,
+ *   H2D  host_in (pinned) -> dev_in          on the pipe's upload stream,
+ *   the caller's captured CUDA graph         (cudaGraphExec_t, e.g. of gfb_render_forward_keep + gfb_render_backward_keep
+ *                                             over dev_in / dev_out) on compute_stream,
+ *   D2H  dev_out -> host_out (pinned)        on the pipe's download stream,
+ * ordered by events, so with depth >= 2 the copies of neighbouring steps overlap the kernels.  A slot may be
+ * re-submitted at once (the call orders it behind the slot's previous step); host_out is valid after
+ * gfb_hostpipe_wait.  One pipe per device; not thread safe. */
+typedef struct gfb_hostpipe gfb_hostpipe;
+int gfb_hostpipe_create(int depth, gfb_hostpipe **pipe);
+int gfb_hostpipe_submit(gfb_hostpipe *pipe, int slot, void *dev_in, const void *host_in, size_t in_bytes,
+                        void *graph_exec, void *compute_stream, void *host_out, const void *dev_out, size_t out_bytes);
+int gfb_hostpipe_wait(gfb_hostpipe *pipe);
+int gfb_hostpipe_destroy(gfb_hostpipe *pipe);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,6 +255,14 @@ enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0, cudaStreamCaptur
 static inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* s) { *s = cudaStreamCaptureStatusNone; return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+// host pipe (hostpipe.cu): streams and events are tokens, copies happen at once, a "graph" is a host callback
+typedef void (*cudaGraphExec_t)(void);
+enum { cudaStreamNonBlocking = 1, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (void*)1; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t) { g(); return cudaSuccess; }
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(KArgs...), Args... args) {

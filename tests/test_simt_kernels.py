@@ -262,3 +262,45 @@ def test_sanitized_build_finds_no_out_of_bounds_or_misaligned_access():
                          capture_output=True, text=True, env=env, cwd=os.path.dirname(here), timeout=1800)
     assert res.returncode == 0 and " passed" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
     assert "runtime error" not in res.stderr and "AddressSanitizer" not in res.stderr
+
+
+def test_host_pipe_orders_copy_compute_copy():
+    """csrc/hostpipe.cu under the shim (copies happen at once, the "graph" is a host callback): every submitted step
+    sees its own input in its slot's device block and its own result lands in the host block it named, slots are reused
+    round-robin, bad arguments are refused."""
+    import ctypes
+
+    import numpy as np
+
+    L = emu.load()
+    pipe = ctypes.c_void_p()
+    assert L.gfb_hostpipe_create(0, ctypes.byref(pipe)) != 0
+    assert L.gfb_hostpipe_create(2, ctypes.byref(pipe)) == 0
+    n = 64
+    dev_in = [np.zeros(n, np.float32) for _ in range(2)]
+    dev_out = [np.zeros(n + 1, np.float32) for _ in range(2)]
+    current = {"slot": 0}
+
+    @ctypes.CFUNCTYPE(None)
+    def graph():  # stands for the captured render step: reads the slot's input block, writes its output block
+        k = current["slot"]
+        dev_out[k][:n] = 2.0 * dev_in[k]
+        dev_out[k][n] = dev_in[k].sum()
+
+    exec_ptr = ctypes.cast(graph, ctypes.c_void_p)
+    outs = []
+    for step in range(5):
+        k = step % 2
+        current["slot"] = k
+        host_in = np.full(n, float(step + 1), np.float32)
+        host_out = np.zeros(n + 1, np.float32)
+        rc = L.gfb_hostpipe_submit(pipe, k, dev_in[k].ctypes.data, host_in.ctypes.data, 4 * n, exec_ptr, None,
+                                   host_out.ctypes.data, dev_out[k].ctypes.data, 4 * (n + 1))
+        assert rc == 0
+        outs.append(host_out)
+    assert L.gfb_hostpipe_wait(pipe) == 0
+    for step, o in enumerate(outs):
+        assert np.all(o[:n] == 2.0 * (step + 1)) and o[n] == n * (step + 1)
+    assert L.gfb_hostpipe_submit(pipe, 2, None, None, 0, exec_ptr, None, None, None, 0) != 0  # no such slot
+    assert L.gfb_hostpipe_submit(pipe, 0, None, None, 0, None, None, None, None, 0) != 0      # no graph
+    assert L.gfb_hostpipe_destroy(pipe) == 0

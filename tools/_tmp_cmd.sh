@@ -1,3 +1,6 @@
-python tools/diag_chain.py 100
-python tools/diag_host.py 2>&1 | tail -7
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -p no:cacheprovider -x 2>&1 | tail -2
+for c in 1 2 3 4; do
+python tools/bench_fit.py --native --frames 12 --iters 300 --concurrent $c 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('concurrent $c', {k:(round(v,2) if isinstance(v,float) else v) for k,v in d.items() if k in ('iters_per_sec','seconds','value','frame_iterations_per_s','concurrent_frames')} , list(d.keys())[:12])"
+done
+for c in 1 2 4; do
+python tools/bench_fit.py --native --ssim --frames 8 --iters 300 --concurrent $c 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ssim concurrent $c', d.get('seconds'))"
+done
