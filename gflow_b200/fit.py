@@ -764,6 +764,9 @@ class NativeFitLoop:
         return self._view(self.lay.out, C * self.H * self.W).reshape(C, self.H, self.W)
 
 
+_SIDE_STREAMS: Dict[tuple, list] = {}
+
+
 def fit_frames_concurrently(fitters, targets, cfg: FitConfig, streams=None, loop_cls=None):
     """Runs the native loop of several independent frames of ONE GPU side by side, each on its own CUDA stream.
 
@@ -774,7 +777,13 @@ def fit_frames_concurrently(fitters, targets, cfg: FitConfig, streams=None, loop
     histories, final state).  No densification in this mode."""
     loop_cls = loop_cls or NativeFitLoop
     if streams is None:
-        streams = [torch.cuda.Stream(device=f.attrs["xyz"].device) for f in fitters]
+        # the same streams for every group of frames: the caching allocator keeps one pool per stream, and a fresh stream
+        # per call would send every workspace allocation of every group to cudaMalloc
+        dev_ = fitters[0].attrs["xyz"].device
+        pool = _SIDE_STREAMS.setdefault((dev_.type, dev_.index), [])
+        while len(pool) < len(fitters):
+            pool.append(torch.cuda.Stream(device=dev_))
+        streams = pool[:len(fitters)]
         cur = torch.cuda.current_stream(fitters[0].attrs["xyz"].device)
         for s_ in streams:  # the fitters' tensors were produced on the current stream
             s_.wait_stream(cur)

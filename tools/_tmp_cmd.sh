@@ -1,6 +1,4 @@
-for c in 1 2 3 4; do
-python tools/bench_fit.py --native --frames 12 --iters 300 --concurrent $c 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('concurrent $c', {k:(round(v,2) if isinstance(v,float) else v) for k,v in d.items() if k in ('iters_per_sec','seconds','value','frame_iterations_per_s','concurrent_frames')} , list(d.keys())[:12])"
-done
-for c in 1 2 4; do
-python tools/bench_fit.py --native --ssim --frames 8 --iters 300 --concurrent $c 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ssim concurrent $c', d.get('seconds'))"
-done
+for rep in 1 2 3; do for c in 1 3; do
+python tools/bench_fit.py --native --frames 48 --iters 300 --concurrent $c 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('concurrent $c', round(d['value'],1), round(d['seconds'],3))"
+nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu,clocks_throttle_reasons.active --format=csv,noheader
+done; done
