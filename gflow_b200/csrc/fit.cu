@@ -444,7 +444,7 @@ struct FitMasks {
     int n_still, camera_only, freeze_rgb;
 };
 
-// two CTAs per SM (<= 128 registers, 12 bytes of spill): this kernel waits on ~30 global loads per thread
+// two CTAs per SM (112 registers, no spill): this kernel waits on ~30 global loads per thread
 __global__ void __launch_bounds__(kThreads, 2)
 fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_raw, float4* __restrict__ rot_raw,
                              float* __restrict__ op_raw, float* __restrict__ rgb_raw, const float* __restrict__ cam,
@@ -455,7 +455,6 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
                              float* __restrict__ dbg_grads) {
     __shared__ float s_cam[16];
     load_camera(s_cam, cam + 12, cam);  // written by the previous iteration's fit_finish: long complete
-    gfb_pdl_wait();                     // grad_pack comes from blend_bwd (no-op without the PDL attribute)
     const float* e = s_cam;
     const float* in = s_cam + 12;
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
@@ -464,21 +463,38 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
+    // The Gaussian's own forward quantities are recomputed BEFORE the wait on blend_bwd (programmatic dependent launch):
+    // these CTAs move into the SM slots blend_bwd's last wave leaves idle and are ready when the gradient pack is.
+    // Nothing upstream still reads the raw parameters: the blend kernels work from the packed record streams.
+    float p[3] = {0.0f, 0.0f, 0.0f}, sr[3] = {0.0f, 0.0f, 0.0f}, s[3] = {0.0f, 0.0f, 0.0f}, c_raw[3] = {0.0f, 0.0f, 0.0f}, S[6];
+    float4 qr = make_float4(0.0f, 0.0f, 0.0f, 1.0f), q = qr;
+    float o_raw = 0.0f, qn = 1.0f, u = 0.0f, v = 0.0f, xc = 0.0f, yc = 0.0f, zc = 1.0f;
+    EwaMid m;
+    bool seen = false, live = false;
+    if (i < N) {
+        p[0] = xyz[3 * i], p[1] = xyz[3 * i + 1], p[2] = xyz[3 * i + 2];
+        sr[0] = scale_raw[3 * i], sr[1] = scale_raw[3 * i + 1], sr[2] = scale_raw[3 * i + 2];
+        qr = rot_raw[i];
+        o_raw = op_raw[i];
+        c_raw[0] = rgb_raw[3 * i], c_raw[1] = rgb_raw[3 * i + 1], c_raw[2] = rgb_raw[3 * i + 2];
+        s[0] = fabsf(sr[0]), s[1] = fabsf(sr[1]), s[2] = fabsf(sr[2]);
+        q = normalize4(qr, qn);
+        seen = project_one(in, e, W, H, nearest, extent, p[0], p[1], p[2], u, v, xc, yc, zc);
+        if (seen) {
+            cov3d_fwd_one(s, q, S);
+            ewa_mid_eval(p, S, in, e, W, H, m);
+            float rf;
+            int x0, y0, x1, y1;
+            live = ewa_live(m, u, v, gx, gy, rf, x0, y0, x1, y1);
+        }
+    }
+    gfb_pdl_wait();  // grad_pack comes from blend_bwd (no-op without the PDL attribute)
     if (i < N) {
         const float4 g0 = grad_pack[3 * (size_t)i], g1 = grad_pack[3 * (size_t)i + 1], g2 = grad_pack[3 * (size_t)i + 2];
-        float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
-        float sr[3] = {scale_raw[3 * i], scale_raw[3 * i + 1], scale_raw[3 * i + 2]};
-        float4 qr = rot_raw[i];
-        float o_raw = op_raw[i];
-        float c_raw[3] = {rgb_raw[3 * i], rgb_raw[3 * i + 1], rgb_raw[3 * i + 2]};
-        const float s[3] = {fabsf(sr[0]), fabsf(sr[1]), fabsf(sr[2])};
-        float qn;
-        const float4 q = normalize4(qr, qn);
         float dp[3] = {0.0f, 0.0f, 0.0f}, ds[3] = {0.0f, 0.0f, 0.0f};
         float4 dq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         float gd = (C > 3) ? g2.y : 0.0f;  // dL/d(depth_i): the depth map's feature gradient
-        float u, v, xc, yc, zc;
-        if (project_one(in, e, W, H, nearest, extent, p[0], p[1], p[2], u, v, xc, yc, zc)) {
+        if (seen) {
             if (lambda_scale != 0.0f && u > 0.0f && u < (float)(W - 1) && v > 0.0f && v < (float)(H - 1) &&
                 (!rg.scale_sel || rg.scale_sel[i])) {
                 const float nrm = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
@@ -489,13 +505,7 @@ fit_geometry_bwd_adam_kernel(float* __restrict__ xyz, float* __restrict__ scale_
                 }
                 gd += -wgt * nrm / (zc * zc);
             }
-            float S[6];
-            cov3d_fwd_one(s, q, S);
-            EwaMid m;
-            ewa_mid_eval(p, S, in, e, W, H, m);
-            float rf;
-            int x0, y0, x1, y1;
-            if (ewa_live(m, u, v, gx, gy, rf, x0, y0, x1, y1)) {
+            if (live) {
                 float dS[6], ds2[3];
                 ewa_bwd_one(m, p, S, in, e, g0.z, g0.w, g1.x, dp, dS, acc);
                 cov3d_bwd_one(s, q, dS, ds2, dq);

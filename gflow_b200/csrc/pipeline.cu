@@ -177,7 +177,6 @@ geometry_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ sca
                     float* __restrict__ d_feature, float* __restrict__ d_cam) {
     __shared__ float s_cam[16];
     load_camera(s_cam, intr, extr);
-    gfb_pdl_wait();  // grad_pack comes from blend_bwd
     const float* e = s_cam;
     const float* in = s_cam + 12;
     const int gx = (W + GFB_TILE - 1) / GFB_TILE, gy = (H + GFB_TILE - 1) / GFB_TILE;
@@ -185,6 +184,28 @@ geometry_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ sca
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
+    // Everything that does not need the gradient pack -- the Gaussian's own forward quantities -- comes BEFORE the wait on
+    // blend_bwd: under programmatic dependent launch these CTAs take the SM slots blend_bwd's last wave leaves idle
+    // (a third of its run time) and have their recomputation done when the pack is complete.
+    float p[3] = {0.0f, 0.0f, 0.0f}, s[3] = {0.0f, 0.0f, 0.0f}, S[6];
+    float4 q = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    float u = 0.0f, v = 0.0f, xc = 0.0f, yc = 0.0f, zc = 0.0f;
+    EwaMid m;
+    bool seen = false, live = false;
+    if (i < N) {
+        p[0] = xyz[3 * i], p[1] = xyz[3 * i + 1], p[2] = xyz[3 * i + 2];
+        seen = project_one(in, e, W, H, nearest, extent, p[0], p[1], p[2], u, v, xc, yc, zc);
+        if (seen) {
+            s[0] = scale[3 * i], s[1] = scale[3 * i + 1], s[2] = scale[3 * i + 2];
+            q = rotate[i];
+            cov3d_fwd_one(s, q, S);
+            ewa_mid_eval(p, S, in, e, W, H, m);
+            float rf;
+            int x0, y0, x1, y1;
+            live = ewa_live(m, u, v, gx, gy, rf, x0, y0, x1, y1);
+        }
+    }
+    gfb_pdl_wait();  // grad_pack comes from blend_bwd
     if (i < N) {
         const float4 g0 = grad_pack[3 * (size_t)i], g1 = grad_pack[3 * (size_t)i + 1], g2 = grad_pack[3 * (size_t)i + 2];
         if (clear_pack) {  // a kept pack is handed back zeroed: the next backward accumulates into it without a memset
@@ -195,18 +216,8 @@ geometry_bwd_kernel(const float* __restrict__ xyz, const float* __restrict__ sca
         }
         float dp[3] = {0.0f, 0.0f, 0.0f}, ds[3] = {0.0f, 0.0f, 0.0f};
         float4 dq = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        const float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
-        float u, v, xc, yc, zc;
-        if (project_one(in, e, W, H, nearest, extent, p[0], p[1], p[2], u, v, xc, yc, zc)) {
-            const float s[3] = {scale[3 * i], scale[3 * i + 1], scale[3 * i + 2]};
-            const float4 q = rotate[i];
-            float S[6];
-            cov3d_fwd_one(s, q, S);
-            EwaMid m;
-            ewa_mid_eval(p, S, in, e, W, H, m);
-            float rf;
-            int x0, y0, x1, y1;
-            if (ewa_live(m, u, v, gx, gy, rf, x0, y0, x1, y1)) {
+        if (seen) {
+            if (live) {
                 float dS[6];
                 ewa_bwd_one(m, p, S, in, e, g0.z, g0.w, g1.x, dp, dS, acc);
                 cov3d_bwd_one(s, q, dS, ds, dq);
