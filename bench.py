@@ -788,7 +788,7 @@ def ncu_constants(N, W, H, profile):
         with open(tp) as fh:
             rec = json.load(fh)
         for r in rec.get("captures", []):
-            if (r["N"], r["W"], r["H"], r["profile"]) == (N, W, H, profile):
+            if (r["N"], r["W"], r["H"], r["profile"]) == (N, W, H, profile) and "path" not in r:  # operator-level capture
                 return r
     except Exception:
         pass

@@ -11,7 +11,7 @@ on the drop-in `msplat` module.
 Two execution modes with the same semantics:
   * operator path (default): the msplat operators one by one + torch autograd + torch.optim.Adam, the way
     trainer.py drives them (~150 launches and 2-3 ms of host work per iteration);
-  * native path (FitConfig.native): the whole iteration as eight kernels with no host synchronisation
+  * native path (FitConfig.native): the whole iteration as seven kernels with no host synchronisation
     (csrc/fit.cu through gfb_fit_init / gfb_fit_iterate): activations + geometry + binning, one 4-channel
     blend for rgb and the depth map, fused losses, blend backward, geometry backward with the Adam update
     in the same kernel.
