@@ -788,22 +788,24 @@ def test_graphed_render_step_equals_the_eager_step(G):
         small.check()
 
 
-def test_host_render_step_matches_the_device_step(G):
+@pytest.mark.parametrize("depth,steps", [(2, 3), (3, 8)])
+def test_host_render_step_matches_the_device_step(G, depth, steps):
     """gflow_b200.hostapi.HostRenderStep (pinned host blocks in, gradients + loss out; the compute of a slot is one
-    CUDA graph): every submitted step returns the gradients of the device-resident autograd step for ITS inputs, also
-    when consecutive steps carry different inputs through the two slots."""
+    CUDA graph on the slot's own stream, the plumbing one gfb_hostpipe_submit per step): every submitted step returns
+    the gradients of the device-resident autograd step for ITS inputs, also when consecutive steps carry different
+    inputs through the slots and every slot is reused while its neighbours are still in flight."""
     from gflow_b200 import hostapi
 
     sc = make_scene(6000, 320, 200, seed=21, bg=0.1)
     Gimg = cu(make_grad_image(3, sc.W, sc.H))
     host = None
     ins, outs, refs = [], [], []
-    for i in range(3):
+    for i in range(steps):
         xyz = sc.xyz + 0.02 * i
         tens = [xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb * (1.0 - 0.1 * i), sc.intr, sc.extr]
         if host is None:
             block = torch.cat([t.reshape(-1) for t in tens]).pin_memory()
-            host = hostapi.HostRenderStep(6000, sc.W, sc.H, (3,), Gimg, sc.bg, DEV, depth=2, sample_input=block)
+            host = hostapi.HostRenderStep(6000, sc.W, sc.H, (3,), Gimg, sc.bg, DEV, depth=depth, sample_input=block)
             assert host.graphed
         hin = host.host_input_block()
         host.pack_input(hin, tens)
