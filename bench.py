@@ -40,6 +40,7 @@ if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["ref
     os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
 
 import argparse  # noqa: E402
+import ctypes  # noqa: E402
 import importlib.util  # noqa: E402
 import json  # noqa: E402
 import statistics  # noqa: E402
@@ -102,9 +103,13 @@ def load_peaks():
 
 def algorithmic_bytes(N, K, P, T, C=3):
     """SURVEY.md 8d / BASELINE.md per-op compulsory traffic."""
+    key_bytes = (32 + max(1, (T - 1).bit_length()) + 7) // 8  # p = ceil((32 + ceil(log2 T)) / 8)
     return {
         "blend_fwd": (28 + 4 * C) * K + (4 * C + 8) * P + 8 * T,
         "blend_bwd": (28 + 4 * C) * K + (4 * C + 8) * P + 2 * (24 + 4 * C) * N,
+        "project_fwd": 24 * N, "project_bwd": 36 * N, "cov3d_fwd": 53 * N, "cov3d_bwd": 81 * N,
+        "ewa_fwd": 65 * N, "ewa_bwd": 93 * N,
+        "sort": 28 * N + 28 * K + 24 * key_bytes * K + 8 * T,  # global-radix model; a segmented design is credited the same
     }
 
 
@@ -848,6 +853,40 @@ def kernel_roofline(G, lib, params, intr, extr, Gimg, bg, N, W, H, T, P, flush_l
 
         fwd()
         ms_f, ms_b = timeit(fwd), timeit(bwd)
+
+        # SURVEY 8d unit (i): every other operator's kernels alone, same harness (C ABI calls, events, L2 flushed)
+        visb = vis.reshape(-1).to(torch.uint8).contiguous()
+        f32 = lambda *sh: torch.empty(*sh, device=dev)  # noqa: E731
+        i32 = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.int32)  # noqa: E731
+        o_uv, o_depth, o_cov, o_conic, o_rad, o_tiles = f32(N, 2), f32(N, 1), f32(N, 6), f32(N, 3), i32(N, 1), i32(N, 1)
+        g_uv, g_depth, g_cov, g_conic = torch.rand(N, 2, device=dev), torch.rand(N, 1, device=dev), torch.rand(N, 6, device=dev), torch.rand(N, 3, device=dev)
+        d_xyz, d_cam, d_scale, d_rot, d_cov = f32(N, 3), f32(16), f32(N, 3), f32(N, 4), f32(N, 6)
+        xyz_c, scale_c, rot_c, intr_c, extr_c = (t.detach().contiguous() for t in (xyz, scale, rot, intr, extr))
+        P_ = lambda t: t.data_ptr()  # noqa: E731
+        tile_ws = torch.empty(lib.gfb_sort_tile_workspace_bytes(W, H), device=dev, dtype=torch.uint8)
+        keys = torch.empty(max(K, 1), device=dev, dtype=torch.int64)
+        ids2, rng2, k_host = i32(max(K, 1)), i32(T, 2), ctypes.c_int64(0)
+        ops_alone = {
+            "project_fwd": lambda: lib.gfb_project_point_fwd(P_(xyz_c), P_(intr_c), P_(extr_c), N, W, H, 0.2, 1.3, P_(o_uv), P_(o_depth), st),
+            "project_bwd": lambda: lib.gfb_project_point_bwd(P_(xyz_c), P_(intr_c), P_(extr_c), N, W, H, 0.2, 1.3, P_(g_uv), P_(g_depth),
+                                                             P_(d_xyz), P_(d_cam), st),
+            "cov3d_fwd": lambda: lib.gfb_compute_cov3d_fwd(P_(scale_c), P_(rot_c), P_(visb), N, P_(o_cov), st),
+            "cov3d_bwd": lambda: lib.gfb_compute_cov3d_bwd(P_(scale_c), P_(rot_c), P_(visb), N, P_(g_cov), P_(d_scale), P_(d_rot), st),
+            "ewa_fwd": lambda: lib.gfb_ewa_project_fwd(P_(xyz_c), P_(cov), P_(intr_c), P_(extr_c), P_(uv), N, W, H, P_(visb), P_(o_conic),
+                                                       P_(o_rad), P_(o_tiles), st),
+            "ewa_bwd": lambda: lib.gfb_ewa_project_bwd(P_(xyz_c), P_(cov), P_(intr_c), P_(extr_c), P_(uv), N, W, H, P_(visb), P_(g_conic),
+                                                       P_(d_xyz), P_(d_cov), P_(d_cam), st),
+            "sort": lambda: lib.gfb_sort_gaussian(P_(uv), P_(depth), P_(radius), P_(tiles), N, W, H, P_(tile_ws), K, P_(keys), P_(ids2),
+                                                  P_(rng2), ctypes.addressof(k_host), st),
+        }
+        ab_all = algorithmic_bytes(N, K, P, T)
+        op_level = {}
+        for name, fn_ in ops_alone.items():
+            def checked(fn_=fn_, name=name):
+                capi.check(fn_(), name)
+            ms_ = timeit(checked)
+            op_level[name] = {"kernel_ms": ms_, "algorithmic_bytes": ab_all[name], "achieved": ab_all[name] / (ms_ * 1e-3) / 1e9,
+                              "frac": ab_all[name] / (ms_ * 1e-3) / 1e9 / peak}
     ab = algorithmic_bytes(N, K, P, T)
     ach = ab["blend_bwd"] / (ms_b * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "blend_bwd_kernel<3,false> (gfb_alpha_blending_bwd)", "achieved": ach, "peak": peak,
@@ -856,7 +895,10 @@ def kernel_roofline(G, lib, params, intr, extr, Gimg, bg, N, W, H, T, P, flush_l
             "blend_fwd": {"kernel_ms": ms_f, "algorithmic_bytes_per_launch": ab["blend_fwd"],
                           "achieved": ab["blend_fwd"] / (ms_f * 1e-3) / 1e9, "frac": ab["blend_fwd"] / (ms_f * 1e-3) / 1e9 / peak},
             "note": "working set fits the 126 MB L2; the kernel is bound by the instruction issue rate, not by HBM (DESIGN.md)",
-            "K": K}
+            "K": K,
+            "op_level": dict(op_level, what="SURVEY 8d unit (i): each operator's kernels alone through the C ABI (GB/s of "
+                                            "algorithmic bytes, frac of the HBM peak; sort = count+scan, scatter, per-tile "
+                                            "sort incl. the wait for K; blend: blend_fwd above and the headline figures)")}
     cap = ncu_constants(N, W, H, profile)
     if cap is not None:
         mhz = clocks.summary().get("sm_mhz") or clocks.max_mhz or 1965
