@@ -9,11 +9,16 @@ synthetic 60 000-Gaussian / 854x480 scene (BASELINE config 2).
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 What one line reports:
-  value            device-resident render step; BLOCKS blocks of K steps, each block bracketed by a barrier +
-                   synchronize, CUDA events around every step (L2 flushed in between), max over ranks per block,
-                   MEDIAN block reported (a 20-step mean moved by 19 % between two runs of round 1)
+  value            device-resident render step as ONE CUDA graph (gflow_b200.GraphedRenderStep: the five kernels of
+                   gfb_render_forward_keep + gfb_render_backward_keep, one cudaGraphLaunch per step); BLOCKS blocks of K
+                   steps, each block bracketed by a barrier + synchronize, CUDA events around every step (L2 flushed in
+                   between), max over ranks per block, MEDIAN block reported.  With SH colours (cfg5): the eager step
+  eager            the same step as the eager autograd call msplat.rasterization(...).backward(): same kernels, but
+                   host-bound (107 us of host work per 106 us of kernels), so it follows the box's CPU
+  graphed          = value's measurement, plus frames_in_flight: four independent graphed steps on four streams
   e2e              the same step through gflow_b200.hostapi.HostRenderStep with pinned HOST buffers: H2D of the
-                   inputs and D2H of gradients + loss inside the timed region, double buffered on a copy stream
+                   inputs and D2H of gradients + loss inside the timed region, --e2e-depth steps in flight
+  reference_gpu    probe for a real MSplat on the box (baseline/_ref, site-packages); timed in the same harness if found
   operator_chain   the step through the five operators one by one (render.py:21-64 pattern)
   gflow_iteration  SURVEY 8d unit (iii): the render_multiple call pattern (four blends over one sort) + the rgb and
                    depth backward (render.py:6-108, trainer.py:404-533)
@@ -386,6 +391,7 @@ def run_ours(args):
             gstep()
         g_ms, g_blocks, _, _ = timed_blocks(gstep, args.steps, max(1, args.blocks))
         gstep.check()
+        graph_kernels = gstep.kernels_per_step
         graphed = {"value": world * args.steps / (g_ms / 1e3), "unit": UNIT, "ms_per_step": g_ms / args.steps,
                    "blocks_ms": [round(b, 4) for b in g_blocks], "K": gstep.k(), "capacity": gstep.capacity,
                    "what": "gflow_b200.GraphedRenderStep: gfb_render_forward + gfb_render_backward captured once into a CUDA "
@@ -531,6 +537,9 @@ def run_ours(args):
     # ---- BASELINE config 3 (300-iteration per-frame Adam loop), operator path and native path, each in a
     #      process of its own (tools/bench_fit.py) so a fault there cannot touch the numbers above
     fit_loop = proxy = cpu = None
+    ref_gpu = None
+    if not use_sh:
+        ref_gpu = reference_gpu_section(params, intr, extr_p, W, H, sc.bg, Gimg, timed_blocks, args.steps, world)
     single = rank == 0 and world == 1
     if single and args.workload == "cfg2" and not args.no_fit_loop and not args.quick:
         fit_loop = fit_loop_section()
@@ -540,6 +549,19 @@ def run_ours(args):
         cpu = cpu_reference(N, W, H, args.profile, None, 1, budget_s=12.0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # `value`: the render step with inputs resident in HBM.  Where the step can be one CUDA graph (plain colours) that is
+    # the figure -- same kernels, and the GPU is the only limit; the eager autograd call of the same step is host-bound
+    # (107 us of host per 106 us of kernels) and follows the box's CPU (4 800 - 9 300 iters/s over this round's boxes),
+    # it is reported beside it as `eager`.  With an SH colour callback (cfg5) the eager step is the step.
+    eager = {"value": value, "unit": UNIT, "ms_per_step": blk_ms / args.steps, "blocks_ms": [round(b, 4) for b in blocks_ms],
+             "gpu_launches": int(launches), "ms_per_step_median": statistics.median(step_ms),
+             "api": f"msplat.rasterization (gflow_b200.ops, fused pipeline, {G.BACKEND} binding) -> C ABI, eager autograd"}
+    value_api = eager["api"]
+    if graphed is not None:
+        value, blk_ms, blocks_ms = graphed["value"], graphed["ms_per_step"] * args.steps, graphed["blocks_ms"]
+        launches = graph_kernels * args.steps
+        value_api = ("gflow_b200.GraphedRenderStep: gfb_render_forward_keep + gfb_render_backward_keep (C ABI) captured once, "
+                     "one cudaGraphLaunch per step")
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -548,7 +570,7 @@ def run_ours(args):
             "config": {"workload": workload_string(args, N, W, H),
                        "K": roof.pop("K"), "sharding": "one frame (camera + target) per rank, no in-loop collective",
                        "l2": "256 MiB written between timed steps" if not args.no_flush else "not flushed (working set < L2)",
-                       "api": f"msplat.rasterization (gflow_b200.ops, fused pipeline, {G.BACKEND} binding) -> C ABI",
+                       "api": value_api,
                        "timing": f"median of {max(1, args.blocks)} blocks of {args.steps} steps, max over ranks per block"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes, "d2h_bytes_per_step": host.d2h_bytes,
                     "steps": n_e2e, "copies_alone_ms_per_step": link_ms,
@@ -563,13 +585,14 @@ def run_ours(args):
             "clocks": clocks.summary(),
             "roofline": roof,
             "blocks_ms": [round(b, 4) for b in blocks_ms],
-            "ms_per_step_median": statistics.median(step_ms),
+            "eager": eager,
+            "ms_per_step_median": statistics.median(step_ms) if graphed is None else blk_ms / args.steps,
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / (args.steps * max(1, args.blocks)),
         }
         if cores_per_rank is not None:
             line["config"]["host_cores_per_rank"] = cores_per_rank
         for k, v in (("graphed", graphed), ("operator_chain", chain), ("gflow_iteration", iteration), ("sequence", sequence), ("cpu_baseline", cpu),
-                     ("fit_loop", fit_loop), ("gpu_proxy_baseline", proxy)):
+                     ("fit_loop", fit_loop), ("gpu_proxy_baseline", proxy), ("reference_gpu", ref_gpu)):
             if v is not None:
                 line[k] = v
         if distributed:
@@ -723,6 +746,57 @@ def fit_loop_section():
         except Exception as e:  # noqa: BLE001
             out[key] = {"error": repr(e)[:300]}
     return out
+
+
+def find_real_msplat():
+    """A real MSplat build (github.com/pointrix-project/msplat), should one be on the box: `baseline/_ref` first, then
+    site-packages -- never this repository's drop-in.  Loaded under an alias so it coexists with the drop-in `msplat`.
+    Returns (module or None, list of probed directories)."""
+    probed = [os.path.join(ROOT, "baseline", "_ref")] + [p for p in sys.path if "site-packages" in p]
+    for base in probed:
+        init = os.path.join(base, "msplat", "__init__.py")
+        try:
+            if os.path.exists(init) and "gflow_b200" not in open(init).read():
+                spec = importlib.util.spec_from_file_location("_real_msplat", init,
+                                                              submodule_search_locations=[os.path.dirname(init)])
+                mod = importlib.util.module_from_spec(spec)
+                sys.modules["_real_msplat"] = mod
+                spec.loader.exec_module(mod)
+                return mod, probed
+        except Exception:  # noqa: BLE001  (a broken install is reported as absent, with the probe list)
+            pass
+    return None, probed
+
+
+def reference_gpu_section(params, intr, extr_p, W, H, bg, Gimg, timed_blocks, steps, world):
+    """SURVEY.md 8d "Reference GPU path": the identical render step (five operators, C = 3 blend, full backward) through a
+    real MSplat on this GPU, in the same process and harness -- when one can be imported.  Otherwise says so, with what
+    was probed; the eager-PyTorch proxy (`gpu_proxy_baseline`) is then the only GPU-side comparator, and it is not MSplat."""
+    real, probed = find_real_msplat()
+    if real is None:
+        return {"available": False, "probed": probed,
+                "note": "no MSplat build on this box (not vendored by the reference, unpinned, no network): the target "
+                        "'>= 1.5x MSplat' cannot be measured here; tests/test_gpu_parity.py::test_against_real_msplat "
+                        "makes the same probe and records a golden set on first contact"}
+
+    def step():
+        for p in params:
+            p.grad = None
+        extr_p.grad = None
+        xyz, scale, rot, op, rgb = params
+        uv, depth = real.project_point(xyz, intr, extr_p, W, H)
+        vis = depth != 0
+        cov = real.compute_cov3d(scale, rot, vis)
+        conic, radius, tiles = real.ewa_project(xyz, cov, intr, extr_p, uv, W, H, vis)
+        ids, rng = real.sort_gaussian(uv, depth, W, H, radius, tiles)
+        real.alpha_blending(uv, conic, op, rgb, ids, rng, bg, W, H).backward(Gimg)
+
+    for _ in range(5):
+        step()
+    n = max(5, min(steps, 50))
+    ms, _, _, _ = timed_blocks(step, n, 3)
+    return {"available": True, "module": getattr(real, "__file__", "?"), "value": world * n / (ms / 1e3), "unit": UNIT,
+            "ms_per_step": ms / n, "what": "the operator-chain render step through the real MSplat, same inputs and harness"}
 
 
 def eager_proxy_section(args):

@@ -86,6 +86,7 @@ class GraphedRenderStep:
             k_off = 8 * T + self.lib.gfb_render_control_k_offset(self.W, self.H)
             self._k_word = self._tbuf[k_off:k_off + 4].view(torch.int32)
             self.graph = self.graph_fwd = self.graph_bwd = None
+            self.kernels_per_step = 0
             if capture:
                 self.warm_up()
                 self.graph = torch.cuda.CUDAGraph()  # forward + backward in one launch (g_image known beforehand)
@@ -105,7 +106,9 @@ class GraphedRenderStep:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):
+                n0 = self.lib.gfb_kernel_launch_count()
                 self.enqueue()
+                self.kernels_per_step = int(self.lib.gfb_kernel_launch_count() - n0)  # what one replay launches
                 if extra is not None:
                     extra()
         torch.cuda.current_stream(dev).wait_stream(side)
