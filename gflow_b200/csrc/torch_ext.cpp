@@ -263,6 +263,7 @@ struct GeomCache {
     uint32_t ver[4] = {0, 0, 0, 0};
     Tensor refs[4];
     Tensor stream_buf;
+    void* cuda_stream = nullptr;  // part of the key: a stream packed on one CUDA stream is not read from another
 } g_geom;
 std::mutex g_geom_mutex;
 
@@ -272,7 +273,7 @@ Tensor geometry_stream(const Tensor& uv_in, const Tensor& conic_in, const Tensor
                        const Tensor& feature, float* feat0, bool* packed0) {
     std::lock_guard<std::mutex> lock(g_geom_mutex);
     const Tensor* in[4] = {&uv_in, &conic_in, &op_in, &ids_in};
-    bool hit = g_geom.stream_buf.defined();
+    bool hit = g_geom.stream_buf.defined() && g_geom.cuda_stream == stream();
     for (int i = 0; i < 4 && hit; ++i)
         hit = g_geom.impl[i] == in[i]->unsafeGetTensorImpl() && g_geom.ver[i] == in[i]->_version();
     if (hit) return g_geom.stream_buf;
@@ -293,6 +294,7 @@ Tensor geometry_stream(const Tensor& uv_in, const Tensor& conic_in, const Tensor
         g_geom.refs[i] = *in[i];  // pins the key tensors so an address cannot be recycled under a stale entry
     }
     g_geom.stream_buf = buf;
+    g_geom.cuda_stream = stream();
     return buf;
 }
 

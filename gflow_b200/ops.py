@@ -310,15 +310,19 @@ class _GeomStreamCache:
         self.refs = None
         self.stream = None
 
+    @staticmethod
+    def _key(uv, conic, opacity, ids):
+        # the CUDA stream is part of the key: a stream packed on one stream must not be read from another unsynchronised
+        return (id(uv), uv._version, id(conic), conic._version, id(opacity), opacity._version, id(ids), ids._version,
+                _stream() if uv.is_cuda else 0)
+
     def get(self, uv, conic, opacity, ids):
-        key = (id(uv), uv._version, id(conic), conic._version, id(opacity), opacity._version, id(ids), ids._version)
-        if self.key == key:
+        if self.key == self._key(uv, conic, opacity, ids):
             return self.stream
         return None
 
     def put(self, uv, conic, opacity, ids, stream):
-        self.key = (id(uv), uv._version, id(conic), conic._version, id(opacity), opacity._version, id(ids),
-                    ids._version)
+        self.key = self._key(uv, conic, opacity, ids)
         self.refs = (uv, conic, opacity, ids)
         self.stream = stream
 
