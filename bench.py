@@ -62,7 +62,7 @@ WORKLOADS = {"cfg1": (1_000, 256, 256), "cfg2": (60_000, 854, 480), "cfg5": (200
 BLOCKS = 10
 SEQ_FRAMES, SEQ_ITERS = 48, 300
 FRAMES_IN_FLIGHT = 4  # graphed.frames_in_flight: independent frames of one GPU side by side
-SEQ_RUNS = 3
+SEQ_RUNS = 5
 SEQ_CONCURRENT = 3  # independent frames a rank fits side by side (one stream each): 48 / N frames per rank divide evenly
 
 
