@@ -81,7 +81,7 @@ def parse_args():
     ap.add_argument("--no-sequence", action="store_true", help="skip the config-4 frame-sharded sequence section")
     ap.add_argument("--no-proxy", action="store_true", help="skip the eager-PyTorch-on-CUDA proxy baseline")
     ap.add_argument("--quick", action="store_true", help="value / e2e / roofline only")
-    ap.add_argument("--e2e-depth", type=int, default=4, help="steps in flight in the e2e leg (HostRenderStep depth)")
+    ap.add_argument("--e2e-depth", type=int, default=6, help="steps in flight in the e2e leg (HostRenderStep depth)")
     return ap.parse_args()
 
 
