@@ -428,7 +428,27 @@ def run_ours(args):
             "frames": FRAMES_IN_FLIGHT, "value": world * n_steps / (c_ms / 1e3), "unit": UNIT, "ms_per_step": c_ms / n_steps,
             "what": f"{FRAMES_IN_FLIGHT} independent graphed steps (own buffers) replayed round-robin on {FRAMES_IN_FLIGHT} "
                     "streams: aggregate steps/s of one GPU when frames do not depend on each other"}
-        del gstep, others, gsteps
+        del others, gsteps
+        # a batch of cameras over one set of Gaussians (BASELINE config 5's "8-frame batch"): gflow_b200.BatchedRenderStep,
+        # frames side by side on streams, joined per batch, per-frame gradients summed by one kernel
+        batch = {}
+        for n_f in (4, 8):
+            cams = [make_camera(W, H, torch.Generator().manual_seed(2000 + 17 * rank + f)) for f in range(n_f)]
+            bstep = G.BatchedRenderStep(*[p.detach() for p in params], torch.stack([c[0] for c in cams]).to(dev),
+                                        torch.stack([c[1] for c in cams]).to(dev), W, H, sc.bg)
+            for g_ in bstep.g_images:
+                g_.copy_(Gimg)
+            for _ in range(3):
+                bstep()
+            n_b = max(3, args.steps // n_f)
+            b_ms, _, _, _ = timed_blocks(bstep, n_b, max(1, min(args.blocks, 5)))
+            bstep.check()
+            batch[f"frames_{n_f}"] = {"value": world * n_b * n_f / (b_ms / 1e3), "unit": UNIT, "ms_per_batch": b_ms / n_b}
+            del bstep
+        batch["what"] = ("gflow_b200.BatchedRenderStep: F cameras over one set of Gaussians, forward + backward side by side on F "
+                         "streams, joined per batch, parameter gradients summed over the views; frames/s")
+        graphed["batch_of_frames"] = batch
+        del gstep
 
     # ---- e2e: the same step with pinned HOST buffers (gflow_b200.hostapi.HostRenderStep): H2D of the step's inputs
     #      and D2H of loss + gradients inside the timed region, copies double buffered against the kernels

@@ -20,7 +20,7 @@ from .ops import (  # noqa: F401
     sort_gaussian,
 )
 
-from .graphs import GraphedRenderStep  # noqa: F401,E402  (forward + backward as one CUDA graph)
+from .graphs import BatchedRenderStep, GraphedRenderStep  # noqa: F401,E402  (forward + backward as one CUDA graph; a batch of cameras side by side)
 
 __version__ = "1.1"
 DROPIN_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "dropin")

@@ -788,6 +788,42 @@ def test_graphed_render_step_equals_the_eager_step(G):
         small.check()
 
 
+def test_batched_render_step_equals_the_frames_one_by_one(G):
+    """gflow_b200.BatchedRenderStep: F cameras over one set of Gaussians replayed side by side on F streams give, per
+    camera, the image and camera gradients of the eager step for that camera, and as parameter gradients the sum over
+    the cameras (the gradient of a loss summed over the views) -- also on a second call after an in-place update."""
+    from gflow_b200.synthetic import make_camera
+
+    sc = make_scene(7000, 320, 208, seed=41, bg=0.2)
+    F = 3
+    cams = [(sc.intr, sc.extr)] + [make_camera(sc.W, sc.H, torch.Generator().manual_seed(50 + f)) for f in range(F - 1)]
+    intrs = torch.stack([c[0] for c in cams])
+    extrs = torch.stack([c[1] for c in cams])
+    Gs = [cu(make_grad_image(3, sc.W, sc.H, seed=60 + f)) for f in range(F)]
+    step = G.BatchedRenderStep(*cu(sc.xyz, sc.scale, sc.rotate, sc.opacity, sc.rgb), cu(intrs), cu(extrs), sc.W, sc.H, sc.bg)
+    for f in range(F):
+        step.g_images[f].copy_(Gs[f])
+    for rnd in range(2):
+        if rnd == 1:  # the caller's optimiser moves the shared parameters in place
+            step.xyz.add_(0.01)
+            step.feature.mul_(0.9)
+        step()
+        step.check()
+        ps = [p.detach().clone().requires_grad_(True) for p in (step.xyz, step.scale, step.rotate, step.opacity.reshape(-1, 1), step.feature)]
+        total = None
+        for f in range(F):
+            ex = cu(extrs[f]).requires_grad_(True)
+            img = G.rasterization(*ps, cu(intrs[f]), ex, sc.W, sc.H, sc.bg)
+            assert_close(step.images[f], img.detach(), 1e-6, f"batched image {f}")
+            loss = (img * Gs[f]).sum()
+            total = loss if total is None else total + loss
+            (g_ex,) = torch.autograd.grad(loss, ex, retain_graph=True)
+            assert_close(step.cam_grads[f]["extr"], g_ex, 1e-3, f"batched d_extr {f}")
+        total.backward()
+        for name, p in zip(["xyz", "scale", "rotate", "opacity", "feature"], ps):
+            assert_close(step.grads[name].reshape(p.grad.shape), p.grad, 1e-3, "batched grad " + name)
+
+
 @pytest.mark.parametrize("depth,steps", [(2, 3), (3, 8)])
 def test_host_render_step_matches_the_device_step(G, depth, steps):
     """gflow_b200.hostapi.HostRenderStep (pinned host blocks in, gradients + loss out; the compute of a slot is one
